@@ -1,0 +1,279 @@
+// oracle/stereo_oracle.cpp — TEST INFRASTRUCTURE ONLY (never linked into / called by the product path).
+//
+// Line-by-line CPU restatement of the reference's own Rust loops on the stereo front-end path:
+//   match_features        /root/reference/src/tracking/frame/stereo.rs:80-161
+//   descriptor_distance   /root/reference/src/tracking/frame/stereo.rs:166-175
+//   triangulate           /root/reference/src/tracking/frame/stereo.rs:178-216
+//   FeatureGrid           /root/reference/src/tracking/tracking_frame.rs:52-128
+//   local-map search      /root/reference/src/tracking/tracker.rs:863-923
+//   motion-model search   /root/reference/src/tracking/tracker.rs:1093-1158
+//   ref-KF BFMatcher      /root/reference/src/tracking/tracker.rs:1001-1010 (cv::BFMatcher(NORM_HAMMING, crossCheck))
+//
+// PARITY UNPINNED for this file: the reference cannot be built here (no Rust toolchain) and holds no test
+// for these functions; the only related known-answer vectors are the popcount twins at
+// vocabulary/mod.rs:430-441 and loop_closing/corrector.rs:626-633 (checked in tests/test_oracle_kat.py).
+// The BFMatcher restatement IS pinned against cv2.BFMatcher in tests.
+//
+// Rust cast semantics are coded explicitly: float->int `as` saturates (NaN -> 0), int->int `as` wraps.
+// Build with -ffp-contract=off so no f64/f32 expression is fused.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+extern "C" {
+
+struct OrcKeyPoint {
+  float x, y, size, angle, response;
+  int octave, class_id;
+};
+struct OrcDMatch {
+  int query_idx, train_idx, img_idx;
+  float distance;
+};
+struct OrcCamera {
+  double fx, fy, cx, cy, baseline;
+};
+
+// stereo.rs:166-175 — byte-wise popcount of XOR over min(cols) bytes.
+uint32_t orc_descriptor_distance(const uint8_t* a, int cols_a, const uint8_t* b, int cols_b) {
+  uint32_t d = 0;
+  int cols = cols_a < cols_b ? cols_a : cols_b;
+  for (int j = 0; j < cols; ++j) d += (uint32_t)__builtin_popcount((unsigned)(a[j] ^ b[j]));
+  return d;
+}
+
+// stereo.rs:80-161. Returns number of matches (ascending left index).
+int orc_match_features(const OrcKeyPoint* kl, const uint8_t* dl, int nl, const OrcKeyPoint* kr, const uint8_t* dr,
+                       int nr, const OrcCamera* cam, OrcDMatch* out) {
+  const double MIN_DEPTH = 0.1, MAX_DEPTH = 40.0;
+  const float VERTICAL_MARGIN = 2.0f;
+  const uint32_t TH_HIGH = 100;
+  float max_disparity = (float)(cam->fx * cam->baseline / MIN_DEPTH);
+  float min_disparity = (float)(cam->fx * cam->baseline / MAX_DEPTH);
+  int nm = 0;
+  for (int li = 0; li < nl; ++li) {
+    float ul = kl[li].x, vl = kl[li].y;
+    float min_u = std::fmax(ul - max_disparity, 0.0f);
+    float max_u = std::fmin(ul - min_disparity, ((float)nr * ul) / (float)nl);
+    uint32_t best = TH_HIGH, second = TH_HIGH;
+    int best_idx = -1;
+    for (int ri = 0; ri < nr; ++ri) {
+      float ur = kr[ri].x, vr = kr[ri].y;
+      if (std::fabs(vl - vr) > VERTICAL_MARGIN) continue;
+      if (ur < min_u || ur > max_u) continue;
+      if (ul <= ur) continue;
+      uint32_t d = orc_descriptor_distance(dl + (size_t)li * 32, 32, dr + (size_t)ri * 32, 32);
+      if (d < best) {
+        second = best;
+        best = d;
+        best_idx = ri;
+      } else if (d < second) {
+        second = d;
+      }
+    }
+    if (best_idx >= 0) {
+      if ((float)best < 0.9f * (float)second || second == TH_HIGH) {
+        out[nm].query_idx = li;
+        out[nm].train_idx = best_idx;
+        out[nm].img_idx = 0;
+        out[nm].distance = (float)best;
+        ++nm;
+      }
+    }
+  }
+  return nm;
+}
+
+// stereo.rs:186-216. points: nl x 3 f64; valid: nl bytes (Option tag).
+void orc_triangulate(const OrcKeyPoint* kl, int nl, const OrcKeyPoint* kr, int nr, const OrcDMatch* m, int nm,
+                     const OrcCamera* cam, double* points, uint8_t* valid) {
+  memset(valid, 0, (size_t)nl);
+  for (int i = 0; i < nl * 3; ++i) points[i] = 0.0;
+  for (int i = 0; i < nm; ++i) {
+    int q = m[i].query_idx, t = m[i].train_idx;
+    if (q < 0 || q >= nl || t < 0 || t >= nr) continue;
+    double lx = (double)kl[q].x, ly = (double)kl[q].y, rx = (double)kr[t].x;
+    double disparity = lx - rx;
+    if (std::fabs(disparity) < 0.5) continue;
+    double z = cam->fx * cam->baseline / disparity;
+    double x = (lx - cam->cx) * z / cam->fx;
+    double y = (ly - cam->cy) * z / cam->fy;
+    points[3 * q + 0] = x;
+    points[3 * q + 1] = y;
+    points[3 * q + 2] = z;
+    valid[q] = 1;
+  }
+}
+
+// ---- Rust `as` casts --------------------------------------------------------------------------
+static inline uint64_t f64_as_usize(double v) {  // saturating, NaN -> 0
+  if (!(v > 0.0)) return 0;
+  if (v >= 18446744073709551616.0) return std::numeric_limits<uint64_t>::max();
+  return (uint64_t)v;
+}
+static inline int32_t f64_as_i32(double v) {  // saturating, NaN -> 0
+  if (v != v) return 0;
+  if (v <= -2147483648.0) return std::numeric_limits<int32_t>::min();
+  if (v >= 2147483647.0) return std::numeric_limits<int32_t>::max();
+  return (int32_t)v;
+}
+
+enum { GRID_COLS = 64, GRID_ROWS = 48 };
+
+// tracking_frame.rs:52-89. cell_start has GRID_COLS*GRID_ROWS+1 entries (CSR); cell_items has n entries:
+// row-major cells, ascending keypoint index inside each cell (push order).
+void orc_grid_build(const OrcKeyPoint* kp, int n, double img_w, double img_h, int* cell_start, int* cell_items) {
+  double inv_w = (double)GRID_COLS / (img_w - 0.0);
+  double inv_h = (double)GRID_ROWS / (img_h - 0.0);
+  const int nc = GRID_COLS * GRID_ROWS;
+  std::vector<int> cell_of(n);
+  std::vector<int> count(nc + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    double x = (double)kp[i].x, y = (double)kp[i].y;
+    uint64_t cx = f64_as_usize((x - 0.0) * inv_w);
+    uint64_t cy = f64_as_usize((y - 0.0) * inv_h);
+    if (cx > GRID_COLS - 1) cx = GRID_COLS - 1;
+    if (cy > GRID_ROWS - 1) cy = GRID_ROWS - 1;
+    cell_of[i] = (int)(cy * GRID_COLS + cx);
+    count[cell_of[i] + 1]++;
+  }
+  for (int c = 0; c < nc; ++c) count[c + 1] += count[c];
+  memcpy(cell_start, count.data(), sizeof(int) * (nc + 1));
+  std::vector<int> fill(count.begin(), count.end() - 1);
+  for (int i = 0; i < n; ++i) cell_items[fill[cell_of[i]]++] = i;
+}
+
+// tracking_frame.rs:104-128 — returns the cell rectangle (inclusive); empty iff x0>x1 or y0>y1.
+void orc_grid_query_rect(double x, double y, double r, double img_w, double img_h, int* x0, int* x1, int* y0,
+                         int* y1) {
+  double inv_w = (double)GRID_COLS / (img_w - 0.0);
+  double inv_h = (double)GRID_ROWS / (img_h - 0.0);
+  int32_t min_cx = f64_as_i32(std::floor((x - 0.0 - r) * inv_w));
+  int32_t max_cx = f64_as_i32(std::ceil((x - 0.0 + r) * inv_w));
+  int32_t min_cy = f64_as_i32(std::floor((y - 0.0 - r) * inv_h));
+  int32_t max_cy = f64_as_i32(std::ceil((y - 0.0 + r) * inv_h));
+  uint64_t ux0 = (uint64_t)(int64_t)(min_cx > 0 ? min_cx : 0);
+  uint64_t ux1 = (uint64_t)(int64_t)max_cx;  // i32 -> usize wraps (sign extension)
+  if (ux1 > GRID_COLS - 1) ux1 = GRID_COLS - 1;
+  uint64_t uy0 = (uint64_t)(int64_t)(min_cy > 0 ? min_cy : 0);
+  uint64_t uy1 = (uint64_t)(int64_t)max_cy;
+  if (uy1 > GRID_ROWS - 1) uy1 = GRID_ROWS - 1;
+  // min_c* can exceed the grid (query right of / below the image): keep as-is, the range is then empty
+  *x0 = ux0 > 1000000 ? 1000000 : (int)ux0;
+  *x1 = (int)ux1;
+  *y0 = uy0 > 1000000 ? 1000000 : (int)uy0;
+  *y1 = (int)uy1;
+}
+
+// get_features_in_area: writes candidates in scan order; returns count.
+int orc_grid_query(const int* cell_start, const int* cell_items, double x, double y, double r, double img_w,
+                   double img_h, int* out) {
+  int x0, x1, y0, y1, n = 0;
+  orc_grid_query_rect(x, y, r, img_w, img_h, &x0, &x1, &y0, &y1);
+  for (int cy = y0; cy <= y1; ++cy)
+    for (int cx = x0; cx <= x1; ++cx) {
+      int c = cy * GRID_COLS + cx;
+      for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) out[n++] = cell_items[k];
+    }
+  return n;
+}
+
+// Projection searches. uv: M x 2 f64 (already projected by the host, z > 0 only).
+// mode 0 = local-map search (tracker.rs:863-923): accept best <= th_high, ratio test when > 1 candidate.
+// mode 1 = motion-model search (tracker.rs:1093-1158): bounds 0<=u<2cx, 0<=v<2cy; d < best && d < th_high.
+// out_idx[m] = keypoint index or -1; out_dist[m] = best distance (undefined when -1).
+void orc_search_by_projection(const OrcKeyPoint* kp, const uint8_t* desc, int n, double img_w, double img_h,
+                              const double* uv, const uint8_t* mp_desc, int M, double radius, uint32_t th_high,
+                              float nn_ratio, int mode, double bound_w, double bound_h, int* out_idx,
+                              int* out_dist) {
+  const int nc = GRID_COLS * GRID_ROWS;
+  std::vector<int> cs(nc + 1), items(n > 0 ? n : 1), cand(n > 0 ? n : 1);
+  orc_grid_build(kp, n, img_w, img_h, cs.data(), items.data());
+  for (int m = 0; m < M; ++m) {
+    out_idx[m] = -1;
+    out_dist[m] = -1;
+    double u = uv[2 * m], v = uv[2 * m + 1];
+    if (mode == 1) {
+      if (u < 0.0 || u >= bound_w || v < 0.0 || v >= bound_h) continue;
+    }
+    int nc_ = orc_grid_query(cs.data(), items.data(), u, v, radius, img_w, img_h, cand.data());
+    if (mode == 0) {
+      if (nc_ == 0) continue;
+      uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+      int best_idx = -1;
+      for (int k = 0; k < nc_; ++k) {
+        uint32_t d = orc_descriptor_distance(mp_desc + (size_t)m * 32, 32, desc + (size_t)cand[k] * 32, 32);
+        if (d < best) {
+          second = best;
+          best = d;
+          best_idx = cand[k];
+        } else if (d < second) {
+          second = d;
+        }
+      }
+      if (best > th_high) continue;
+      if (nc_ > 1) {
+        if ((float)best > nn_ratio * (float)second) continue;
+      }
+      out_idx[m] = best_idx;
+      out_dist[m] = (int)best;
+    } else {
+      uint32_t best = 0xFFFFFFFFu;
+      int best_idx = -1;
+      for (int k = 0; k < nc_; ++k) {
+        uint32_t d = orc_descriptor_distance(mp_desc + (size_t)m * 32, 32, desc + (size_t)cand[k] * 32, 32);
+        if (d < best && d < th_high) {
+          best = d;
+          best_idx = cand[k];
+        }
+      }
+      if (best_idx >= 0) {
+        out_idx[m] = best_idx;
+        out_dist[m] = (int)best;
+      }
+    }
+  }
+}
+
+// cv::BFMatcher(NORM_HAMMING, crossCheck=true).match(query, train) as used at tracker.rs:1001-1010
+// (query = keyframe descriptors, train = frame descriptors). OpenCV's batchDistance cross-check
+// (4.x, pinned against cv2 4.13.0 in tests): sidx[q] = nearest train row of q (first minimum),
+// tidx[t] = nearest query row of t (first minimum); the pair (q,t) is kept iff tidx[t]==q and sidx[q]==t.
+// Returns matches in ascending query index; distance is the integer Hamming distance as float.
+int orc_bf_match_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt, OrcDMatch* out) {
+  std::vector<int> sidx(nq, -1), sd(nq, 0x7FFFFFFF), tidx(nt, -1);
+  for (int i = 0; i < nq; ++i)
+    for (int j = 0; j < nt; ++j) {
+      int d = (int)orc_descriptor_distance(q + (size_t)i * 32, 32, t + (size_t)j * 32, 32);
+      if (d < sd[i]) {
+        sd[i] = d;
+        sidx[i] = j;
+      }
+    }
+  for (int j = 0; j < nt; ++j) {
+    int bd = 0x7FFFFFFF;
+    for (int i = 0; i < nq; ++i) {
+      int d = (int)orc_descriptor_distance(t + (size_t)j * 32, 32, q + (size_t)i * 32, 32);
+      if (d < bd) {
+        bd = d;
+        tidx[j] = i;
+      }
+    }
+  }
+  int n = 0;
+  for (int i = 0; i < nq; ++i) {
+    int j = sidx[i];
+    if (j >= 0 && tidx[j] == i) {
+      out[n].query_idx = i;
+      out[n].train_idx = j;
+      out[n].img_idx = 0;
+      out[n].distance = (float)sd[i];
+      ++n;
+    }
+  }
+  return n;
+}
+
+}  // extern "C"
