@@ -1,0 +1,218 @@
+/*
+ * vslam_b200.h — C ABI of the B200-native stereo ORB front end (libvslam_b200.so).
+ *
+ * Drop-in boundary for ONE path of jurmy24/orb-slam3-rust (crate `rust-vslam`): the per-frame stereo front end.
+ * Every entry point below replaces a piece of the reference's Rust API; the citations are file:line under the
+ * reference repository root.  A Rust `StereoProcessor` with the reference's exact signature binds these through
+ * `extern "C"` (see INTEGRATION.md and orb-slam3-rust_b200/rust/).
+ *
+ *   vslam_create / vslam_destroy        <- StereoProcessor::new              src/tracking/frame/stereo.rs:37-50
+ *   vslam_process                       <- StereoProcessor::process          src/tracking/frame/stereo.rs:52-66
+ *   vslam_process_batch[_device]        <- the caller loop around process()  src/main.rs:66-85 (offline batch form)
+ *   vslam_detect_and_compute            <- StereoProcessor::detect_features  src/tracking/frame/stereo.rs:68-78
+ *   vslam_match_features                <- StereoProcessor::match_features   src/tracking/frame/stereo.rs:80-161
+ *   vslam_triangulate                   <- triangulate                       src/tracking/frame/stereo.rs:186-216
+ *   vslam_descriptor_distance           <- descriptor_distance               src/tracking/frame/stereo.rs:166-175
+ *   vslam_grid_build / vslam_grid_query <- FeatureGrid::{new,get_features_in_area}  src/tracking/tracking_frame.rs:52-128
+ *   vslam_search_by_projection          <- the two inline searches in Tracker       src/tracking/tracker.rs:863-923, 1093-1158
+ *   vslam_bf_match_crosscheck           <- BFMatcher(NORM_HAMMING,true).train_match src/tracking/tracker.rs:1001-1010
+ *
+ * All pixel/descriptor arithmetic runs in hand-written CUDA kernels for sm_100a.  There is NO CPU fallback:
+ * every call fails with VSLAM_ERR_CUDA when no usable device is present.
+ *
+ * Threading: a handle is single-caller (the reference's `process(&mut self)`); use one handle per host thread /
+ * per GPU.  All outputs are plain host memory owned by the caller (no device affinity), so they can be moved into
+ * `StereoFrame` / `KeyFrame` and read from other threads exactly like the reference's values.
+ *
+ * Results are bit-identical to the reference's CPU path (cv::ORB as configured at stereo.rs:38-48 + the Rust loops):
+ * keypoint order, coordinates, octaves, angles, responses, descriptors, match pairs, f64 points.
+ */
+#ifndef VSLAM_B200_H_
+#define VSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSLAM_ABI_VERSION 1
+
+/* status codes (0 = ok). vslam_last_error() holds the message of the last failing call on the handle. */
+enum {
+  VSLAM_OK = 0,
+  VSLAM_ERR_INVALID_ARGUMENT = 1,
+  VSLAM_ERR_CUDA = 2,              /* no device / driver / kernel failure: the path fails loudly, never falls back */
+  VSLAM_ERR_CAPACITY = 3,          /* a caller-provided output buffer is too small */
+  VSLAM_ERR_KEYPOINT_OVERFLOW = 4, /* more keypoints than cfg.keypoint_capacity (response ties at the cut) */
+  VSLAM_ERR_OUT_OF_MEMORY = 5
+};
+
+/* Thresholds of the reference (stereo.rs:10-12). */
+#define VSLAM_TH_HIGH 100u
+#define VSLAM_TH_LOW 50u
+#define VSLAM_NN_RATIO 0.75f
+
+/* cv::KeyPoint memory layout (28 bytes) — what `Vector<KeyPoint>` holds in FeatureSet (stereo.rs:16-19). */
+typedef struct vslam_keypoint {
+  float x, y;     /* pt, level coordinate * level scale (f32) */
+  float size;     /* 31 * level scale */
+  float angle;    /* degrees, cv::fastAtan2 */
+  float response; /* Harris response */
+  int32_t octave; /* pyramid level */
+  int32_t class_id; /* -1 */
+} vslam_keypoint;
+
+/* cv::DMatch memory layout (16 bytes) — `Vector<DMatch>` matches_lr (stereo.rs:25). */
+typedef struct vslam_dmatch {
+  int32_t query_idx; /* left keypoint index */
+  int32_t train_idx; /* right keypoint index */
+  int32_t img_idx;   /* 0 */
+  float distance;    /* best Hamming distance */
+} vslam_dmatch;
+
+/* CameraModel (src/tracking/frame/camera.rs:3-10). */
+typedef struct vslam_camera {
+  double fx, fy, cx, cy, baseline;
+} vslam_camera;
+
+typedef struct vslam_config {
+  int32_t abi_version;  /* VSLAM_ABI_VERSION */
+  int32_t width, height; /* image size in pixels (8UC1) */
+  int32_t n_features;   /* StereoProcessor::new(camera, n_features); the reference passes 1200 (main.rs:53) */
+  int32_t n_levels;     /* 0 -> 8   (stereo.rs:41) */
+  float scale_factor;   /* 0 -> 1.2f (stereo.rs:40) */
+  int32_t edge_threshold; /* 0 -> 31 (stereo.rs:42) */
+  int32_t fast_threshold; /* 0 -> 20 (stereo.rs:47) */
+  vslam_camera camera;
+  int32_t device;       /* CUDA device ordinal */
+  int32_t max_batch;    /* stereo frames resident per pipeline stage; 0 -> 64 */
+  int32_t keypoint_capacity; /* per image; 0 -> n_features + max(n_features/8, 64) */
+  int32_t reserved[8];
+} vslam_config;
+
+/* Caller-owned, capacity-checked result of one stereo frame == StereoFrame (stereo.rs:21-29). */
+typedef struct vslam_frame_out {
+  int32_t capacity;          /* elements available in each array below */
+  vslam_keypoint* kp_left;   /* [capacity] */
+  vslam_keypoint* kp_right;  /* [capacity] */
+  uint8_t* desc_left;        /* [capacity][32] */
+  uint8_t* desc_right;       /* [capacity][32] */
+  vslam_dmatch* matches;     /* [capacity], ascending query_idx */
+  double* points_cam;        /* [capacity][3]; valid where points_valid[i] != 0 (Option<Vector3<f64>>) */
+  uint8_t* points_valid;     /* [capacity] */
+  int32_t n_left, n_right, n_matches; /* written by the call */
+  int32_t status;            /* per-frame status (VSLAM_OK / VSLAM_ERR_*) */
+  uint64_t timestamp_ns;     /* copied through */
+} vslam_frame_out;
+
+typedef struct vslam_handle_s* vslam_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int vslam_create(const vslam_config* cfg, vslam_handle* out);
+void vslam_destroy(vslam_handle h);
+/* Message of the last error on this handle (or of the last failed vslam_create when h == NULL). */
+const char* vslam_last_error(vslam_handle h);
+/* Per-image keypoint capacity the handle was created with (size caller buffers with this). */
+int vslam_keypoint_capacity(vslam_handle h);
+
+/* ---- StereoProcessor::process ------------------------------------------------------------------------------ */
+/* One stereo pair from HOST memory (borrowed &Mat: 8UC1, row stride in bytes). */
+int vslam_process(vslam_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
+                  uint64_t timestamp_ns, vslam_frame_out* out);
+
+/* n independent stereo pairs from HOST memory; frames are pipelined (H2D / kernels / D2H overlap) in chunks of
+ * cfg.max_batch.  left[i]/right[i] point to 8UC1 images with the given row stride.  Pinned host memory gives the
+ * best transfer rate; pageable memory is staged. */
+int vslam_process_batch(vslam_handle h, int n, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
+                        const uint64_t* timestamps_ns, vslam_frame_out* outs);
+
+/* Same, with the images already resident in device memory (HBM) of cfg.device: left_dev/right_dev are DEVICE
+ * pointers to n images each, `image_stride` bytes apart, rows `row_stride` bytes apart (row_stride % 16 == 0 and
+ * 16-byte aligned bases).  Results still land in host memory.  If outs == NULL the results stay on the device
+ * (throughput measurement of the kernels alone) and only per-frame counts are validated. */
+int vslam_process_batch_device(vslam_handle h, int n, const uint8_t* left_dev, const uint8_t* right_dev,
+                               size_t image_stride, size_t row_stride, const uint64_t* timestamps_ns,
+                               vslam_frame_out* outs);
+
+/* ---- the pieces of process(), individually --------------------------------------------------------------- */
+/* detect_features: ORB keypoints + descriptors of one image.  kps[capacity], desc[capacity][32]. */
+int vslam_detect_and_compute(vslam_handle h, const uint8_t* image, size_t stride, vslam_keypoint* kps, uint8_t* desc,
+                             int capacity, int* n_out);
+
+/* match_features on caller-provided features.  matches[n_left]. */
+int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const uint8_t* desc_left, int n_left,
+                         const vslam_keypoint* kp_right, const uint8_t* desc_right, int n_right, vslam_dmatch* matches,
+                         int* n_matches);
+
+/* triangulate on caller-provided matches.  points[n_left][3], valid[n_left]. */
+int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left, const vslam_keypoint* kp_right,
+                      int n_right, const vslam_dmatch* matches, int n_matches, double* points, uint8_t* valid);
+
+/* descriptor_distance for `n` pairs of 32-byte descriptors: out[i] = popcount(a[i] ^ b[i]). */
+int vslam_descriptor_distance(vslam_handle h, const uint8_t* a, const uint8_t* b, int n, uint32_t* out);
+
+/* ---- tracking-side searches ---------------------------------------------------------------------------------- */
+#define VSLAM_GRID_COLS 64
+#define VSLAM_GRID_ROWS 48
+
+/* FeatureGrid::new: CSR form of the 64x48 grid. cell_start[64*48+1], cell_items[n] (row-major cells, ascending
+ * keypoint index inside a cell).  img_w/img_h: the reference hard-codes 752x480 (tracking_frame.rs:194-197). */
+int vslam_grid_build(vslam_handle h, const vslam_keypoint* kps, int n, double img_w, double img_h, int32_t* cell_start,
+                     int32_t* cell_items);
+
+/* FeatureGrid::get_features_in_area for nq queries (x,y,r as f64 triples).  Results are concatenated in query
+ * order: out_start[nq+1] (CSR), out_items[out_capacity].  Bug-compatible with the reference's casts. */
+int vslam_grid_query(vslam_handle h, const vslam_keypoint* kps, int n, double img_w, double img_h, const double* xyr,
+                     int nq, int32_t* out_start, int32_t* out_items, int out_capacity);
+
+enum {
+  VSLAM_SEARCH_LOCAL_MAP = 0,   /* tracker.rs:863-923: best<=th_high, ratio test when >1 candidate */
+  VSLAM_SEARCH_MOTION_MODEL = 1 /* tracker.rs:1093-1158: 0<=u<bound_w, 0<=v<bound_h, d<th_high, no ratio */
+};
+
+typedef struct vslam_search_params {
+  int32_t mode;       /* VSLAM_SEARCH_* */
+  double radius;      /* 15.0 */
+  uint32_t th_high;   /* 100 */
+  float nn_ratio;     /* 0.75 */
+  double img_w, img_h;     /* grid extent: 752, 480 */
+  double bound_w, bound_h; /* motion-model bounds: 2*cx, 2*cy */
+} vslam_search_params;
+
+/* Projection search of M map points against one frame.  uv[M][2]: host-projected pixel coordinates (the nalgebra
+ * projection stays in the caller); mp_desc[M][32].  out_idx[M] = matched keypoint index or -1,
+ * out_dist[M] = best distance or -1. */
+int vslam_search_by_projection(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, const double* uv,
+                               const uint8_t* mp_desc, int M, const vslam_search_params* params, int32_t* out_idx,
+                               int32_t* out_dist);
+
+/* BFMatcher(NORM_HAMMING, crossCheck=true).train_match(query, train): matches[n_query], ascending query index. */
+int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query, const uint8_t* train, int n_train,
+                              vslam_dmatch* matches, int* n_matches);
+
+/* ---- introspection for parity tests and profiling ---------------------------------------------------------- */
+enum {
+  VSLAM_STAGE_PYRAMID = 0,  /* u8 level image */
+  VSLAM_STAGE_BLURRED = 1   /* u8 blurred level image */
+};
+/* Geometry of pyramid level `level`: width, height, scale, per-level feature quota. */
+int vslam_level_info(vslam_handle h, int level, int* w, int* h_out, float* scale, int* n_features);
+/* Copies a level image of image slot `image` (0 = left, 1 = right of the LAST processed frame / last frame of the
+ * last batch chunk) into dst (tightly packed w*h bytes). */
+int vslam_debug_level_image(vslam_handle h, int stage, int image, int level, uint8_t* dst, size_t dst_capacity);
+/* FAST corners (post NMS + border filter, raster order) of `image`/`level` as triples (x, y, score) of int32. */
+int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys, int capacity, int* n_out);
+/* Number of kernels launched by this handle since creation (monotonic). */
+uint64_t vslam_kernel_launches(vslam_handle h);
+/* Device time (ms, CUDA events on the handle's stream) of the last vslam_process_batch* call, per stage:
+ * [0]=pyramid [1]=fast [2]=select+harris+angle [3]=blur [4]=brief [5]=match+triangulate [6]=total kernels.
+ * Only filled when profiling was enabled with vslam_set_profiling(h,1) (it serialises the pipeline). */
+int vslam_set_profiling(vslam_handle h, int enabled);
+int vslam_last_stage_ms(vslam_handle h, float* ms7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSLAM_B200_H_ */

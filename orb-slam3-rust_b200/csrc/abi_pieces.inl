@@ -1,0 +1,303 @@
+// Stand-alone entry points of the C ABI (the pieces of process() and the tracking-side searches).
+// Included at the end of vslam_b200.cu.  Inputs come from host memory, are staged into a grow-only device
+// arena owned by the handle, processed by the same kernels the batch pipeline uses, and copied back.
+namespace {
+
+// Reserve `total` bytes (grow-only); sub-allocations are carved with arena_take.
+int arena_begin(vslam_handle h, size_t total) {
+  total += 4096;
+  if (h->arena_cap < total) {
+    if (h->arena_base) cudaFree(h->arena_base);
+    h->arena_base = nullptr;
+    h->arena_cap = 0;
+    size_t want = std::max(total, (size_t)1 << 20);
+    if (cudaMalloc(&h->arena_base, want) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, VSLAM_ERR_OUT_OF_MEMORY, "device scratch allocation of %zu bytes failed", want);
+    }
+    h->arena_cap = want;
+  }
+  h->arena_used = 0;
+  return VSLAM_OK;
+}
+template <typename T>
+T* arena_take(vslam_handle h, size_t count) {
+  size_t off = align_up(h->arena_used, 256);
+  h->arena_used = off + count * sizeof(T);
+  return reinterpret_cast<T*>(h->arena_base + off);
+}
+inline size_t pad256(size_t b) { return align_up(b, 256) + 256; }
+
+}  // namespace
+
+extern "C" {
+
+int vslam_descriptor_distance(vslam_handle h, const uint8_t* a, const uint8_t* b, int n, uint32_t* out) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t nb = (size_t)n * 32;
+  int rc = arena_begin(h, 2 * pad256(nb) + pad256((size_t)n * 4));
+  if (rc) return rc;
+  unsigned* da = arena_take<unsigned>(h, (size_t)n * 8);
+  unsigned* db = arena_take<unsigned>(h, (size_t)n * 8);
+  unsigned* dout = arena_take<unsigned>(h, (size_t)n);
+  cudaStream_t st = h->slots[0].stream;
+  CU_TRY(h, cudaMemcpyAsync(da, a, nb, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(db, b, nb, cudaMemcpyHostToDevice, st));
+  vk::k_hamming<<<(n + 255) / 256, 256, 0, st>>>(da, db, n, dout);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
+// Build a one-frame result slab (same layout as the pipeline's) around caller-provided features.
+static int stage_features(vslam_handle h, const vslam_keypoint* kl, const uint8_t* dl, int nl, const vslam_keypoint* kr,
+                          const uint8_t* dr, int nr, vk::FrameLayout* F, int2** ml, cudaStream_t st) {
+  const size_t cap = (size_t)std::max(std::max(nl, nr), 1);
+  size_t o = sizeof(ResHdr);
+  vk::FrameLayout L;
+  L.off_kp[0] = (int)o; o += align_up(cap * 28, 16);
+  L.off_kp[1] = (int)o; o += align_up(cap * 28, 16);
+  L.off_desc[0] = (int)o; o += cap * 32;
+  L.off_desc[1] = (int)o; o += cap * 32;
+  L.off_matches = (int)o; o += cap * 16;
+  L.off_pts = (int)o; o += cap * 24;
+  L.off_valid = (int)o; o += align_up(cap, 16);
+  L.frame_stride = (long long)align_up(o, 256);
+  L.cap = (int)cap;
+  int rc = arena_begin(h, pad256((size_t)L.frame_stride) + pad256(cap * sizeof(int2)));
+  if (rc) return rc;
+  L.base = arena_take<unsigned char>(h, (size_t)L.frame_stride);
+  *ml = arena_take<int2>(h, cap);
+  ResHdr hdr;
+  memset(&hdr, 0, sizeof(hdr));
+  hdr.n_kp[0] = nl;
+  hdr.n_kp[1] = nr;
+  CU_TRY(h, cudaMemcpyAsync(L.base, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+  if (nl > 0) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_kp[0], kl, (size_t)nl * 28, cudaMemcpyHostToDevice, st));
+  if (nr > 0) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_kp[1], kr, (size_t)nr * 28, cudaMemcpyHostToDevice, st));
+  if (nl > 0 && dl) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_desc[0], dl, (size_t)nl * 32, cudaMemcpyHostToDevice, st));
+  if (nr > 0 && dr) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_desc[1], dr, (size_t)nr * 32, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaStreamSynchronize(st));  // hdr is a stack variable
+  *F = L;
+  return VSLAM_OK;
+}
+
+int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const uint8_t* desc_left, int n_left,
+                         const vslam_keypoint* kp_right, const uint8_t* desc_right, int n_right, vslam_dmatch* matches,
+                         int* n_matches) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n_left < 0 || n_right < 0 || !n_matches || (n_left > 0 && (!kp_left || !desc_left || !matches)) ||
+      (n_right > 0 && (!kp_right || !desc_right)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_left > 65535 || n_right > 65535) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "more than 65535 keypoints");
+  *n_matches = 0;
+  if (n_left == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  vk::FrameLayout F;
+  int2* ml;
+  int rc = stage_features(h, kp_left, desc_left, n_left, kp_right, desc_right, n_right, &F, &ml, st);
+  if (rc) return rc;
+  dim3 grid((F.cap + vk::kMatchLeftPerBlock - 1) / vk::kMatchLeftPerBlock, 1);
+  vk::k_match<<<grid, 256, 0, st>>>(F, h->S, ml);
+  vk::k_match_finalize<<<1, 256, 0, st>>>(F, h->S, ml);
+  h->launches += 2;
+  ResHdr hdr;
+  CU_TRY(h, cudaMemcpyAsync(&hdr, F.base, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  *n_matches = hdr.n_matches;
+  if (hdr.n_matches > 0)
+    CU_TRY(h, cudaMemcpy(matches, F.base + F.off_matches, (size_t)hdr.n_matches * 16, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+// triangulate: the device kernel is shared with the pipeline (k_match_finalize consumes a per-left table).
+int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left, const vslam_keypoint* kp_right,
+                      int n_right, const vslam_dmatch* matches, int n_matches, double* points, uint8_t* valid) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n_left < 0 || n_right < 0 || n_matches < 0 || (n_left > 0 && (!kp_left || !points || !valid)) ||
+      (n_right > 0 && !kp_right) || (n_matches > 0 && !matches))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_left == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  vk::FrameLayout F;
+  int2* ml;
+  int rc = stage_features(h, kp_left, nullptr, n_left, kp_right, nullptr, n_right, &F, &ml, st);
+  if (rc) return rc;
+  // per-left table from the caller's match list.  match_features never emits a left index twice; if a caller does,
+  // the last entry wins (the reference's loop would keep an earlier valid point when a later one has |d| < 0.5).
+  std::vector<int2> tab((size_t)F.cap, make_int2(-1, 0));
+  for (int i = 0; i < n_matches; ++i) {
+    int q = matches[i].query_idx, t = matches[i].train_idx;
+    if (q < 0 || q >= n_left || t < 0 || t >= n_right) continue;  // .get() returned None
+    tab[q] = make_int2(t, (int)matches[i].distance);
+  }
+  CU_TRY(h, cudaMemcpyAsync(ml, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  vk::k_match_finalize<<<1, 256, 0, st>>>(F, h->S, ml);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(points, F.base + F.off_pts, (size_t)n_left * 24, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(valid, F.base + F.off_valid, (size_t)n_left, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
+static vk::GridP grid_params(double img_w, double img_h) {
+  vk::GridP G;
+  G.inv_w = (double)VSLAM_GRID_COLS / (img_w - 0.0);
+  G.inv_h = (double)VSLAM_GRID_ROWS / (img_h - 0.0);
+  return G;
+}
+
+int vslam_grid_build(vslam_handle h, const vslam_keypoint* kps, int n, double img_w, double img_h, int32_t* cell_start,
+                     int32_t* cell_items) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n < 0 || !cell_start || (n > 0 && (!kps || !cell_items))) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nn = (size_t)std::max(n, 1);
+  int rc = arena_begin(h, pad256(nn * 28) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4));
+  if (rc) return rc;
+  unsigned char* dk = arena_take<unsigned char>(h, nn * 28);
+  int* dcs = arena_take<int>(h, vk::kGridCells + 1);
+  int* dci = arena_take<int>(h, nn);
+  int* dco = arena_take<int>(h, nn);
+  if (n > 0) CU_TRY(h, cudaMemcpyAsync(dk, kps, (size_t)n * 28, cudaMemcpyHostToDevice, st));
+  vk::k_grid_build<<<1, 1024, 0, st>>>(dk, n, grid_params(img_w, img_h), dcs, dci, dco);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(cell_start, dcs, (vk::kGridCells + 1) * 4, cudaMemcpyDeviceToHost, st));
+  if (n > 0) CU_TRY(h, cudaMemcpyAsync(cell_items, dci, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
+int vslam_grid_query(vslam_handle h, const vslam_keypoint* kps, int n, double img_w, double img_h, const double* xyr,
+                     int nq, int32_t* out_start, int32_t* out_items, int out_capacity) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n < 0 || nq < 0 || !out_start || (n > 0 && !kps) || (nq > 0 && !xyr) || out_capacity < 0 ||
+      (out_capacity > 0 && !out_items))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nn = (size_t)std::max(n, 1), qq = (size_t)std::max(nq, 1), oc = (size_t)std::max(out_capacity, 1);
+  int rc = arena_begin(h, pad256(nn * 28) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4) + pad256(qq * 24) +
+                              2 * pad256((qq + 1) * 4) + pad256(oc * 4));
+  if (rc) return rc;
+  unsigned char* dk = arena_take<unsigned char>(h, nn * 28);
+  int* dcs = arena_take<int>(h, vk::kGridCells + 1);
+  int* dci = arena_take<int>(h, nn);
+  int* dco = arena_take<int>(h, nn);
+  double* dq = arena_take<double>(h, qq * 3);
+  int* dcnt = arena_take<int>(h, qq + 1);
+  int* dstart = arena_take<int>(h, qq + 1);
+  int* dout = arena_take<int>(h, oc);
+  const vk::GridP G = grid_params(img_w, img_h);
+  if (n > 0) CU_TRY(h, cudaMemcpyAsync(dk, kps, (size_t)n * 28, cudaMemcpyHostToDevice, st));
+  if (nq > 0) CU_TRY(h, cudaMemcpyAsync(dq, xyr, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+  vk::k_grid_build<<<1, 1024, 0, st>>>(dk, n, G, dcs, dci, dco);
+  h->launches++;
+  if (nq > 0) {
+    vk::k_grid_count<<<(nq + 255) / 256, 256, 0, st>>>(dcs, G, dq, nq, dcnt);
+    h->launches++;
+  }
+  vk::k_scan_counts<<<1, 1024, 0, st>>>(dcnt, nq, dstart);
+  h->launches++;
+  if (nq > 0) {
+    vk::k_grid_fill<<<(nq * 32 + 255) / 256, 256, 0, st>>>(dcs, dci, G, dq, nq, dstart, dout, out_capacity);
+    h->launches++;
+  }
+  CU_TRY(h, cudaMemcpyAsync(out_start, dstart, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  const int total = out_start[nq];
+  if (total > out_capacity) return fail(h, VSLAM_ERR_CAPACITY, "grid query needs %d items, capacity %d", total, out_capacity);
+  if (total > 0) CU_TRY(h, cudaMemcpy(out_items, dout, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_search_by_projection(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, const double* uv,
+                               const uint8_t* mp_desc, int M, const vslam_search_params* sp, int32_t* out_idx,
+                               int32_t* out_dist) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n < 0 || M < 0 || !sp || (n > 0 && (!kps || !desc)) || (M > 0 && (!uv || !mp_desc || !out_idx || !out_dist)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (sp->mode != VSLAM_SEARCH_LOCAL_MAP && sp->mode != VSLAM_SEARCH_MOTION_MODEL)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown search mode %d", sp->mode);
+  if (sp->th_high > 1024) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "th_high out of range");
+  if (M == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nn = (size_t)std::max(n, 1), mm = (size_t)M;
+  int rc = arena_begin(h, pad256(nn * 28) + pad256(nn * 32) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4) +
+                              pad256(mm * 16) + pad256(mm * 32) + 2 * pad256(mm * 4));
+  if (rc) return rc;
+  unsigned char* dk = arena_take<unsigned char>(h, nn * 28);
+  unsigned* dd = arena_take<unsigned>(h, nn * 8);
+  int* dcs = arena_take<int>(h, vk::kGridCells + 1);
+  int* dci = arena_take<int>(h, nn);
+  int* dco = arena_take<int>(h, nn);
+  double* duv = arena_take<double>(h, mm * 2);
+  unsigned* dmd = arena_take<unsigned>(h, mm * 8);
+  int* doi = arena_take<int>(h, mm);
+  int* dod = arena_take<int>(h, mm);
+  const vk::GridP G = grid_params(sp->img_w, sp->img_h);
+  vk::SearchP S;
+  S.mode = sp->mode;
+  S.radius = sp->radius;
+  S.th_high = sp->th_high;
+  S.nn_ratio = sp->nn_ratio;
+  S.bound_w = sp->bound_w;
+  S.bound_h = sp->bound_h;
+  if (n > 0) {
+    CU_TRY(h, cudaMemcpyAsync(dk, kps, (size_t)n * 28, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  }
+  CU_TRY(h, cudaMemcpyAsync(duv, uv, mm * 16, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(dmd, mp_desc, mm * 32, cudaMemcpyHostToDevice, st));
+  vk::k_grid_build<<<1, 1024, 0, st>>>(dk, n, G, dcs, dci, dco);
+  vk::k_search<<<(M * 32 + 255) / 256, 256, 0, st>>>(dcs, dci, dd, G, S, duv, dmd, M, doi, dod);
+  h->launches += 2;
+  CU_TRY(h, cudaMemcpyAsync(out_idx, doi, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out_dist, dod, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
+int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query, const uint8_t* train, int n_train,
+                              vslam_dmatch* matches, int* n_matches) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n_query < 0 || n_train < 0 || !n_matches || (n_query > 0 && (!query || !matches)) || (n_train > 0 && !train))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  *n_matches = 0;
+  if (n_query == 0 || n_train == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nq = (size_t)n_query, nt = (size_t)n_train;
+  int rc = arena_begin(h, pad256(nq * 32) + pad256(nt * 32) + 2 * pad256(nq * 4) + 2 * pad256(nt * 4) + pad256(nq * 16) + 512);
+  if (rc) return rc;
+  unsigned* dq = arena_take<unsigned>(h, nq * 8);
+  unsigned* dt = arena_take<unsigned>(h, nt * 8);
+  int* sidx = arena_take<int>(h, nq);
+  int* sdist = arena_take<int>(h, nq);
+  int* tidx = arena_take<int>(h, nt);
+  int* tdist = arena_take<int>(h, nt);
+  int4* dm = arena_take<int4>(h, nq);
+  int* dn = arena_take<int>(h, 1);
+  CU_TRY(h, cudaMemcpyAsync(dq, query, nq * 32, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(dt, train, nt * 32, cudaMemcpyHostToDevice, st));
+  vk::k_nearest<<<(n_query + 7) / 8, 256, 0, st>>>(dq, n_query, dt, n_train, sidx, sdist);
+  vk::k_nearest<<<(n_train + 7) / 8, 256, 0, st>>>(dt, n_train, dq, n_query, tidx, tdist);
+  vk::k_cross<<<1, 256, 0, st>>>(sidx, sdist, tidx, n_query, dm, dn);
+  h->launches += 3;
+  int nm = 0;
+  CU_TRY(h, cudaMemcpyAsync(&nm, dn, 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  *n_matches = nm;
+  if (nm > 0) CU_TRY(h, cudaMemcpy(matches, dm, (size_t)nm * 16, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+}  // extern "C"

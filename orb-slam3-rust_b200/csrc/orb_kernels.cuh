@@ -1,0 +1,814 @@
+// Hand-written sm_100a kernels for ORB extraction, bit-exact with cv::ORB as the reference configures it
+// (/root/reference/src/tracking/frame/stereo.rs:38-48,72-73; arithmetic spec: SURVEY.md §8.A0-A6).
+//
+//   k_resize   A1  INTER_LINEAR_EXACT chain (Q8.8 x Q8.8 fixed point), one launch per level, batch in grid.y
+//   k_fast     A2  FAST-9/16 score for every pixel with DPX u16x2 min/max (VIMNMX3.U16x2), NMS, border filter,
+//                  raster-ordered emission per 16-row strip (no atomics on global memory, no sort)
+//   k_select   A3/A4  gather strips -> exact libstdc++ retainBest replay (warp-parallel Hoare passes) ->
+//                  Harris -> retainBest -> intensity-centroid angle
+//   k_blur     A5  separable 7-tap float32 FMA Gaussian, reflect-101, round-half-even
+//   k_brief    A6  steered BRIEF (one warp per keypoint, one descriptor byte per lane) + KeyPoint assembly
+//
+// Everything is integer / explicitly rounded float: the file is compiled with -fmad=false and uses the
+// __f*_rn intrinsics wherever the rounding sequence is part of the specification.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "select_serial.h"
+#include "vslam_params.h"
+
+namespace vk {
+
+#define VSLAM_FULL 0xffffffffu
+
+// Global (not __constant__) memory: every lane reads a different test, which the constant cache would serialise.
+__device__ int g_brief_pattern[1024] = {
+#include "brief_pattern.inc"
+};
+
+struct __align__(4) LvlKp {
+  unsigned xy;  // (y<<16)|x in level coordinates
+  float resp;
+  float angle;
+};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int img, const uint8_t* in_l,
+                                                    const uint8_t* in_r, const uint8_t* pyr, int& pitch) {
+  if (l == 0) {
+    int f = img / P.eyes, e = img - f * P.eyes;
+    pitch = P.in_pitch;
+    return (e ? in_r : in_l) + (long long)f * P.in_frame_stride;
+  }
+  pitch = P.lv[l].pitch;
+  return pyr + (long long)img * P.pyr_img_stride + P.lv[l].pyr_off;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A1 — pyramid level l from level l-1.  grid = (ceil(h_l / VSLAM_RESIZE_ROWS), n_img), block = 256.
+// coef[] holds per destination column/row (src offset | alpha1 << 16), computed on the host in f64.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ PyrP P, int l, const uint8_t* __restrict__ in_l,
+                                                const uint8_t* __restrict__ in_r, uint8_t* __restrict__ pyr,
+                                                const uint32_t* __restrict__ coef) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const LevelP& D = P.lv[l];
+  const LevelP& S = P.lv[l - 1];
+  const int img = blockIdx.y;
+  const int y0 = blockIdx.x * VSLAM_RESIZE_ROWS;
+  const int rows = min(VSLAM_RESIZE_ROWS, D.h - y0);
+  int spitch;
+  const uint8_t* src = level_ptr(P, l - 1, img, in_l, in_r, pyr, spitch);
+  uint8_t* dst = pyr + (long long)img * P.pyr_img_stride + D.pyr_off;
+  const uint32_t* yc = coef + D.ycoef_off;
+  const uint32_t* xc = coef + D.xcoef_off;
+  const int sy0 = (int)(yc[y0] & 0xffffu);
+  const int sy1 = min((int)(yc[y0 + rows - 1] & 0xffffu) + 1, S.h - 1);
+  const int nrows = sy1 - sy0 + 1;
+  const int vpr = spitch >> 4;
+  for (int i = threadIdx.x; i < nrows * vpr; i += 256) {
+    int r = i / vpr, c = i - r * vpr;
+    reinterpret_cast<uint4*>(smem)[i] = *reinterpret_cast<const uint4*>(src + (size_t)(sy0 + r) * spitch + 16 * c);
+  }
+  __syncthreads();
+  const int ngroups = D.pitch >> 2;
+  for (int g = threadIdx.x; g < ngroups; g += 256) {
+    int ox[4], ox1[4];
+    unsigned a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned c = xc[min(4 * g + k, D.w - 1)];
+      ox[k] = (int)(c & 0xffffu);
+      ox1[k] = min(ox[k] + 1, S.w - 1);
+      a1[k] = c >> 16;
+    }
+    for (int r = 0; r < rows; ++r) {
+      unsigned yy = yc[y0 + r];
+      int o = (int)(yy & 0xffffu);
+      unsigned b1 = yy >> 16, b0 = 256u - b1;
+      const uint8_t* r0 = smem + (o - sy0) * spitch;
+      const uint8_t* r1 = smem + (min(o + 1, S.h - 1) - sy0) * spitch;
+      unsigned word = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned a0 = 256u - a1[k];
+        unsigned h0 = a0 * r0[ox[k]] + a1[k] * r0[ox1[k]];
+        unsigned h1 = a0 * r1[ox[k]] + a1[k] * r1[ox1[k]];
+        unsigned v = b0 * h0 + b1 * h1;
+        word |= ((v + 32768u) >> 16) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * D.pitch + 4 * g) = word;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A2 — FAST-9/16.  For a circle p[0..15] around centre c the FAST score is
+//     S = max( max_k min_{j=k..k+8} p_j  -  c ,  c  -  min_k max_{j=k..k+8} p_j )
+// (corner iff S > t, response = S-1).  min/max over the 16 circular 9-windows are computed with 3-input DPX
+// min/max on u16x2 lanes: two pixels per instruction, no branches, no divergence.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned max3u(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ unsigned min3u(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
+
+// p: 16 circle samples (u16x2 = two adjacent pixels); c2: the two centres.  Returns max(S - t, 0) per lane.
+__device__ __forceinline__ unsigned fast_score2(const unsigned (&p)[16], unsigned c2, unsigned t2) {
+  unsigned a3[16], b3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    a3[k] = min3u(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+    b3[k] = max3u(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+  }
+  unsigned a9[16], b9[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    a9[k] = min3u(a3[k], a3[(k + 3) & 15], a3[(k + 6) & 15]);
+    b9[k] = max3u(b3[k], b3[(k + 3) & 15], b3[(k + 6) & 15]);
+  }
+  unsigned M9 = max3u(max3u(max3u(a9[0], a9[1], a9[2]), max3u(a9[3], a9[4], a9[5]), max3u(a9[6], a9[7], a9[8])),
+                      max3u(max3u(a9[9], a9[10], a9[11]), max3u(a9[12], a9[13], a9[14]), a9[15]), 0u);
+  unsigned m9 = min3u(min3u(min3u(b9[0], b9[1], b9[2]), min3u(b9[3], b9[4], b9[5]), min3u(b9[6], b9[7], b9[8])),
+                      min3u(min3u(b9[9], b9[10], b9[11]), min3u(b9[12], b9[13], b9[14]), b9[15]), 0xffffffffu);
+  unsigned bright = __vmaxu2(M9, c2) - c2;  // lane-wise non-negative: no borrow between lanes
+  unsigned dark = c2 - __vminu2(m9, c2);
+  unsigned S = __vmaxu2(bright, dark);
+  return __vmaxu2(S, t2) - t2;
+}
+
+// 4 pixels starting at byte offset dx relative to word b, from the three consecutive words a|b|c.
+template <int DX>
+__device__ __forceinline__ unsigned shifted4(unsigned a, unsigned b, unsigned c) {
+  if constexpr (DX < 0) return __funnelshift_r(a, b, 8u * (unsigned)(4 + DX));
+  else if constexpr (DX > 0) return __funnelshift_r(b, c, 8u * (unsigned)DX);
+  else return b;
+}
+__device__ __forceinline__ unsigned pair_lo(unsigned s) { return __byte_perm(s, 0u, 0x4140); }
+__device__ __forceinline__ unsigned pair_hi(unsigned s) { return __byte_perm(s, 0u, 0x4342); }
+
+// Shared-memory footprint of k_fast for a level of the given pitch.
+__host__ __device__ inline int fast_sp(int pitch) { return pitch + 32; }
+__host__ __device__ inline int fast_bw(int pitch) { return (pitch + 31) >> 5; }
+__host__ inline size_t fast_smem_bytes(int pitch) {
+  size_t sp = fast_sp(pitch), bw = fast_bw(pitch);
+  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + 2 * VSLAM_FAST_ROWS * bw * 4 + 64;
+}
+
+// grid = (total_fast_strips, n_img), block = 256.
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+                                              const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                              int* __restrict__ strip_cnt, vrec_t* __restrict__ strip_rec) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int strip = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  int l = 0;
+  for (int k = 0; k < P.nlevels; ++k)
+    if (strip >= P.lv[k].fast_strip0 && strip < P.lv[k].fast_strip0 + P.lv[k].fast_nstrips) l = k;
+  const LevelP& L = P.lv[l];
+  const int s_local = strip - L.fast_strip0;
+  const int ys = L.ey0 + s_local * VSLAM_FAST_ROWS;
+  const int ye = min(ys + VSLAM_FAST_ROWS, L.ey1);
+  const int rows = ye - ys;
+  int pitch;
+  const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
+  const int SP = fast_sp(pitch), BW = fast_bw(pitch);
+  uint8_t* pix = smem;                                   // (rows+8) x SP, image row ys-4+r at pix + r*SP + 16
+  uint8_t* sc = pix + (VSLAM_FAST_ROWS + 8) * SP;        // (rows+2) x SP, score row of image row ys-1+r
+  uint32_t* bits = reinterpret_cast<uint32_t*>(sc + (VSLAM_FAST_ROWS + 2) * SP);  // rows x BW corner bitmask
+  uint32_t* woff = bits + VSLAM_FAST_ROWS * BW;          // rows x BW exclusive corner offsets
+  __shared__ int s_total;
+
+  // ---- stage the pixel tile (128-bit loads), clear margins / score tile / bitmask
+  const int vpr = pitch >> 4;
+  for (int i = tid; i < (rows + 8) * vpr; i += 256) {
+    int r = i / vpr, c = i - r * vpr;
+    int gy = min(max(ys - 4 + r, 0), L.h - 1);
+    *reinterpret_cast<uint4*>(pix + r * SP + 16 + 16 * c) =
+        *reinterpret_cast<const uint4*>(img_base + (size_t)gy * pitch + 16 * c);
+  }
+  for (int i = tid; i < (rows + 8) * 2; i += 256) {
+    int r = i >> 1;
+    *reinterpret_cast<uint4*>(pix + r * SP + ((i & 1) ? 16 + pitch : 0)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += 256)
+    reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * VSLAM_FAST_ROWS * BW; i += 256) bits[i] = 0;
+  __syncthreads();
+
+  // ---- scores on the emission region dilated by one pixel (clipped to FAST's own 3-px border)
+  const int sx0 = max(3, L.ex0 - 1), sx1 = min(L.w - 3, L.ex1 + 1);
+  const int sy_lo = max(3, ys - 1), sy_hi = min(L.h - 3, ye + 1);  // [sy_lo, sy_hi)
+  const int gx0 = sx0 >> 2, ngx = ((sx1 - 1) >> 2) - gx0 + 1;
+  const int nsr = sy_hi - sy_lo;
+  const unsigned t2 = (unsigned)P.fast_threshold * 0x00010001u;
+  for (int it = tid; it < nsr * ngx; it += 256) {
+    const int ry = it / ngx;
+    const int g = gx0 + (it - ry * ngx);
+    const int y = sy_lo + ry;
+    const uint8_t* base = pix + (y - (ys - 4)) * SP + 16 + 4 * g;  // centre word of this group
+    unsigned w[7][3];
+#pragma unroll
+    for (int dy = -3; dy <= 3; ++dy) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(base + dy * SP);
+      w[dy + 3][0] = q[-1];
+      w[dy + 3][1] = q[0];
+      w[dy + 3][2] = q[1];
+    }
+#define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
+    unsigned s[16];
+    s[0] = shifted4<0>(VS_ROW(3));
+    s[1] = shifted4<1>(VS_ROW(3));
+    s[2] = shifted4<2>(VS_ROW(2));
+    s[3] = shifted4<3>(VS_ROW(1));
+    s[4] = shifted4<3>(VS_ROW(0));
+    s[5] = shifted4<3>(VS_ROW(-1));
+    s[6] = shifted4<2>(VS_ROW(-2));
+    s[7] = shifted4<1>(VS_ROW(-3));
+    s[8] = shifted4<0>(VS_ROW(-3));
+    s[9] = shifted4<-1>(VS_ROW(-3));
+    s[10] = shifted4<-2>(VS_ROW(-2));
+    s[11] = shifted4<-3>(VS_ROW(-1));
+    s[12] = shifted4<-3>(VS_ROW(0));
+    s[13] = shifted4<-3>(VS_ROW(1));
+    s[14] = shifted4<-2>(VS_ROW(2));
+    s[15] = shifted4<-1>(VS_ROW(3));
+#undef VS_ROW
+    const unsigned cw = w[3][1];
+    unsigned p[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p[k] = pair_lo(s[k]);
+    const unsigned xlo = fast_score2(p, pair_lo(cw), t2);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p[k] = pair_hi(s[k]);
+    const unsigned xhi = fast_score2(p, pair_hi(cw), t2);
+    unsigned word = __byte_perm(xlo, xhi, 0x6420);
+    unsigned mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int x = 4 * g + k;
+      if (x >= sx0 && x < sx1) mask |= 0xffu << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(sc + (y - (ys - 1)) * SP + 16 + 4 * g) = word & mask;
+  }
+  __syncthreads();
+
+  // ---- non-maximum suppression (strictly greater than the 8 neighbours) + runByImageBorder
+  const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
+  for (int it = tid; it < rows * negx; it += 256) {
+    const int ry = it / negx;
+    const int g = egx0 + (it - ry * negx);
+    const uint8_t* srow = sc + (ry + 1) * SP + 16;
+    unsigned word = *reinterpret_cast<const uint32_t*>(srow + 4 * g);
+    if (word == 0) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int v = (word >> (8 * k)) & 0xff;
+      int x = 4 * g + k;
+      if (v == 0 || x < L.ex0 || x >= L.ex1) continue;
+      const uint8_t* c = srow + x;
+      bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
+                  v > c[SP] && v > c[SP + 1];
+      if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+    }
+  }
+  __syncthreads();
+
+  // ---- raster-ordered emission: exclusive scan of the bitmask popcounts by warp 0, then every thread
+  //      expands its words.  Order inside the strip == (y, x) == cv::FAST's output order.
+  const int nwords = rows * BW;
+  if (tid < 32) {
+    const int per = (nwords + 31) >> 5;
+    const int b = tid * per, e = min(b + per, nwords);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += __popc(bits[i]);
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+      if (tid >= d) incl += o;
+    }
+    int run = incl - sum;
+    for (int i = b; i < e; ++i) {
+      woff[i] = run;
+      run += __popc(bits[i]);
+    }
+    if (tid == 31) s_total = incl;
+  }
+  __syncthreads();
+  vrec_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
+  for (int wi = tid; wi < nwords; wi += 256) {
+    unsigned bw = bits[wi];
+    if (!bw) continue;
+    int off = woff[wi];
+    const int ry = wi / BW;
+    const int xb = (wi - ry * BW) << 5;
+    while (bw) {
+      int b = __ffs(bw) - 1;
+      bw &= bw - 1;
+      int x = xb + b;
+      int score = (int)sc[(ry + 1) * SP + 16 + x] + P.fast_threshold - 1;  // S - 1
+      unsigned xy = ((unsigned)(ys + ry) << 16) | (unsigned)x;
+      out[off++] = ((vrec_t)__float_as_uint((float)score) << 32) | xy;
+    }
+  }
+  if (tid == 0) strip_cnt[(long long)img * P.total_fast_strips + strip] = s_total;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A3 — exact replay of KeyPointsFilter::retainBest (libstdc++ std::nth_element + std::partition) by ONE warp.
+// A Hoare pass of __unguarded_partition pairs the k-th "left stopper" (v[i] <= pivot, ascending) with the k-th
+// "right stopper" (v[j] >= pivot, descending) for as long as L_k < R_k; every swap touches a distinct pair, so the
+// pass is: two ordered stream compactions (ballot + popc), a count, and a parallel swap.  The cut the serial
+// algorithm returns is min(L_{K+1}, R_K).  (Checked against libstdc++ in tests/test_select_replay.py.)
+// ----------------------------------------------------------------------------------------------------------
+template <typename IdxT>
+__device__ int warp_partition_pivot(vrec_t* rec, int first, int last, IdxT* Ll, IdxT* Rl, int lane) {
+  if (lane == 0) vsel::median_to_first(rec, first, first + 1, first + (last - first) / 2, last - 1);
+  __syncwarp();
+  const float p = vsel::resp_of(rec[first]);
+  const unsigned lt = (1u << lane) - 1u;
+  int nR = 0;
+  for (int base = last - 1; base >= first; base -= 32) {  // right stoppers: !(pivot > v[j]), descending j
+    int j = base - lane;
+    bool st = (j >= first) && !(p > vsel::resp_of(rec[j]));
+    unsigned m = __ballot_sync(VSLAM_FULL, st);
+    if (st) Rl[nR + __popc(m & lt)] = (IdxT)j;
+    nR += __popc(m);
+  }
+  int nL = 0;
+  for (int base = first + 1; base < last; base += 32) {  // left stoppers: !(v[i] > pivot), ascending i
+    int i = base + lane;
+    bool st = (i < last) && !(vsel::resp_of(rec[i]) > p);
+    unsigned m = __ballot_sync(VSLAM_FULL, st);
+    if (st) Ll[nL + __popc(m & lt)] = (IdxT)i;
+    nL += __popc(m);
+  }
+  __syncwarp();
+  const int nmin = min(nL, nR);
+  int K = 0;
+  for (int k0 = 0; k0 < nmin; k0 += 32) {  // L ascending, R descending: the predicate is a prefix
+    int k = k0 + lane;
+    bool ok = (k < nmin) && ((int)Ll[k] < (int)Rl[k]);
+    unsigned m = __ballot_sync(VSLAM_FULL, ok);
+    K += __popc(m);
+    if (m != VSLAM_FULL) break;
+  }
+  int cut = last;
+  if (K < nL) cut = min(cut, (int)Ll[K]);
+  if (K > 0) cut = min(cut, (int)Rl[K - 1]);
+  for (int k = lane; k < K; k += 32) {
+    int a = (int)Ll[k], b = (int)Rl[k];
+    vrec_t t = rec[a];
+    rec[a] = rec[b];
+    rec[b] = t;
+  }
+  __syncwarp();
+  return cut;
+}
+
+// Returns the retained count; rec[0..count) is exactly what std::vector<KeyPoint> holds after retainBest(n_points).
+template <typename IdxT>
+__device__ int warp_retain_best(vrec_t* rec, int n, int n_points, IdxT* Ll, IdxT* Rl, int lane) {
+  if (n_points < 0 || n <= n_points) return n;
+  if (n_points == 0) return 0;
+  const int nth = n_points - 1;
+  int first = 0, last = n;
+  int depth = 2 * vsel::floor_log2(n);
+  bool sorted_tail = true;
+  while (last - first > 3) {
+    if (depth == 0) {  // std::__heap_select fallback (serial; practically never taken)
+      if (lane == 0) vsel::heap_select_fallback(rec, first, nth, last);
+      sorted_tail = false;
+      break;
+    }
+    --depth;
+    int cut = warp_partition_pivot<IdxT>(rec, first, last, Ll, Rl, lane);
+    if (cut <= nth) first = cut;
+    else last = cut;
+  }
+  if (sorted_tail && lane == 0) vsel::insertion_sort(rec, first, last);
+  __syncwarp();
+  // std::partition(v + n_points, end, resp >= thr): the k-th failing element from the left swaps with the k-th
+  // passing element from the right while A_k < B_k; only the kept front part is materialised.
+  const float thr = vsel::resp_of(rec[nth]);
+  const unsigned lt = (1u << lane) - 1u;
+  int nB = 0;
+  for (int base = n - 1; base >= n_points; base -= 32) {
+    int j = base - lane;
+    bool st = (j >= n_points) && (vsel::resp_of(rec[j]) >= thr);
+    unsigned m = __ballot_sync(VSLAM_FULL, st);
+    if (st) Rl[nB + __popc(m & lt)] = (IdxT)j;
+    nB += __popc(m);
+  }
+  int nA = 0;
+  for (int base = n_points; base < n; base += 32) {
+    int i = base + lane;
+    bool st = (i < n) && !(vsel::resp_of(rec[i]) >= thr);
+    unsigned m = __ballot_sync(VSLAM_FULL, st);
+    if (st) Ll[nA + __popc(m & lt)] = (IdxT)i;
+    nA += __popc(m);
+  }
+  __syncwarp();
+  const int nmin = min(nA, nB);
+  for (int k = lane; k < nmin; k += 32) {
+    int a = (int)Ll[k], b = (int)Rl[k];
+    if (a < b) rec[a] = rec[b];
+  }
+  __syncwarp();
+  return n_points + nB;
+}
+
+// A3(iii) — HarrisResponses (blockSize 7, k = 0.04) on the un-blurred level; float formula without FMA.
+__device__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y, float scale4) {
+  // Ix = [1 2 1]^T (rows) applied to dx[r][j] = v[r][j+1] - v[r][j-1];  Iy = sm[r+1][j] - sm[r-1][j] with
+  // sm[r][j] = v[r][j-1] + 2 v[r][j] + v[r][j+1].  Three rows of (dx, sm) are kept live while walking 9 rows.
+  const uint8_t* p0 = img + (size_t)(y - 4) * pitch + (x - 4);
+  int dx0[7], dx1[7], dx2[7], sm0[7], sm1[7], sm2[7];
+  int a = 0, b = 0, c = 0;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    int v[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] = p0[r * pitch + j];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      dx0[j] = dx1[j];
+      dx1[j] = dx2[j];
+      sm0[j] = sm1[j];
+      sm1[j] = sm2[j];
+      dx2[j] = v[j + 2] - v[j];
+      sm2[j] = v[j] + 2 * v[j + 1] + v[j + 2];
+    }
+    if (r >= 2) {  // rows r-2, r-1, r are live: block row i = r-1
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        int Ix = dx1[j] * 2 + dx0[j] + dx2[j];
+        int Iy = sm2[j] - sm0[j];
+        a += Ix * Ix;
+        b += Iy * Iy;
+        c += Ix * Iy;
+      }
+    }
+  }
+  float fa = __int2float_rn(a), fb = __int2float_rn(b), fc = __int2float_rn(c);
+  float t = __fadd_rn(fa, fb);
+  float det = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
+  float tr = __fmul_rn(__fmul_rn(0.04f, t), t);
+  return __fmul_rn(__fsub_rn(det, tr), scale4);
+}
+
+// cv::fastAtan2 (scalar float path, degrees), every operation individually rounded.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float rad2deg = (float)(180.0 / 3.141592653589793238462643383279502884);
+  const float p1 = 0.9997878412794807f * rad2deg;
+  const float p3 = -0.3258083974640975f * rad2deg;
+  const float p5 = 0.1555786518463281f * rad2deg;
+  const float p7 = -0.04432655554792128f * rad2deg;
+  const float eps = (float)2.2204460492503131e-16;
+  float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(
+        90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// A4 — intensity-centroid angle, one warp per keypoint: lane v+15 sums row v of the 31-px disc.
+__device__ float ic_angle_warp(const uint8_t* __restrict__ img, int pitch, int x, int y, int lane) {
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int v = lane - 15;
+    const int av = v < 0 ? -v : v;
+    const int d = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);  // umax[|v|]
+    const uint8_t* row = img + (size_t)(y + v) * pitch + x;
+    int s = 0, su = 0;
+    for (int u = -d; u <= d; ++u) {
+      int val = row[u];
+      s += val;
+      su += u * val;
+    }
+    m10 = su;
+    m01 = v * s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(VSLAM_FULL, m10, o);
+    m01 += __shfl_xor_sync(VSLAM_FULL, m01, o);
+  }
+  return fast_atan2_deg(__int2float_rn(m01), __int2float_rn(m10));
+}
+
+__host__ inline size_t select_smem_bytes(int cap) { return (size_t)cap * (sizeof(vrec_t) + 2 * sizeof(uint16_t)) + 16; }
+
+// One launch per level: grid = (1, n_img), block = 128.  Dynamic smem = select_smem_bytes(P.sel_smem_cap).
+// When a level holds more corners than sel_smem_cap (or than 65535) the replay runs in global memory
+// (in place in the strip-record slab, 32-bit index lists in `glists`).
+__global__ void __launch_bounds__(128) k_select(const __grid_constant__ PyrP P, const int l,
+                                                const uint8_t* __restrict__ in_l,
+                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                                const int* __restrict__ strip_cnt, vrec_t* __restrict__ strip_rec,
+                                                uint32_t* __restrict__ glists, LvlKp* __restrict__ lvl_kp,
+                                                int* __restrict__ lvl_cnt, float harris_scale4,
+                                                unsigned char* __restrict__ results) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_off[128];
+  __shared__ int s_n;
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const LevelP& L = P.lv[l];
+  const int* cnt = strip_cnt + (long long)img * P.total_fast_strips + L.fast_strip0;
+  vrec_t* lrec = strip_rec + (long long)img * P.rec_img_stride + L.rec_off;
+
+  // ---- strip offsets (nstrips <= 128 enforced by the host)
+  if (warp == 0) {
+    int run = 0;
+    for (int b = 0; b < L.fast_nstrips; b += 32) {
+      int i = b + lane;
+      int c = i < L.fast_nstrips ? cnt[i] : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (i < L.fast_nstrips) s_off[i] = run + incl - c;
+      run += __shfl_sync(VSLAM_FULL, incl, 31);
+    }
+    if (lane == 0) s_n = run;
+  }
+  __syncthreads();
+  const int n_in = s_n;
+  const bool use_smem = n_in <= P.sel_smem_cap && n_in <= 65535;
+  vrec_t* rec;
+  if (use_smem) {
+    rec = reinterpret_cast<vrec_t*>(smem);
+    for (int s = 0; s < L.fast_nstrips; ++s) {
+      const vrec_t* src = lrec + (long long)s * L.strip_cap;
+      const int c = cnt[s], o = s_off[s];
+      for (int i = tid; i < c; i += 128) rec[o + i] = src[i];
+    }
+  } else {
+    // compact the strips in place, strip by strip (destination never overtakes a later strip's source)
+    rec = lrec;
+    for (int s = 1; s < L.fast_nstrips; ++s) {
+      const vrec_t* src = lrec + (long long)s * L.strip_cap;
+      const int c = cnt[s], o = s_off[s];
+      for (int b = 0; b < c; b += 128) {
+        int i = b + tid;
+        vrec_t v = i < c ? src[i] : 0;
+        __syncthreads();
+        if (i < c) rec[o + i] = v;
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- retainBest(2 * N_l) on the FAST score
+  uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)P.sel_smem_cap * sizeof(vrec_t));
+  uint16_t* r16 = l16 + P.sel_smem_cap;
+  uint32_t* l32 = glists + 2 * ((long long)img * P.rec_img_stride + L.rec_off);
+  uint32_t* r32 = l32 + (long long)L.fast_nstrips * L.strip_cap;
+  if (warp == 0) {
+    int m = use_smem ? warp_retain_best<uint16_t>(rec, n_in, 2 * L.nfeat, l16, r16, lane)
+                     : warp_retain_best<uint32_t>(rec, n_in, 2 * L.nfeat, l32, r32, lane);
+    if (lane == 0) s_n = m;
+  }
+  __syncthreads();
+  const int m1 = s_n;
+
+  // ---- Harris response of every survivor
+  int pitch;
+  const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
+  for (int i = tid; i < m1; i += 128) {
+    vrec_t r = rec[i];
+    unsigned xy = (unsigned)r;
+    float h = harris_response(img_base, pitch, (int)(xy & 0xffffu), (int)(xy >> 16), harris_scale4);
+    rec[i] = ((vrec_t)__float_as_uint(h) << 32) | xy;
+  }
+  __syncthreads();
+
+  // ---- retainBest(N_l) on the Harris response
+  if (warp == 0) {
+    int m = use_smem ? warp_retain_best<uint16_t>(rec, m1, L.nfeat, l16, r16, lane)
+                     : warp_retain_best<uint32_t>(rec, m1, L.nfeat, l32, r32, lane);
+    if (lane == 0) s_n = m;
+  }
+  __syncthreads();
+  int m2 = s_n;
+  if (m2 > P.kp_cap) {  // more ties than the handle was sized for: flag, keep the first kp_cap
+    if (tid == 0) {
+      ResHdr* hdr = reinterpret_cast<ResHdr*>(results + (long long)(img / P.eyes) * P.res_frame_stride);
+      atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
+    }
+    m2 = P.kp_cap;
+  }
+
+  // ---- orientation, one warp per keypoint
+  LvlKp* out = lvl_kp + ((long long)img * P.nlevels + l) * P.kp_cap;
+  for (int i = warp; i < m2; i += 4) {
+    vrec_t r = rec[i];
+    unsigned xy = (unsigned)r;
+    float ang = ic_angle_warp(img_base, pitch, (int)(xy & 0xffffu), (int)(xy >> 16), lane);
+    if (lane == 0) {
+      LvlKp k;
+      k.xy = xy;
+      k.resp = __uint_as_float((unsigned)(r >> 32));
+      k.angle = ang;
+      out[i] = k;
+    }
+  }
+  if (tid == 0) lvl_cnt[(long long)img * P.nlevels + l] = m2;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A5 — the blur cv::ORB applies to each level: separable 7-tap float32 Gaussian (sigma 2) as OpenCV's AVX2
+// sepFilter2D evaluates it: row pass s = k0*x0, s = fma(x_j, k_j, s); column pass s = k3*r3,
+// s = fma(r_{3+j} + r_{3-j}, k_{3+j}, s); BORDER_REFLECT_101; round-half-even to u8.
+// grid = (total_blur_tiles, n_img), block = 256, tile = 128 x 32.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+__device__ __forceinline__ float u8_to_f32(unsigned word, int byte) {
+  // exact: place the byte in the mantissa of 2^23 and subtract 2^23
+  unsigned sel = 0x7540u | (unsigned)byte;
+  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+                                              const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                              uint8_t* __restrict__ blur) {
+  constexpr int TW = VSLAM_BLUR_TW, TH = VSLAM_BLUR_TH;
+  constexpr int IW = TW + 8;  // input tile bytes per row: x0-4 .. x0+TW+3
+  __shared__ __align__(16) uint8_t s_in[(TH + 6) * IW];
+  __shared__ __align__(16) float s_row[(TH + 6) * TW];
+  const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
+  const int tile = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  int l = 0;
+  for (int k = 0; k < P.nlevels; ++k)
+    if (tile >= P.lv[k].blur_tile0 && tile < P.lv[k].blur_tile0 + P.lv[k].blur_tx * P.lv[k].blur_ty) l = k;
+  const LevelP& L = P.lv[l];
+  const int tl = tile - L.blur_tile0;
+  const int ty = tl / L.blur_tx, tx = tl - ty * L.blur_tx;
+  const int x0 = tx * TW, y0 = ty * TH;
+  int pitch;
+  const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
+  uint8_t* dst = blur + (long long)img * P.blur_img_stride + L.blur_off;
+
+  // ---- stage input rows y0-3 .. y0+TH+2 (reflected), columns x0-4 .. x0+TW+3 (reflected)
+  constexpr int WPR = IW / 4;
+  for (int i = tid; i < (TH + 6) * WPR; i += 256) {
+    int r = i / WPR, wq = i - r * WPR;
+    int gy = reflect101(y0 - 3 + r, L.h);
+    int gx = x0 - 4 + 4 * wq;
+    const uint8_t* row = src + (size_t)gy * pitch;
+    unsigned word;
+    if (gx >= 0 && gx + 3 < L.w) {
+      word = *reinterpret_cast<const uint32_t*>(row + gx);
+    } else {
+      word = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) word |= (unsigned)row[reflect101(gx + k, L.w)] << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(s_in + r * IW + 4 * wq) = word;
+  }
+  __syncthreads();
+
+  // ---- row pass: 4 outputs per item from 10 input bytes
+  for (int it = tid; it < (TH + 6) * (TW / 4); it += 256) {
+    int r = it / (TW / 4), gq = it - r * (TW / 4);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(s_in + r * IW + 4 * gq);
+    unsigned w0 = q[0], w1 = q[1], w2 = q[2];
+    float f[10];  // tile bytes 4gq+1 .. 4gq+10  ==  image x = x0+4gq-3 .. x0+4gq+6
+    f[0] = u8_to_f32(w0, 1);
+    f[1] = u8_to_f32(w0, 2);
+    f[2] = u8_to_f32(w0, 3);
+    f[3] = u8_to_f32(w1, 0);
+    f[4] = u8_to_f32(w1, 1);
+    f[5] = u8_to_f32(w1, 2);
+    f[6] = u8_to_f32(w1, 3);
+    f[7] = u8_to_f32(w2, 0);
+    f[8] = u8_to_f32(w2, 1);
+    f[9] = u8_to_f32(w2, 2);
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float s = __fmul_rn(k0, f[k]);
+      s = __fmaf_rn(f[k + 1], k1, s);
+      s = __fmaf_rn(f[k + 2], k2, s);
+      s = __fmaf_rn(f[k + 3], k3, s);
+      s = __fmaf_rn(f[k + 4], k2, s);
+      s = __fmaf_rn(f[k + 5], k1, s);
+      s = __fmaf_rn(f[k + 6], k0, s);
+      o[k] = s;
+    }
+    *reinterpret_cast<float4*>(s_row + r * TW + 4 * gq) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+
+  // ---- column pass: thread = (4 columns) x (4 rows), 10 row vectors in registers
+  {
+    const int cg = tid & 31, rr = tid >> 5;
+    float4 v[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) v[j] = *reinterpret_cast<const float4*>(s_row + (4 * rr + j) * TW + 4 * cg);
+    const int gx = x0 + 4 * cg;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gy = y0 + 4 * rr + i;
+      unsigned word = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        auto at = [&](int j) -> float {
+          const float4& t = v[i + j];
+          return c == 0 ? t.x : c == 1 ? t.y : c == 2 ? t.z : t.w;
+        };
+        float s = __fmul_rn(k3, at(3));
+        s = __fmaf_rn(__fadd_rn(at(4), at(2)), k2, s);
+        s = __fmaf_rn(__fadd_rn(at(5), at(1)), k1, s);
+        s = __fmaf_rn(__fadd_rn(at(6), at(0)), k0, s);
+        int iv = __float2int_rn(s);
+        iv = min(max(iv, 0), 255);
+        word |= (unsigned)iv << (8 * c);
+      }
+      if (gy < L.h && gx < L.pitch) *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = word;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A6 — steered BRIEF + KeyPoint assembly.  grid = (ceil(kp_cap / 8), n_img), block = 256 (8 warps, one keypoint
+// each); lane b computes descriptor byte b (16 rotated pattern points).  Output order: levels 0..n-1 concatenated.
+// ----------------------------------------------------------------------------------------------------------
+struct __align__(4) KeyPoint28 {
+  float x, y, size, angle, response;
+  int octave, class_id;
+};
+
+__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ blur,
+                                               const LvlKp* __restrict__ lvl_kp, const int* __restrict__ lvl_cnt,
+                                               unsigned char* __restrict__ results) {
+  const int img = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int frame = img / P.eyes, eye = img - frame * P.eyes;
+  unsigned char* res = results + (long long)frame * P.res_frame_stride;
+  const int* cnt = lvl_cnt + (long long)img * P.nlevels;
+  int total = 0, l = -1, jl = 0;
+  for (int k = 0; k < P.nlevels; ++k) {
+    int c = cnt[k];
+    if (l < 0 && j < total + c) {
+      l = k;
+      jl = j - total;
+    }
+    total += c;
+  }
+  ResHdr* hdr = reinterpret_cast<ResHdr*>(res);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->n_kp[eye] = min(total, P.kp_cap);
+    if (total > P.kp_cap) atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
+  }
+  if (l < 0 || j >= P.kp_cap) return;
+  const LevelP& L = P.lv[l];
+  const LvlKp kp = lvl_kp[((long long)img * P.nlevels + l) * P.kp_cap + jl];
+  const int cx = (int)(kp.xy & 0xffffu), cy = (int)(kp.xy >> 16);
+  if (lane == 0) {
+    KeyPoint28 o;
+    o.x = __fmul_rn(__int2float_rn(cx), L.scale);
+    o.y = __fmul_rn(__int2float_rn(cy), L.scale);
+    o.size = __fmul_rn(31.0f, L.scale);
+    o.angle = kp.angle;
+    o.response = kp.resp;
+    o.octave = l;
+    o.class_id = -1;
+    reinterpret_cast<KeyPoint28*>(res + P.res_off_kp[eye])[j] = o;
+  }
+  // angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)   (double cos/sin of the f32 angle)
+  const float rad = __fmul_rn(kp.angle, (float)(3.141592653589793238462643383279502884 / 180.0));
+  const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+  const uint8_t* center = blur + (long long)img * P.blur_img_stride + L.blur_off + (size_t)cy * L.pitch + cx;
+  const int4* pat = reinterpret_cast<const int4*>(g_brief_pattern) + 8 * lane;  // 32 ints = 16 points per lane
+  unsigned byte = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    int4 t = pat[q];  // one test: (x0,y0,x1,y1)
+    float px0 = __int2float_rn(t.x), py0 = __int2float_rn(t.y), px1 = __int2float_rn(t.z), py1 = __int2float_rn(t.w);
+    int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
+    int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
+    int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
+    int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
+    int t0 = center[iy0 * L.pitch + ix0], t1 = center[iy1 * L.pitch + ix1];
+    byte |= (unsigned)(t0 < t1) << q;
+  }
+  (res + P.res_off_desc[eye])[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
+}
+
+}  // namespace vk

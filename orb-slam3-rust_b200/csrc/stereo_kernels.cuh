@@ -1,0 +1,194 @@
+// Stereo correspondence + depth kernels, bit-exact with the reference's Rust loops:
+//   k_match            StereoProcessor::match_features   /root/reference/src/tracking/frame/stereo.rs:80-161
+//   k_match_finalize   Vector<DMatch> assembly (ascending left index) + triangulate   stereo.rs:144-157, 186-216
+//   k_hamming          descriptor_distance                stereo.rs:166-175
+//
+// match: one warp per left keypoint scans ALL right keypoints in index order (the reference has no row table);
+// right (u,v) and descriptors are staged in shared memory in chunks, descriptors padded to 9 words per row so that
+// 32 lanes reading 32 different rows hit 32 different banks.  Hamming = 8 x (xor + popc).  "first index wins" and
+// "second best counts duplicates" are reproduced by minimising (dist<<16 | idx) with __reduce_min_sync and taking
+// the minimum of everything except the winner as the runner-up.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vslam_params.h"
+
+namespace vk {
+
+#ifndef VSLAM_FULL
+#define VSLAM_FULL 0xffffffffu
+#endif
+
+constexpr int kMatchRightChunk = 1024;  // right keypoints staged per pass
+constexpr int kMatchLeftPerBlock = 64;  // 8 warps x 8 left keypoints
+
+struct FrameLayout {
+  unsigned char* base;      // result slab (device)
+  long long frame_stride;   // bytes per frame
+  int off_kp[2], off_desc[2], off_matches, off_pts, off_valid;
+  int cap;                  // per-image keypoint capacity of the slab
+};
+
+struct KpXY {  // first 8 bytes of cv::KeyPoint
+  float x, y;
+};
+
+__device__ __forceinline__ const float* kp_ptr(const FrameLayout& F, int frame, int eye, int i) {
+  return reinterpret_cast<const float*>(F.base + (long long)frame * F.frame_stride + F.off_kp[eye] + (size_t)i * 28);
+}
+
+// grid = (ceil(cap / 64), frames), block = 256.  ml[frame*cap + li] = (right idx or -1, best distance).
+__global__ void __launch_bounds__(256) k_match(const FrameLayout F, const StereoP S, int2* __restrict__ ml) {
+  __shared__ float2 s_xy[kMatchRightChunk];
+  __shared__ unsigned s_desc[kMatchRightChunk * 9];
+  __shared__ unsigned s_key[kMatchLeftPerBlock];
+  __shared__ unsigned s_second[kMatchLeftPerBlock];
+  const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned char* fb = F.base + (long long)frame * F.frame_stride;
+  const ResHdr* hdr = reinterpret_cast<const ResHdr*>(fb);
+  const int nL = min(hdr->n_kp[0], F.cap), nR = min(hdr->n_kp[1], F.cap);
+  const int l0 = blockIdx.x * kMatchLeftPerBlock;
+  if (l0 >= nL) return;
+  const unsigned TH = 100u;  // TH_HIGH, stereo.rs:10
+  if (tid < kMatchLeftPerBlock) {
+    s_key[tid] = (TH << 16) | 0xffffu;
+    s_second[tid] = TH;
+  }
+  const unsigned* descL = reinterpret_cast<const unsigned*>(fb + F.off_desc[0]);
+  const unsigned* descR = reinterpret_cast<const unsigned*>(fb + F.off_desc[1]);
+  for (int r0 = 0; r0 < nR; r0 += kMatchRightChunk) {
+    const int rc = min(kMatchRightChunk, nR - r0);
+    __syncthreads();
+    for (int i = tid; i < rc; i += 256) {
+      const float* k = kp_ptr(F, frame, 1, r0 + i);
+      s_xy[i] = make_float2(k[0], k[1]);
+    }
+    for (int i = tid; i < rc * 8; i += 256) s_desc[(i >> 3) * 9 + (i & 7)] = descR[(size_t)r0 * 8 + i];
+    __syncthreads();
+    for (int q = 0; q < kMatchLeftPerBlock / 8; ++q) {
+      const int ls = warp * (kMatchLeftPerBlock / 8) + q;  // slot inside the block
+      const int li = l0 + ls;
+      if (li >= nL) break;  // warp-uniform
+      const float* kl = kp_ptr(F, frame, 0, li);
+      const float ul = kl[0], vl = kl[1];
+      const float min_u = fmaxf(__fsub_rn(ul, S.max_disparity), 0.0f);
+      const float max_u = fminf(__fsub_rn(ul, S.min_disparity), __fdiv_rn(__fmul_rn((float)nR, ul), (float)nL));
+      unsigned dl[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dl[k] = descL[(size_t)li * 8 + k];
+      unsigned best = TH, second = TH, bidx = 0xffffu;
+      for (int r = lane; r < rc; r += 32) {
+        const float2 p = s_xy[r];
+        if (fabsf(__fsub_rn(vl, p.y)) > 2.0f) continue;
+        if (p.x < min_u || p.x > max_u) continue;
+        if (ul <= p.x) continue;
+        const unsigned* dr = s_desc + r * 9;
+        unsigned d = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d += __popc(dl[k] ^ dr[k]);
+        if (d < best) {
+          second = best;
+          best = d;
+          bidx = (unsigned)(r0 + r);
+        } else if (d < second) {
+          second = d;
+        }
+      }
+      const unsigned key = (best << 16) | bidx;
+      const unsigned kmin = __reduce_min_sync(VSLAM_FULL, key);
+      // runner-up = minimum over everything except the single winning element
+      const unsigned other = (key == kmin && best < TH) ? second : best;
+      const unsigned smin = __reduce_min_sync(VSLAM_FULL, other);
+      if (lane == 0) {
+        // merge this chunk's (best, second) summary into the running one (earlier chunk wins ties via idx)
+        const unsigned k0 = s_key[ls], s0 = s_second[ls];
+        const unsigned b0 = k0 >> 16, b1 = kmin >> 16;
+        s_key[ls] = min(k0, kmin);
+        s_second[ls] = min(min(s0, smin), max(b0, b1));
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < kMatchLeftPerBlock) {
+    const int li = l0 + tid;
+    if (li < nL) {
+      const unsigned key = s_key[tid], second = s_second[tid];
+      const unsigned best = key >> 16;
+      int idx = -1;
+      if (best < TH) {  // best_right_idx is Some(..)
+        if (__uint2float_rn(best) < __fmul_rn(0.9f, __uint2float_rn(second)) || second == TH) idx = (int)(key & 0xffffu);
+      }
+      ml[(long long)frame * F.cap + li] = make_int2(idx, (int)best);
+    }
+  }
+}
+
+// grid = frames, block = 256.  Ordered compaction of the per-left results into Vector<DMatch> + triangulation.
+__global__ void __launch_bounds__(256) k_match_finalize(const FrameLayout F, const StereoP S,
+                                                        const int2* __restrict__ ml) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* fb = F.base + (long long)frame * F.frame_stride;
+  ResHdr* hdr = reinterpret_cast<ResHdr*>(fb);
+  const int nL = min(hdr->n_kp[0], F.cap);
+  int4* matches = reinterpret_cast<int4*>(fb + F.off_matches);
+  double* pts = reinterpret_cast<double*>(fb + F.off_pts);
+  unsigned char* valid = fb + F.off_valid;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int b = 0; b < nL; b += 256) {
+    const int li = b + tid;
+    int2 m = make_int2(-1, 0);
+    if (li < nL) m = ml[(long long)frame * F.cap + li];
+    const bool has = m.x >= 0;
+    const unsigned bal = __ballot_sync(VSLAM_FULL, has);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int pos = s_base + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) pos += s_warp[w];
+    if (li < nL) {
+      double X = 0.0, Y = 0.0, Z = 0.0;
+      unsigned char ok = 0;
+      if (has) {
+        matches[pos] = make_int4(li, m.x, 0, __float_as_int(__int2float_rn(m.y)));
+        const float* kl = kp_ptr(F, frame, 0, li);
+        const float* kr = kp_ptr(F, frame, 1, m.x);
+        const double lx = (double)kl[0], ly = (double)kl[1], rx = (double)kr[0];
+        const double disp = __dsub_rn(lx, rx);
+        if (!(fabs(disp) < 0.5)) {
+          Z = __ddiv_rn(S.fxb, disp);
+          X = __ddiv_rn(__dmul_rn(__dsub_rn(lx, S.cx), Z), S.fx);
+          Y = __ddiv_rn(__dmul_rn(__dsub_rn(ly, S.cy), Z), S.fy);
+          ok = 1;
+        }
+      }
+      pts[3 * (size_t)li + 0] = X;
+      pts[3 * (size_t)li + 1] = Y;
+      pts[3 * (size_t)li + 2] = Z;
+      valid[li] = ok;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) hdr->n_matches = s_base;
+}
+
+// descriptor_distance for n pairs: one thread per pair (8 x xor+popc on 32-bit words).
+__global__ void k_hamming(const unsigned* __restrict__ a, const unsigned* __restrict__ b, int n,
+                          unsigned* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned d = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d += __popc(a[(size_t)i * 8 + k] ^ b[(size_t)i * 8 + k]);
+  out[i] = d;
+}
+
+}  // namespace vk

@@ -1,0 +1,59 @@
+// Internal parameter blocks shared by the host pipeline (vslam_b200.cu) and the kernels.
+// Passed BY VALUE as __grid_constant__ kernel parameters (constant bank, no extra load latency).
+#pragma once
+#include <stdint.h>
+
+#define VSLAM_MAX_LEVELS 12
+#define VSLAM_FAST_ROWS 16      // emission rows per FAST strip
+#define VSLAM_RESIZE_ROWS 8     // dst rows per resize strip
+#define VSLAM_BLUR_TW 128       // blur tile width
+#define VSLAM_BLUR_TH 32        // blur tile height
+#define VSLAM_DESC_BYTES 32
+
+// 8-byte corner record permuted by the selection replay: hi = float bits of the response, lo = (y<<16)|x.
+typedef unsigned long long vrec_t;
+
+struct LevelP {
+  int w, h, pitch;        // pitch: bytes per row, multiple of 16
+  int pyr_off;            // byte offset inside the per-image pyramid slab (levels >= 1; level 0 = the input image)
+  int blur_off;           // byte offset inside the per-image blurred slab (all levels)
+  float scale;            // layerScale[l]
+  int nfeat;              // nfeaturesPerLevel[l]
+  int xcoef_off, ycoef_off;  // u32 offsets into the resize coefficient table (levels >= 1)
+  int ex0, ex1, ey0, ey1; // emission region of FAST corners after runByImageBorder: [ex0,ex1) x [ey0,ey1)
+  int fast_strip0, fast_nstrips;   // strips of VSLAM_FAST_ROWS emission rows
+  int strip_cap;          // corner records per strip (worst case after NMS)
+  int rec_off;            // record offset of this level inside the per-image strip-record slab
+  int blur_tile0, blur_tx, blur_ty;  // first tile index, tiles in x, tiles in y
+};
+
+struct PyrP {
+  int nlevels;
+  int eyes;               // images per frame in this launch (2 = stereo, 1 = mono)
+  int in_pitch;           // row pitch of level-0 images
+  int fast_threshold;
+  int total_fast_strips;
+  int total_blur_tiles;
+  int kp_cap;             // per-image keypoint capacity
+  int sel_smem_cap;       // records the selection kernel can hold in shared memory
+  long long in_frame_stride;   // bytes between consecutive frames in the input (per eye base)
+  long long pyr_img_stride;    // bytes per image in the pyramid slab
+  long long blur_img_stride;   // bytes per image in the blurred slab
+  long long rec_img_stride;    // records per image in the strip-record slab
+  long long res_frame_stride;  // bytes per frame in the result slab
+  int res_off_kp[2], res_off_desc[2], res_off_matches, res_off_pts, res_off_valid;  // byte offsets in a frame's result
+  LevelP lv[VSLAM_MAX_LEVELS];
+};
+
+// Result-slab header (one per frame, first 32 bytes of the frame's result).
+struct ResHdr {
+  int n_kp[2];
+  int n_matches;
+  int status;
+  int pad[4];
+};
+
+struct StereoP {
+  float max_disparity, min_disparity;  // (fx*b/0.1) as f32, (fx*b/40) as f32   stereo.rs:89-90
+  double fxb, fx, fy, cx, cy;          // fx*baseline (f64 product), intrinsics
+};

@@ -1,0 +1,405 @@
+"""Host-side mirror of the reference's stereo front-end interface, over the C ABI (ctypes).
+
+Names, argument meaning and error behaviour follow /root/reference/src/tracking/frame/{stereo,camera}.rs and
+src/tracking/tracking_frame.rs so that tests read like tests of the reference:
+
+    StereoProcessor(camera, n_features)            <- StereoProcessor::new           stereo.rs:37
+    StereoProcessor.process(left, right, ts)       <- StereoProcessor::process       stereo.rs:52
+    FeatureSet / StereoFrame / CameraModel         <- stereo.rs:15-29, camera.rs:3-10
+    descriptor_distance(a, b)                      <- stereo.rs:166
+    Frame.from_stereo(stereo_frame)                <- tracking_frame.rs:194
+    FeatureGrid.get_features_in_area(x, y, r)      <- tracking_frame.rs:104
+    search_by_projection(...)                      <- tracker.rs:863-923 / 1093-1158
+    bf_match_crosscheck(query, train)              <- tracker.rs:1001-1010
+
+Errors: the reference returns anyhow::Result; here a non-zero C status raises VslamError carrying
+vslam_last_error().  There is no CPU path: without the CUDA library or a B200 every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import DMATCH_DTYPE, KP_DTYPE
+
+TH_HIGH = 100  # stereo.rs:10
+TH_LOW = 50  # stereo.rs:11
+NN_RATIO = 0.75  # stereo.rs:12
+
+
+class VslamError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"vslam_b200 status {status}: {message}")
+        self.status = status
+
+
+@dataclass(frozen=True)
+class CameraModel:  # camera.rs:3-10
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    baseline: float
+
+    @staticmethod
+    def from_k_and_baseline(k, baseline):  # camera.rs:13-21
+        k = np.asarray(k, dtype=np.float64)
+        return CameraModel(float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]), float(baseline))
+
+
+@dataclass
+class FeatureSet:  # stereo.rs:15-19
+    keypoints: np.ndarray  # KP_DTYPE [n]  (cv::KeyPoint layout)
+    descriptors: np.ndarray  # uint8 [n, 32]
+
+
+@dataclass
+class StereoFrame:  # stereo.rs:21-29
+    left_features: FeatureSet
+    right_features: FeatureSet
+    matches_lr: np.ndarray  # DMATCH_DTYPE [m], ascending query_idx
+    points_cam: np.ndarray  # float64 [n_left, 3]
+    points_valid: np.ndarray  # uint8 [n_left]  (Option tag of Vec<Option<Vector3<f64>>>)
+    timestamp_ns: int = 0
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check_image(img, w, h, name):
+    if not isinstance(img, np.ndarray) or img.dtype != np.uint8 or img.ndim != 2:
+        raise VslamError(_abi.ERR_INVALID_ARGUMENT, f"{name}: expected a 2-D uint8 (8UC1) array")
+    if img.shape != (h, w):
+        raise VslamError(_abi.ERR_INVALID_ARGUMENT, f"{name}: expected {w}x{h}, got {img.shape[1]}x{img.shape[0]}")
+    if img.strides[1] != 1:
+        raise VslamError(_abi.ERR_INVALID_ARGUMENT, f"{name}: pixels of a row must be contiguous")
+    return img
+
+
+class _OutBuffers:
+    """Caller-owned, capacity-checked output arrays for n frames (vslam_frame_out)."""
+
+    def __init__(self, n, cap):
+        self.n, self.cap = n, cap
+        self.kpl = np.zeros((n, cap), dtype=KP_DTYPE)
+        self.kpr = np.zeros((n, cap), dtype=KP_DTYPE)
+        self.dl = np.zeros((n, cap, 32), dtype=np.uint8)
+        self.dr = np.zeros((n, cap, 32), dtype=np.uint8)
+        self.m = np.zeros((n, cap), dtype=DMATCH_DTYPE)
+        self.pts = np.zeros((n, cap, 3), dtype=np.float64)
+        self.valid = np.zeros((n, cap), dtype=np.uint8)
+        self.outs = (_abi.FrameOut * n)()
+        for i in range(n):
+            o = self.outs[i]
+            o.capacity = cap
+            o.kp_left = self.kpl[i].ctypes.data
+            o.kp_right = self.kpr[i].ctypes.data
+            o.desc_left = self.dl[i].ctypes.data
+            o.desc_right = self.dr[i].ctypes.data
+            o.matches = self.m[i].ctypes.data
+            o.points_cam = self.pts[i].ctypes.data
+            o.points_valid = self.valid[i].ctypes.data
+
+    def frame(self, i, copy=True):
+        o = self.outs[i]
+        nl, nr, nm = o.n_left, o.n_right, o.n_matches
+        c = (lambda a: a.copy()) if copy else (lambda a: a)
+        return StereoFrame(
+            FeatureSet(c(self.kpl[i, :nl]), c(self.dl[i, :nl])),
+            FeatureSet(c(self.kpr[i, :nr]), c(self.dr[i, :nr])),
+            c(self.m[i, :nm]), c(self.pts[i, :nl]), c(self.valid[i, :nl]), int(o.timestamp_ns),
+        )
+
+
+class StereoProcessor:
+    """B200 drop-in for the reference's StereoProcessor (stereo.rs:31-161)."""
+
+    def __init__(self, camera: CameraModel, n_features: int, width: int = 752, height: int = 480, device: int = 0,
+                 max_batch: int = 64, n_levels: int = 8, scale_factor: float = 1.2, edge_threshold: int = 31,
+                 fast_threshold: int = 20, keypoint_capacity: int = 0):
+        self._lib = _abi.lib()
+        self._h = C.c_void_p()
+        cfg = _abi.Config()
+        cfg.abi_version = _abi.ABI_VERSION
+        cfg.width, cfg.height, cfg.n_features = int(width), int(height), int(n_features)
+        cfg.n_levels, cfg.scale_factor = int(n_levels), float(scale_factor)
+        cfg.edge_threshold, cfg.fast_threshold = int(edge_threshold), int(fast_threshold)
+        cfg.camera = _abi.Camera(camera.fx, camera.fy, camera.cx, camera.cy, camera.baseline)
+        cfg.device, cfg.max_batch, cfg.keypoint_capacity = int(device), int(max_batch), int(keypoint_capacity)
+        rc = self._lib.vslam_create(C.byref(cfg), C.byref(self._h))
+        if rc != _abi.OK:
+            msg = self._lib.vslam_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise VslamError(rc, msg)
+        self.camera, self.n_features, self.width, self.height = camera, n_features, width, height
+        self.max_batch = max_batch
+        self.capacity = int(self._lib.vslam_keypoint_capacity(self._h))
+        self.n_levels = n_levels
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vslam_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _raise(self, rc):
+        raise VslamError(rc, self._lib.vslam_last_error(self._h).decode())
+
+    # -- StereoProcessor::process (stereo.rs:52-66)
+    def process(self, left: np.ndarray, right: np.ndarray, timestamp_ns: int = 0) -> StereoFrame:
+        left = _check_image(left, self.width, self.height, "left")
+        right = _check_image(right, self.width, self.height, "right")
+        ob = _OutBuffers(1, self.capacity)
+        rc = self._lib.vslam_process(self._h, _ptr(left), left.strides[0], _ptr(right), right.strides[0],
+                                     int(timestamp_ns), ob.outs)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return ob.frame(0)
+
+    # -- offline batch form of the caller loop (main.rs:66-85)
+    def process_batch(self, lefts, rights, timestamps_ns=None, out: _OutBuffers | None = None, copy=True):
+        """lefts/rights: uint8 arrays [n, H, W] (or lists of [H, W]) in HOST memory -> list[StereoFrame]."""
+        n = len(lefts)
+        if n != len(rights):
+            raise VslamError(_abi.ERR_INVALID_ARGUMENT, "left/right batch sizes differ")
+        if n == 0:
+            return []
+        lp = (C.c_void_p * n)()
+        rp = (C.c_void_p * n)()
+        stride = None
+        for i in range(n):
+            l = _check_image(lefts[i], self.width, self.height, f"left[{i}]")
+            r = _check_image(rights[i], self.width, self.height, f"right[{i}]")
+            if stride is None:
+                stride = l.strides[0]
+            if l.strides[0] != stride or r.strides[0] != stride:
+                raise VslamError(_abi.ERR_INVALID_ARGUMENT, "all images of a batch must share one row stride")
+            lp[i], rp[i] = l.ctypes.data, r.ctypes.data
+        ts = None
+        if timestamps_ns is not None:
+            ts = np.ascontiguousarray(timestamps_ns, dtype=np.uint64)
+        ob = out or _OutBuffers(n, self.capacity)
+        rc = self._lib.vslam_process_batch(self._h, n, lp, rp, stride, _ptr(ts) if ts is not None else None, ob.outs)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return [ob.frame(i, copy) for i in range(n)]
+
+    def new_output_buffers(self, n):
+        return _OutBuffers(n, self.capacity)
+
+    def process_batch_raw(self, n, left_ptrs, right_ptrs, stride, out: _OutBuffers):
+        """Zero-overhead variant for benchmarking: pre-built pointer arrays, results land in `out`."""
+        rc = self._lib.vslam_process_batch(self._h, n, left_ptrs, right_ptrs, stride, None, out.outs)
+        if rc != _abi.OK:
+            self._raise(rc)
+
+    def process_batch_device(self, n, left_dev_ptr, right_dev_ptr, image_stride, row_stride, out: _OutBuffers | None):
+        """Images already resident in HBM (device pointers as ints).  out=None keeps results on the device."""
+        rc = self._lib.vslam_process_batch_device(self._h, int(n), C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr),
+                                                  int(image_stride), int(row_stride), None,
+                                                  out.outs if out is not None else None)
+        if rc != _abi.OK:
+            self._raise(rc)
+
+    # -- detect_features (stereo.rs:68-78)
+    def detect_features(self, image: np.ndarray) -> FeatureSet:
+        image = _check_image(image, self.width, self.height, "image")
+        kps = np.zeros(self.capacity, dtype=KP_DTYPE)
+        desc = np.zeros((self.capacity, 32), dtype=np.uint8)
+        n = C.c_int(0)
+        rc = self._lib.vslam_detect_and_compute(self._h, _ptr(image), image.strides[0], _ptr(kps), _ptr(desc),
+                                                self.capacity, C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return FeatureSet(kps[: n.value].copy(), desc[: n.value].copy())
+
+    # -- match_features (stereo.rs:80-161)
+    def match_features(self, left: FeatureSet, right: FeatureSet) -> np.ndarray:
+        kl = np.ascontiguousarray(left.keypoints, dtype=KP_DTYPE)
+        kr = np.ascontiguousarray(right.keypoints, dtype=KP_DTYPE)
+        dl = np.ascontiguousarray(left.descriptors, dtype=np.uint8)
+        dr = np.ascontiguousarray(right.descriptors, dtype=np.uint8)
+        m = np.zeros(max(len(kl), 1), dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        rc = self._lib.vslam_match_features(self._h, _ptr(kl), _ptr(dl), len(kl), _ptr(kr), _ptr(dr), len(kr), _ptr(m),
+                                            C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return m[: n.value].copy()
+
+    # -- triangulate (stereo.rs:186-216)
+    def triangulate(self, left: FeatureSet, right: FeatureSet, matches: np.ndarray):
+        kl = np.ascontiguousarray(left.keypoints, dtype=KP_DTYPE)
+        kr = np.ascontiguousarray(right.keypoints, dtype=KP_DTYPE)
+        m = np.ascontiguousarray(matches, dtype=DMATCH_DTYPE)
+        pts = np.zeros((max(len(kl), 1), 3), dtype=np.float64)
+        valid = np.zeros(max(len(kl), 1), dtype=np.uint8)
+        rc = self._lib.vslam_triangulate(self._h, _ptr(kl), len(kl), _ptr(kr), len(kr), _ptr(m), len(m), _ptr(pts),
+                                         _ptr(valid))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return pts[: len(kl)], valid[: len(kl)]
+
+    # -- descriptor_distance (stereo.rs:166-175), batched
+    def descriptor_distances(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32)
+        if len(a) != len(b):
+            raise VslamError(_abi.ERR_INVALID_ARGUMENT, "descriptor batches differ in length")
+        out = np.zeros(max(len(a), 1), dtype=np.uint32)
+        rc = self._lib.vslam_descriptor_distance(self._h, _ptr(a), _ptr(b), len(a), _ptr(out))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return out[: len(a)]
+
+    # -- FeatureGrid (tracking_frame.rs:52-128)
+    def grid_build(self, keypoints, img_w=752.0, img_h=480.0):
+        kp = np.ascontiguousarray(keypoints, dtype=KP_DTYPE)
+        cs = np.zeros(_abi.GRID_COLS * _abi.GRID_ROWS + 1, dtype=np.int32)
+        items = np.zeros(max(len(kp), 1), dtype=np.int32)
+        rc = self._lib.vslam_grid_build(self._h, _ptr(kp), len(kp), float(img_w), float(img_h), _ptr(cs), _ptr(items))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return cs, items[: len(kp)]
+
+    def grid_query(self, keypoints, xyr, img_w=752.0, img_h=480.0):
+        kp = np.ascontiguousarray(keypoints, dtype=KP_DTYPE)
+        q = np.ascontiguousarray(xyr, dtype=np.float64).reshape(-1, 3)
+        cap = max(len(kp) * max(len(q), 1), 1)
+        start = np.zeros(len(q) + 1, dtype=np.int32)
+        items = np.zeros(cap, dtype=np.int32)
+        rc = self._lib.vslam_grid_query(self._h, _ptr(kp), len(kp), float(img_w), float(img_h), _ptr(q), len(q),
+                                        _ptr(start), _ptr(items), cap)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return [items[start[i]: start[i + 1]].copy() for i in range(len(q))]
+
+    # -- projection searches (tracker.rs:863-923, 1093-1158)
+    def search_by_projection(self, features: FeatureSet, uv, mp_desc, mode=_abi.SEARCH_LOCAL_MAP, radius=15.0,
+                             th_high=TH_HIGH, nn_ratio=NN_RATIO, img_w=752.0, img_h=480.0, bound_w=None, bound_h=None):
+        kp = np.ascontiguousarray(features.keypoints, dtype=KP_DTYPE)
+        d = np.ascontiguousarray(features.descriptors, dtype=np.uint8)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        md = np.ascontiguousarray(mp_desc, dtype=np.uint8).reshape(-1, 32)
+        M = len(uv)
+        sp = _abi.SearchParams(int(mode), float(radius), int(th_high), float(nn_ratio), float(img_w), float(img_h),
+                               float(2.0 * self.camera.cx if bound_w is None else bound_w),
+                               float(2.0 * self.camera.cy if bound_h is None else bound_h))
+        idx = np.full(max(M, 1), -1, dtype=np.int32)
+        dist = np.full(max(M, 1), -1, dtype=np.int32)
+        rc = self._lib.vslam_search_by_projection(self._h, _ptr(kp), _ptr(d), len(kp), _ptr(uv), _ptr(md), M,
+                                                  C.byref(sp), _ptr(idx), _ptr(dist))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return idx[:M], dist[:M]
+
+    # -- BFMatcher(NORM_HAMMING, crossCheck=true) (tracker.rs:1001-1010)
+    def bf_match_crosscheck(self, query, train):
+        q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, dtype=np.uint8).reshape(-1, 32)
+        m = np.zeros(max(len(q), 1), dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        rc = self._lib.vslam_bf_match_crosscheck(self._h, _ptr(q), len(q), _ptr(t), len(t), _ptr(m), C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return m[: n.value].copy()
+
+    # -- introspection (parity tests / profiling)
+    def level_info(self, level):
+        w, h, s, n = C.c_int(), C.c_int(), C.c_float(), C.c_int()
+        rc = self._lib.vslam_level_info(self._h, level, C.byref(w), C.byref(h), C.byref(s), C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return w.value, h.value, s.value, n.value
+
+    def debug_level_image(self, stage, image, level):
+        w, h, _, _ = self.level_info(level)
+        dst = np.zeros((h, w), dtype=np.uint8)
+        rc = self._lib.vslam_debug_level_image(self._h, stage, image, level, _ptr(dst), dst.size)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return dst
+
+    def debug_fast_corners(self, image, level):
+        w, h, _, _ = self.level_info(level)
+        cap = w * h // 4 + 16
+        buf = np.zeros((cap, 3), dtype=np.int32)
+        n = C.c_int(0)
+        rc = self._lib.vslam_debug_fast_corners(self._h, image, level, _ptr(buf), cap, C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return buf[: n.value].copy()
+
+    def kernel_launches(self):
+        return int(self._lib.vslam_kernel_launches(self._h))
+
+    def set_profiling(self, enabled):
+        self._lib.vslam_set_profiling(self._h, int(bool(enabled)))
+
+    def last_stage_ms(self):
+        ms = np.zeros(7, dtype=np.float32)
+        self._lib.vslam_last_stage_ms(self._h, _ptr(ms))
+        return ms
+
+
+def descriptor_distance(processor: StereoProcessor, desc1, desc2) -> int:
+    """descriptor_distance(&desc1, &desc2) (stereo.rs:166): Hamming distance of two 32-byte descriptors."""
+    return int(processor.descriptor_distances(np.asarray(desc1).reshape(1, 32), np.asarray(desc2).reshape(1, 32))[0])
+
+
+class FeatureGrid:
+    """FeatureGrid (tracking_frame.rs:23-128): 64x48 cells; built and queried on the GPU."""
+
+    GRID_COLS, GRID_ROWS = 64, 48
+
+    def __init__(self, processor: StereoProcessor, keypoints, img_width=752.0, img_height=480.0):
+        self._p, self._kp, self._w, self._h = processor, keypoints, float(img_width), float(img_height)
+        self.cell_start, self.cell_items = processor.grid_build(keypoints, img_width, img_height)
+
+    def get_features_in_area(self, x, y, r):
+        return self._p.grid_query(self._kp, [[x, y, r]], self._w, self._h)[0]
+
+
+@dataclass
+class Frame:
+    """Tracking Frame (tracking_frame.rs:172-226)."""
+
+    timestamp_ns: int
+    features: FeatureSet
+    points_cam: np.ndarray
+    points_valid: np.ndarray
+    grid: FeatureGrid
+    map_point_matches: list = field(default_factory=list)
+
+    @staticmethod
+    def from_stereo(processor: StereoProcessor, stereo: StereoFrame):
+        # EuRoC dimensions are hard-coded in the reference (tracking_frame.rs:194-197)
+        return Frame.from_stereo_with_size(processor, stereo, 752.0, 480.0)
+
+    @staticmethod
+    def from_stereo_with_size(processor, stereo, img_width, img_height):
+        n = len(stereo.left_features.keypoints)
+        grid = FeatureGrid(processor, stereo.left_features.keypoints, img_width, img_height)
+        return Frame(stereo.timestamp_ns, stereo.left_features, stereo.points_cam, stereo.points_valid, grid, [None] * n)
+
+    def num_features(self):
+        return len(self.features.keypoints)
+
+    def keypoints(self):
+        return self.features.keypoints
