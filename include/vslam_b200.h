@@ -210,6 +210,9 @@ uint64_t vslam_kernel_launches(vslam_handle h);
  * [0]=pyramid [1]=fast [2]=select+harris+angle [3]=blur [4]=brief [5]=match+triangulate [6]=total kernels.
  * Only filled when profiling was enabled with vslam_set_profiling(h,1) (it serialises the pipeline). */
 int vslam_set_profiling(vslam_handle h, int enabled);
+/* Device time (ms) of the last vslam_process_batch* call: CUDA events recorded on the handle's own streams, from
+ * before the first chunk's first operation to after the last operation of every stream (copies included). */
+float vslam_last_batch_ms(vslam_handle h);
 int vslam_last_stage_ms(vslam_handle h, float* ms7);
 
 #ifdef __cplusplus

@@ -53,34 +53,26 @@ int vslam_descriptor_distance(vslam_handle h, const uint8_t* a, const uint8_t* b
   return VSLAM_OK;
 }
 
-// Build a one-frame result slab (same layout as the pipeline's) around caller-provided features.
+// Build a one-frame result set (same SoA layout as the pipeline's) around caller-provided features.
 static int stage_features(vslam_handle h, const vslam_keypoint* kl, const uint8_t* dl, int nl, const vslam_keypoint* kr,
-                          const uint8_t* dr, int nr, vk::FrameLayout* F, int2** ml, cudaStream_t st) {
-  const size_t cap = (size_t)std::max(std::max(nl, nr), 1);
-  size_t o = sizeof(ResHdr);
-  vk::FrameLayout L;
-  L.off_kp[0] = (int)o; o += align_up(cap * 28, 16);
-  L.off_kp[1] = (int)o; o += align_up(cap * 28, 16);
-  L.off_desc[0] = (int)o; o += cap * 32;
-  L.off_desc[1] = (int)o; o += cap * 32;
-  L.off_matches = (int)o; o += cap * 16;
-  L.off_pts = (int)o; o += cap * 24;
-  L.off_valid = (int)o; o += align_up(cap, 16);
-  L.frame_stride = (long long)align_up(o, 256);
-  L.cap = (int)cap;
-  int rc = arena_begin(h, pad256((size_t)L.frame_stride) + pad256(cap * sizeof(int2)));
+                          const uint8_t* dr, int nr, FrameLayout* F, int2** ml, cudaStream_t st) {
+  const int cap = std::max(std::max(nl, nr), 1);
+  FrameLayout L;
+  const size_t bytes = carve_results(nullptr, 1, cap, &L);
+  int rc = arena_begin(h, pad256(bytes) + pad256((size_t)cap * sizeof(int2)));
   if (rc) return rc;
-  L.base = arena_take<unsigned char>(h, (size_t)L.frame_stride);
-  *ml = arena_take<int2>(h, cap);
+  unsigned char* base = arena_take<unsigned char>(h, bytes);
+  carve_results(base, 1, cap, &L);
+  *ml = arena_take<int2>(h, (size_t)cap);
   ResHdr hdr;
   memset(&hdr, 0, sizeof(hdr));
   hdr.n_kp[0] = nl;
   hdr.n_kp[1] = nr;
-  CU_TRY(h, cudaMemcpyAsync(L.base, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
-  if (nl > 0) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_kp[0], kl, (size_t)nl * 28, cudaMemcpyHostToDevice, st));
-  if (nr > 0) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_kp[1], kr, (size_t)nr * 28, cudaMemcpyHostToDevice, st));
-  if (nl > 0 && dl) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_desc[0], dl, (size_t)nl * 32, cudaMemcpyHostToDevice, st));
-  if (nr > 0 && dr) CU_TRY(h, cudaMemcpyAsync(L.base + L.off_desc[1], dr, (size_t)nr * 32, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(L.hdr, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+  if (nl > 0) CU_TRY(h, cudaMemcpyAsync(L.kp[0], kl, (size_t)nl * 28, cudaMemcpyHostToDevice, st));
+  if (nr > 0) CU_TRY(h, cudaMemcpyAsync(L.kp[1], kr, (size_t)nr * 28, cudaMemcpyHostToDevice, st));
+  if (nl > 0 && dl) CU_TRY(h, cudaMemcpyAsync(L.desc[0], dl, (size_t)nl * 32, cudaMemcpyHostToDevice, st));
+  if (nr > 0 && dr) CU_TRY(h, cudaMemcpyAsync(L.desc[1], dr, (size_t)nr * 32, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaStreamSynchronize(st));  // hdr is a stack variable
   *F = L;
   return VSLAM_OK;
@@ -98,7 +90,7 @@ int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const ui
   if (n_left == 0) return VSLAM_OK;
   CU_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->slots[0].stream;
-  vk::FrameLayout F;
+  FrameLayout F;
   int2* ml;
   int rc = stage_features(h, kp_left, desc_left, n_left, kp_right, desc_right, n_right, &F, &ml, st);
   if (rc) return rc;
@@ -107,11 +99,11 @@ int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const ui
   vk::k_match_finalize<<<1, 256, 0, st>>>(F, h->S, ml);
   h->launches += 2;
   ResHdr hdr;
-  CU_TRY(h, cudaMemcpyAsync(&hdr, F.base, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(&hdr, F.hdr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
   *n_matches = hdr.n_matches;
   if (hdr.n_matches > 0)
-    CU_TRY(h, cudaMemcpy(matches, F.base + F.off_matches, (size_t)hdr.n_matches * 16, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(matches, F.matches, (size_t)hdr.n_matches * 16, cudaMemcpyDeviceToHost));
   return VSLAM_OK;
 }
 
@@ -125,7 +117,7 @@ int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left,
   if (n_left == 0) return VSLAM_OK;
   CU_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->slots[0].stream;
-  vk::FrameLayout F;
+  FrameLayout F;
   int2* ml;
   int rc = stage_features(h, kp_left, nullptr, n_left, kp_right, nullptr, n_right, &F, &ml, st);
   if (rc) return rc;
@@ -140,8 +132,8 @@ int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left,
   CU_TRY(h, cudaMemcpyAsync(ml, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
   vk::k_match_finalize<<<1, 256, 0, st>>>(F, h->S, ml);
   h->launches++;
-  CU_TRY(h, cudaMemcpyAsync(points, F.base + F.off_pts, (size_t)n_left * 24, cudaMemcpyDeviceToHost, st));
-  CU_TRY(h, cudaMemcpyAsync(valid, F.base + F.off_valid, (size_t)n_left, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(points, F.pts, (size_t)n_left * 24, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(valid, F.valid, (size_t)n_left, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
   return VSLAM_OK;
 }

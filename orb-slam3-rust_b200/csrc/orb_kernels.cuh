@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128) k_select(const __grid_constant__ PyrP P, 
                                                 const int* __restrict__ strip_cnt, vrec_t* __restrict__ strip_rec,
                                                 uint32_t* __restrict__ glists, LvlKp* __restrict__ lvl_kp,
                                                 int* __restrict__ lvl_cnt, float harris_scale4,
-                                                unsigned char* __restrict__ results) {
+                                                const FrameLayout F) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_off[128];
   __shared__ int s_n;
@@ -603,10 +603,7 @@ __global__ void __launch_bounds__(128) k_select(const __grid_constant__ PyrP P, 
   __syncthreads();
   int m2 = s_n;
   if (m2 > P.kp_cap) {  // more ties than the handle was sized for: flag, keep the first kp_cap
-    if (tid == 0) {
-      ResHdr* hdr = reinterpret_cast<ResHdr*>(results + (long long)(img / P.eyes) * P.res_frame_stride);
-      atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
-    }
+    if (tid == 0) atomicMax(&F.hdr[img / P.eyes].status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
     m2 = P.kp_cap;
   }
 
@@ -756,11 +753,10 @@ struct __align__(4) KeyPoint28 {
 
 __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ blur,
                                                const LvlKp* __restrict__ lvl_kp, const int* __restrict__ lvl_cnt,
-                                               unsigned char* __restrict__ results) {
+                                               const FrameLayout F) {
   const int img = blockIdx.y, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int frame = img / P.eyes, eye = img - frame * P.eyes;
-  unsigned char* res = results + (long long)frame * P.res_frame_stride;
   const int* cnt = lvl_cnt + (long long)img * P.nlevels;
   int total = 0, l = -1, jl = 0;
   for (int k = 0; k < P.nlevels; ++k) {
@@ -771,7 +767,7 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     }
     total += c;
   }
-  ResHdr* hdr = reinterpret_cast<ResHdr*>(res);
+  ResHdr* hdr = F.hdr + frame;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->n_kp[eye] = min(total, P.kp_cap);
     if (total > P.kp_cap) atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
@@ -789,7 +785,7 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     o.response = kp.resp;
     o.octave = l;
     o.class_id = -1;
-    reinterpret_cast<KeyPoint28*>(res + P.res_off_kp[eye])[j] = o;
+    reinterpret_cast<KeyPoint28*>(F.kp[eye] + (long long)frame * F.kp_stride)[j] = o;
   }
   // angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)   (double cos/sin of the f32 angle)
   const float rad = __fmul_rn(kp.angle, (float)(3.141592653589793238462643383279502884 / 180.0));
@@ -808,7 +804,7 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     int t0 = center[iy0 * L.pitch + ix0], t1 = center[iy1 * L.pitch + ix1];
     byte |= (unsigned)(t0 < t1) << q;
   }
-  (res + P.res_off_desc[eye])[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
+  (F.desc[eye] + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
 }
 
 }  // namespace vk

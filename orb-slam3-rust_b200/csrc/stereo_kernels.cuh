@@ -23,19 +23,12 @@ namespace vk {
 constexpr int kMatchRightChunk = 1024;  // right keypoints staged per pass
 constexpr int kMatchLeftPerBlock = 64;  // 8 warps x 8 left keypoints
 
-struct FrameLayout {
-  unsigned char* base;      // result slab (device)
-  long long frame_stride;   // bytes per frame
-  int off_kp[2], off_desc[2], off_matches, off_pts, off_valid;
-  int cap;                  // per-image keypoint capacity of the slab
-};
-
 struct KpXY {  // first 8 bytes of cv::KeyPoint
   float x, y;
 };
 
 __device__ __forceinline__ const float* kp_ptr(const FrameLayout& F, int frame, int eye, int i) {
-  return reinterpret_cast<const float*>(F.base + (long long)frame * F.frame_stride + F.off_kp[eye] + (size_t)i * 28);
+  return reinterpret_cast<const float*>(F.kp[eye] + (long long)frame * F.kp_stride + (size_t)i * 28);
 }
 
 // grid = (ceil(cap / 64), frames), block = 256.  ml[frame*cap + li] = (right idx or -1, best distance).
@@ -45,8 +38,7 @@ __global__ void __launch_bounds__(256) k_match(const FrameLayout F, const Stereo
   __shared__ unsigned s_key[kMatchLeftPerBlock];
   __shared__ unsigned s_second[kMatchLeftPerBlock];
   const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned char* fb = F.base + (long long)frame * F.frame_stride;
-  const ResHdr* hdr = reinterpret_cast<const ResHdr*>(fb);
+  const ResHdr* hdr = F.hdr + frame;
   const int nL = min(hdr->n_kp[0], F.cap), nR = min(hdr->n_kp[1], F.cap);
   const int l0 = blockIdx.x * kMatchLeftPerBlock;
   if (l0 >= nL) return;
@@ -55,8 +47,8 @@ __global__ void __launch_bounds__(256) k_match(const FrameLayout F, const Stereo
     s_key[tid] = (TH << 16) | 0xffffu;
     s_second[tid] = TH;
   }
-  const unsigned* descL = reinterpret_cast<const unsigned*>(fb + F.off_desc[0]);
-  const unsigned* descR = reinterpret_cast<const unsigned*>(fb + F.off_desc[1]);
+  const unsigned* descL = reinterpret_cast<const unsigned*>(F.desc[0] + (long long)frame * F.desc_stride);
+  const unsigned* descR = reinterpret_cast<const unsigned*>(F.desc[1] + (long long)frame * F.desc_stride);
   for (int r0 = 0; r0 < nR; r0 += kMatchRightChunk) {
     const int rc = min(kMatchRightChunk, nR - r0);
     __syncthreads();
@@ -130,12 +122,11 @@ __global__ void __launch_bounds__(256) k_match_finalize(const FrameLayout F, con
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned char* fb = F.base + (long long)frame * F.frame_stride;
-  ResHdr* hdr = reinterpret_cast<ResHdr*>(fb);
+  ResHdr* hdr = F.hdr + frame;
   const int nL = min(hdr->n_kp[0], F.cap);
-  int4* matches = reinterpret_cast<int4*>(fb + F.off_matches);
-  double* pts = reinterpret_cast<double*>(fb + F.off_pts);
-  unsigned char* valid = fb + F.off_valid;
+  int4* matches = reinterpret_cast<int4*>(F.matches + (long long)frame * F.matches_stride);
+  double* pts = reinterpret_cast<double*>(F.pts + (long long)frame * F.pts_stride);
+  unsigned char* valid = F.valid + (long long)frame * F.valid_stride;
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int b = 0; b < nL; b += 256) {

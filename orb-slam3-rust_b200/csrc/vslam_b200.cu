@@ -46,10 +46,14 @@ struct Slot {
   uint32_t* d_glists = nullptr;
   vk::LvlKp* d_lvl_kp = nullptr;
   int* d_lvl_cnt = nullptr;
-  unsigned char* d_res = nullptr;
+  unsigned char* d_res = nullptr;  // one block, carved into the SoA result arrays (d_lay)
+  FrameLayout d_lay;
   int2* d_ml = nullptr;
   uint8_t* h_in = nullptr;         // pinned
-  unsigned char* h_res = nullptr;  // pinned
+  unsigned char* h_res = nullptr;  // pinned mirror of d_res (h_lay)
+  FrameLayout h_lay;
+  size_t res_bytes = 0;
+  bool direct_out = false;         // D2H went straight into the caller's arrays
   // in-flight chunk bookkeeping
   int frames = 0;
   int first_frame = 0;
@@ -78,8 +82,15 @@ struct vslam_handle_s {
   bool profiling = false;
   float stage_ms[7] = {0};
   cudaEvent_t ev[8] = {nullptr};
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr};
+  float last_batch_ms = 0.f;
   int last_slot = 0;       // slot holding the most recent chunk (debug accessors)
   int last_frames = 0;
+  // geometry of the most recent chunk (debug accessors re-run k_fast on it)
+  const uint8_t* last_in_l = nullptr;
+  const uint8_t* last_in_r = nullptr;
+  long long last_frame_stride = 0;
+  int last_pitch = 0, last_eyes = 2;
   unsigned char* arena_base = nullptr;  // grow-only device scratch of the stand-alone entry points
   size_t arena_cap = 0, arena_used = 0;
 };
@@ -231,19 +242,6 @@ int build_params(vslam_handle h) {
     volatile float s4 = s3 * s;
     h->harris_scale4 = s4;
   }
-  // result slab layout
-  {
-    size_t o = sizeof(ResHdr);
-    const size_t kc = (size_t)h->kp_cap;
-    P.res_off_kp[0] = (int)o; o += align_up(kc * 28, 16);
-    P.res_off_kp[1] = (int)o; o += align_up(kc * 28, 16);
-    P.res_off_desc[0] = (int)o; o += kc * 32;
-    P.res_off_desc[1] = (int)o; o += kc * 32;
-    P.res_off_matches = (int)o; o += kc * 16;
-    P.res_off_pts = (int)o; o += kc * 24;
-    P.res_off_valid = (int)o; o += align_up(kc, 16);
-    P.res_frame_stride = (long long)align_up(o, 256);
-  }
   // stereo constants (stereo.rs:84-90)
   {
     const vslam_camera& cam = c.camera;
@@ -256,6 +254,32 @@ int build_params(vslam_handle h) {
     h->S.cy = cam.cy;
   }
   return VSLAM_OK;
+}
+
+// Carve the SoA result arrays for `nfr` frames out of one block; returns the block size.
+size_t carve_results(unsigned char* base, size_t nfr, int cap, FrameLayout* F) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + o : nullptr;
+    o += align_up(bytes, 256);
+    return p;
+  };
+  const size_t kc = (size_t)cap;
+  F->cap = cap;
+  F->kp_stride = (long long)(kc * 28);
+  F->desc_stride = (long long)(kc * 32);
+  F->matches_stride = (long long)(kc * 16);
+  F->pts_stride = (long long)(kc * 24);
+  F->valid_stride = (long long)kc;
+  F->hdr = reinterpret_cast<ResHdr*>(take(nfr * sizeof(ResHdr)));
+  F->kp[0] = take(nfr * kc * 28);
+  F->kp[1] = take(nfr * kc * 28);
+  F->desc[0] = take(nfr * kc * 32);
+  F->desc[1] = take(nfr * kc * 32);
+  F->matches = take(nfr * kc * 16);
+  F->pts = take(nfr * kc * 24);
+  F->valid = take(nfr * kc);
+  return o;
 }
 
 int alloc_slot(vslam_handle h, Slot& s) {
@@ -271,11 +295,15 @@ int alloc_slot(vslam_handle h, Slot& s) {
   CU_TRY(h, cudaMalloc(&s.d_glists, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * 2 * sizeof(uint32_t)));
   CU_TRY(h, cudaMalloc(&s.d_lvl_kp, nimg * P.nlevels * (size_t)h->kp_cap * sizeof(vk::LvlKp)));
   CU_TRY(h, cudaMalloc(&s.d_lvl_cnt, nimg * P.nlevels * sizeof(int)));
-  CU_TRY(h, cudaMalloc(&s.d_res, nfr * (size_t)P.res_frame_stride));
+  FrameLayout tmp;
+  s.res_bytes = carve_results(nullptr, nfr, h->kp_cap, &tmp);
+  CU_TRY(h, cudaMalloc(&s.d_res, s.res_bytes));
   CU_TRY(h, cudaMalloc(&s.d_ml, nfr * (size_t)h->kp_cap * sizeof(int2)));
   CU_TRY(h, cudaMallocHost(&s.h_in, nimg * h->in_img_bytes));
-  CU_TRY(h, cudaMallocHost(&s.h_res, nfr * (size_t)P.res_frame_stride));
-  CU_TRY(h, cudaMemset(s.d_res, 0, nfr * (size_t)P.res_frame_stride));
+  CU_TRY(h, cudaMallocHost(&s.h_res, s.res_bytes));
+  CU_TRY(h, cudaMemset(s.d_res, 0, s.res_bytes));
+  carve_results(s.d_res, nfr, h->kp_cap, &s.d_lay);
+  carve_results(s.h_res, nfr, h->kp_cap, &s.h_lay);
   return VSLAM_OK;
 }
 
@@ -290,21 +318,6 @@ void free_slot(Slot& s) {
   s = Slot();
 }
 
-vk::FrameLayout frame_layout(const PyrP& P, unsigned char* base) {
-  vk::FrameLayout F;
-  F.base = base;
-  F.frame_stride = P.res_frame_stride;
-  F.off_kp[0] = P.res_off_kp[0];
-  F.off_kp[1] = P.res_off_kp[1];
-  F.off_desc[0] = P.res_off_desc[0];
-  F.off_desc[1] = P.res_off_desc[1];
-  F.off_matches = P.res_off_matches;
-  F.off_pts = P.res_off_pts;
-  F.off_valid = P.res_off_valid;
-  F.cap = P.kp_cap;
-  return F;
-}
-
 // Enqueue every kernel of one chunk on the slot's stream.  in_l / in_r: device pointers of the first frame's
 // left / right level-0 image; frames `frame_stride` bytes apart, rows `pitch` bytes apart.
 int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* in_l, const uint8_t* in_r,
@@ -317,11 +330,16 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   const int nimg = frames * eyes;
   cudaStream_t st = s.stream;
   const bool prof = h->profiling;
+  h->last_in_l = in_l;
+  h->last_in_r = in_r;
+  h->last_frame_stride = frame_stride;
+  h->last_pitch = pitch;
+  h->last_eyes = eyes;
   int evi = 0;
   auto mark = [&]() {
     if (prof) cudaEventRecord(h->ev[evi++], st);
   };
-  CU_TRY(h, cudaMemset2DAsync(s.d_res, (size_t)P.res_frame_stride, 0, sizeof(ResHdr), (size_t)frames, st));
+  CU_TRY(h, cudaMemsetAsync(s.d_lay.hdr, 0, sizeof(ResHdr) * (size_t)frames, st));
   mark();  // 0
   for (int l = 1; l < P.nlevels; ++l) {
     dim3 grid((P.lv[l].h + VSLAM_RESIZE_ROWS - 1) / VSLAM_RESIZE_ROWS, nimg);
@@ -342,7 +360,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     Pl.sel_smem_cap = h->sel_cap[l];
     vk::k_select<<<dim3(1, nimg), 128, vk::select_smem_bytes(h->sel_cap[l]), st>>>(
         Pl, l, in_l, in_r, s.d_pyr, s.d_strip_cnt, s.d_strip_rec, s.d_glists, s.d_lvl_kp, s.d_lvl_cnt,
-        h->harris_scale4, s.d_res);
+        h->harris_scale4, s.d_lay);
     h->launches++;
   }
   mark();  // 3
@@ -354,15 +372,14 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   mark();  // 4
   {
     dim3 grid((P.kp_cap + 7) / 8, nimg);
-    vk::k_brief<<<grid, 256, 0, st>>>(P, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_res);
+    vk::k_brief<<<grid, 256, 0, st>>>(P, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
     h->launches++;
   }
   mark();  // 5
   if (eyes == 2) {
-    vk::FrameLayout F = frame_layout(P, s.d_res);
     dim3 grid((P.kp_cap + vk::kMatchLeftPerBlock - 1) / vk::kMatchLeftPerBlock, frames);
-    vk::k_match<<<grid, 256, 0, st>>>(F, h->S, s.d_ml);
-    vk::k_match_finalize<<<frames, 256, 0, st>>>(F, h->S, s.d_ml);
+    vk::k_match<<<grid, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
+    vk::k_match_finalize<<<frames, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
     h->launches += 2;
   }
   mark();  // 6
@@ -381,10 +398,10 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   return VSLAM_OK;
 }
 
-// Copy one frame's results out of a host-visible slab into the caller's buffers.
-int unpack_frame(vslam_handle h, const unsigned char* fr, vslam_frame_out* out, uint64_t ts) {
-  const PyrP& P = h->P;
-  const ResHdr* hdr = reinterpret_cast<const ResHdr*>(fr);
+// Hand one frame's results (host-visible SoA mirror `L`, frame f of the chunk) to the caller's buffers.
+// direct: the arrays already landed in the caller's memory; only counts and status are filled in.
+int unpack_frame(const FrameLayout& L, int f, bool direct, vslam_frame_out* out, uint64_t ts) {
+  const ResHdr* hdr = L.hdr + f;
   out->n_left = hdr->n_kp[0];
   out->n_right = hdr->n_kp[1];
   out->n_matches = hdr->n_matches;
@@ -396,13 +413,15 @@ int unpack_frame(vslam_handle h, const unsigned char* fr, vslam_frame_out* out, 
     out->status = VSLAM_ERR_CAPACITY;
     return VSLAM_ERR_CAPACITY;
   }
-  if (out->kp_left) memcpy(out->kp_left, fr + P.res_off_kp[0], (size_t)hdr->n_kp[0] * 28);
-  if (out->kp_right) memcpy(out->kp_right, fr + P.res_off_kp[1], (size_t)hdr->n_kp[1] * 28);
-  if (out->desc_left) memcpy(out->desc_left, fr + P.res_off_desc[0], (size_t)hdr->n_kp[0] * 32);
-  if (out->desc_right) memcpy(out->desc_right, fr + P.res_off_desc[1], (size_t)hdr->n_kp[1] * 32);
-  if (out->matches) memcpy(out->matches, fr + P.res_off_matches, (size_t)hdr->n_matches * 16);
-  if (out->points_cam) memcpy(out->points_cam, fr + P.res_off_pts, (size_t)hdr->n_kp[0] * 24);
-  if (out->points_valid) memcpy(out->points_valid, fr + P.res_off_valid, (size_t)hdr->n_kp[0]);
+  if (direct) return VSLAM_OK;
+  const size_t nl = (size_t)hdr->n_kp[0], nr = (size_t)hdr->n_kp[1], nm = (size_t)hdr->n_matches;
+  if (out->kp_left) memcpy(out->kp_left, L.kp[0] + (size_t)f * L.kp_stride, nl * 28);
+  if (out->kp_right) memcpy(out->kp_right, L.kp[1] + (size_t)f * L.kp_stride, nr * 28);
+  if (out->desc_left) memcpy(out->desc_left, L.desc[0] + (size_t)f * L.desc_stride, nl * 32);
+  if (out->desc_right) memcpy(out->desc_right, L.desc[1] + (size_t)f * L.desc_stride, nr * 32);
+  if (out->matches) memcpy(out->matches, L.matches + (size_t)f * L.matches_stride, nm * 16);
+  if (out->points_cam) memcpy(out->points_cam, L.pts + (size_t)f * L.pts_stride, nl * 24);
+  if (out->points_valid) memcpy(out->points_valid, L.valid + (size_t)f * L.valid_stride, nl);
   return VSLAM_OK;
 }
 
@@ -414,7 +433,7 @@ int retire_slot(vslam_handle h, Slot& s, vslam_frame_out* outs, const uint64_t* 
   if (s.want_results && outs) {
     for (int f = 0; f < s.frames; ++f) {
       const int gf = s.first_frame + f;
-      int rc = unpack_frame(h, s.h_res + (size_t)f * (size_t)h->P.res_frame_stride, &outs[gf], ts ? ts[gf] : 0);
+      int rc = unpack_frame(s.h_lay, f, s.direct_out, &outs[gf], ts ? ts[gf] : 0);
       if (rc != VSLAM_OK && *first_error == VSLAM_OK) {
         *first_error = rc;
         fail(h, rc, "frame %d: %s", gf,
@@ -427,6 +446,7 @@ int retire_slot(vslam_handle h, Slot& s, vslam_frame_out* outs, const uint64_t* 
 }
 
 bool is_pinned_host(const void* p) {
+  if (!p) return false;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -435,7 +455,28 @@ bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// kind: 0 = host pointers (left[i], right[i]), 1 = device slabs.
+// True when the caller's output arrays of frames [f0, f0+frames) are page-locked [frames][kp_cap] arrays, i.e. one
+// D2H per array can land in them directly.
+bool outputs_are_direct(vslam_handle h, const vslam_frame_out* o, int frames) {
+  const size_t cap = (size_t)h->kp_cap;
+  const vslam_frame_out& a = o[0];
+  if ((size_t)a.capacity != cap) return false;
+  if (!a.kp_left || !a.kp_right || !a.desc_left || !a.desc_right || !a.matches || !a.points_cam || !a.points_valid)
+    return false;
+  for (int f = 1; f < frames; ++f) {
+    const vslam_frame_out& b = o[f];
+    const size_t k = (size_t)f;
+    if ((size_t)b.capacity != cap || (uint8_t*)b.kp_left != (uint8_t*)a.kp_left + k * cap * 28 ||
+        (uint8_t*)b.kp_right != (uint8_t*)a.kp_right + k * cap * 28 || b.desc_left != a.desc_left + k * cap * 32 ||
+        b.desc_right != a.desc_right + k * cap * 32 || (uint8_t*)b.matches != (uint8_t*)a.matches + k * cap * 16 ||
+        (uint8_t*)b.points_cam != (uint8_t*)a.points_cam + k * cap * 24 || b.points_valid != a.points_valid + k * cap)
+      return false;
+  }
+  return is_pinned_host(a.kp_left) && is_pinned_host(a.kp_right) && is_pinned_host(a.desc_left) &&
+         is_pinned_host(a.desc_right) && is_pinned_host(a.matches) && is_pinned_host(a.points_cam) &&
+         is_pinned_host(a.points_valid);
+}
+
 int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
               const uint8_t* left_dev, const uint8_t* right_dev, size_t image_stride, size_t row_stride,
               const uint64_t* ts, vslam_frame_out* outs, bool device_input) {
@@ -448,6 +489,7 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
   }
   int first_error = VSLAM_OK;
   int chunk = 0;
+  CU_TRY(h, cudaEventRecord(h->ev_batch[0], h->slots[0].stream));
   for (int f0 = 0; f0 < n; f0 += h->max_batch, ++chunk) {
     const int frames = std::min(h->max_batch, n - f0);
     Slot& s = h->slots[chunk % NSLOT];
@@ -462,35 +504,59 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
       fstride = (long long)image_stride;
       pitch = (int)row_stride;
     } else {
-      // level-0 slab layout: image (f, eye) at (f*eyes + eye) * in_img_bytes, rows in_pitch apart
+      // planar level-0 staging: all left images of the chunk, then all right images; rows in_pitch apart
       const size_t ib = h->in_img_bytes;
-      const bool pinned = is_pinned_host(left[f0]) && (eyes == 1 || is_pinned_host(right[f0]));
-      for (int f = 0; f < frames; ++f) {
-        for (int e = 0; e < eyes; ++e) {
-          const uint8_t* src = e ? right[f0 + f] : left[f0 + f];
-          const size_t off = ((size_t)f * eyes + e) * ib;
-          if (pinned) {
-            CU_TRY(h, cudaMemcpy2DAsync(s.d_in + off, P.in_pitch, src, stride, W, H, cudaMemcpyHostToDevice, s.stream));
-          } else if (stride == (size_t)P.in_pitch) {
-            memcpy(s.h_in + off, src, ib);
-          } else {
-            for (int y = 0; y < H; ++y) memcpy(s.h_in + off + (size_t)y * P.in_pitch, src + (size_t)y * stride, W);
+      for (int e = 0; e < eyes; ++e) {
+        const uint8_t* const* src = e ? right + f0 : left + f0;
+        uint8_t* dst = s.d_in + (size_t)e * frames * ib;
+        uint8_t* hst = s.h_in + (size_t)e * frames * ib;
+        const bool pinned = is_pinned_host(src[0]) && is_pinned_host(src[frames - 1]);
+        bool contiguous = true;
+        for (int f = 1; f < frames && contiguous; ++f) contiguous = src[f] == src[0] + (size_t)f * H * stride;
+        if (pinned && contiguous) {
+          CU_TRY(h, cudaMemcpy2DAsync(dst, P.in_pitch, src[0], stride, W, (size_t)frames * H, cudaMemcpyHostToDevice,
+                                      s.stream));
+        } else if (pinned) {
+          for (int f = 0; f < frames; ++f)
+            CU_TRY(h, cudaMemcpy2DAsync(dst + (size_t)f * ib, P.in_pitch, src[f], stride, W, H, cudaMemcpyHostToDevice,
+                                        s.stream));
+        } else {
+          for (int f = 0; f < frames; ++f) {
+            if (stride == (size_t)P.in_pitch) memcpy(hst + (size_t)f * ib, src[f], ib);
+            else
+              for (int y = 0; y < H; ++y) memcpy(hst + (size_t)f * ib + (size_t)y * P.in_pitch, src[f] + (size_t)y * stride, W);
           }
+          CU_TRY(h, cudaMemcpyAsync(dst, hst, (size_t)frames * ib, cudaMemcpyHostToDevice, s.stream));
         }
       }
-      if (!pinned)
-        CU_TRY(h, cudaMemcpyAsync(s.d_in, s.h_in, (size_t)frames * eyes * ib, cudaMemcpyHostToDevice, s.stream));
       in_l = s.d_in;
-      in_r = s.d_in + ib;
-      fstride = (long long)(ib * eyes);
+      in_r = s.d_in + (size_t)frames * ib;
+      fstride = (long long)ib;
       pitch = P.in_pitch;
     }
     rc = enqueue_chunk(h, s, frames, eyes, in_l, in_r, fstride, pitch);
     if (rc != VSLAM_OK) return rc;
     s.want_results = outs != nullptr;
-    if (outs)
-      CU_TRY(h, cudaMemcpyAsync(s.h_res, s.d_res, (size_t)frames * (size_t)P.res_frame_stride, cudaMemcpyDeviceToHost,
-                                s.stream));
+    s.direct_out = false;
+    if (outs) {
+      const FrameLayout& D = s.d_lay;
+      const FrameLayout& M = s.h_lay;
+      const size_t fr = (size_t)frames;
+      CU_TRY(h, cudaMemcpyAsync(M.hdr, D.hdr, fr * sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream));
+      s.direct_out = eyes == 2 && outputs_are_direct(h, outs + f0, frames);
+      const vslam_frame_out& o = outs[f0];
+      void* dst[7] = {s.direct_out ? (void*)o.kp_left : (void*)M.kp[0],      s.direct_out ? (void*)o.kp_right : (void*)M.kp[1],
+                      s.direct_out ? (void*)o.desc_left : (void*)M.desc[0],  s.direct_out ? (void*)o.desc_right : (void*)M.desc[1],
+                      s.direct_out ? (void*)o.matches : (void*)M.matches,    s.direct_out ? (void*)o.points_cam : (void*)M.pts,
+                      s.direct_out ? (void*)o.points_valid : (void*)M.valid};
+      const void* src[7] = {D.kp[0], D.kp[1], D.desc[0], D.desc[1], D.matches, D.pts, D.valid};
+      const size_t bytes[7] = {fr * D.kp_stride,      fr * D.kp_stride,  fr * D.desc_stride, fr * D.desc_stride,
+                               fr * D.matches_stride, fr * D.pts_stride, fr * D.valid_stride};
+      for (int a = 0; a < 7; ++a) {
+        if (eyes == 1 && (a == 1 || a == 3 || a >= 4)) continue;
+        CU_TRY(h, cudaMemcpyAsync(dst[a], src[a], bytes[a], cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
     CU_TRY(h, cudaEventRecord(s.done, s.stream));
     s.busy = true;
     s.frames = frames;
@@ -498,18 +564,23 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
     h->last_slot = chunk % NSLOT;
     h->last_frames = frames;
   }
+  // join every slot's stream into slot 0's and close the device-time bracket of this batch
+  for (int k = 1; k < NSLOT; ++k)
+    if (h->slots[k].busy) CU_TRY(h, cudaStreamWaitEvent(h->slots[0].stream, h->slots[k].done, 0));
+  CU_TRY(h, cudaEventRecord(h->ev_batch[1], h->slots[0].stream));
   // drain in submission order
   for (int k = 0; k < NSLOT; ++k) {
     Slot& s = h->slots[(chunk + k) % NSLOT];
     int rc = retire_slot(h, s, outs, ts, &first_error);
     if (rc != VSLAM_OK) return rc;
   }
+  CU_TRY(h, cudaEventSynchronize(h->ev_batch[1]));
+  cudaEventElapsedTime(&h->last_batch_ms, h->ev_batch[0], h->ev_batch[1]);
   if (!outs) {
     // results stay on the device: still surface per-frame overflow flags of the last chunk
     Slot& s = h->slots[h->last_slot];
     std::vector<ResHdr> hdrs((size_t)h->last_frames);
-    CU_TRY(h, cudaMemcpy2D(hdrs.data(), sizeof(ResHdr), s.d_res, (size_t)P.res_frame_stride, sizeof(ResHdr),
-                           (size_t)h->last_frames, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(hdrs.data(), s.d_lay.hdr, sizeof(ResHdr) * hdrs.size(), cudaMemcpyDeviceToHost));
     for (const ResHdr& r : hdrs)
       if (r.status != VSLAM_OK && first_error == VSLAM_OK) {
         first_error = r.status;
@@ -591,6 +662,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     return bail(VSLAM_ERR_CUDA);
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+  cudaEventCreate(&h->ev_batch[0]);
+  cudaEventCreate(&h->ev_batch[1]);
   // opt in to large dynamic shared memory where needed
   size_t max_resize = 0, max_sel = 0;
   for (int l = 1; l < h->P.nlevels; ++l) max_resize = std::max(max_resize, h->resize_smem[l]);
@@ -625,6 +698,8 @@ void vslam_destroy(vslam_handle h) {
   cudaFree(h->arena_base);
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_batch[i]) cudaEventDestroy(h->ev_batch[i]);
   delete h;
 }
 
@@ -694,6 +769,8 @@ int vslam_set_profiling(vslam_handle h, int enabled) {
   return VSLAM_OK;
 }
 
+float vslam_last_batch_ms(vslam_handle h) { return h ? h->last_batch_ms : 0.f; }
+
 int vslam_last_stage_ms(vslam_handle h, float* ms7) {
   if (!h || !ms7) return VSLAM_ERR_INVALID_ARGUMENT;
   memcpy(ms7, h->stage_ms, sizeof(h->stage_ms));
@@ -721,7 +798,12 @@ int vslam_debug_level_image(vslam_handle h, int stage, int image, int level, uin
   const uint8_t* src;
   int pitch = L.pitch;
   if (stage == VSLAM_STAGE_BLURRED) src = s.d_blur + (size_t)image * (size_t)P.blur_img_stride + L.blur_off;
-  else if (level == 0) src = s.d_in + (size_t)image * h->in_img_bytes;
+  else if (level == 0) {
+    // planar staging: image index = frame * eyes + eye
+    const int f = image / h->last_eyes, e = image % h->last_eyes;
+    src = (e ? h->last_in_r : h->last_in_l) + (size_t)f * (size_t)h->last_frame_stride;
+    pitch = h->last_pitch;
+  }
   else src = s.d_pyr + (size_t)image * (size_t)P.pyr_img_stride + L.pyr_off;
   CU_TRY(h, cudaMemcpy2D(dst, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
   return VSLAM_OK;
@@ -734,7 +816,21 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
   const LevelP& L = P.lv[level];
   CU_TRY(h, cudaSetDevice(h->cfg.device));
   Slot& s = h->slots[h->last_slot];
-  // NOTE: k_select compacts strips in place only in its global-memory fallback; the strip slab is otherwise intact.
+  if (h->last_frames <= 0 || image >= h->last_frames * h->last_eyes)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image %d was not part of the last chunk", image);
+  {
+    // k_select may compact the strip slab in place (global-memory fallback): re-run k_fast on the last chunk.
+    PyrP Pr = h->P;
+    Pr.eyes = h->last_eyes;
+    Pr.in_pitch = h->last_pitch;
+    Pr.lv[0].pitch = h->last_pitch;
+    Pr.in_frame_stride = h->last_frame_stride;
+    dim3 grid(Pr.total_fast_strips, h->last_frames * h->last_eyes);
+    vk::k_fast<<<grid, 256, vk::fast_smem_bytes(std::max(h->last_pitch, h->P.in_pitch)), s.stream>>>(
+        Pr, h->last_in_l, h->last_in_r, s.d_pyr, s.d_strip_cnt, s.d_strip_rec);
+    h->launches++;
+    CU_TRY(h, cudaStreamSynchronize(s.stream));
+  }
   std::vector<int> cnt(std::max(L.fast_nstrips, 1));
   CU_TRY(h, cudaMemcpy(cnt.data(), s.d_strip_cnt + (size_t)image * P.total_fast_strips + L.fast_strip0,
                        sizeof(int) * L.fast_nstrips, cudaMemcpyDeviceToHost));

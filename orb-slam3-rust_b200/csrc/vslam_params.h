@@ -40,17 +40,29 @@ struct PyrP {
   long long pyr_img_stride;    // bytes per image in the pyramid slab
   long long blur_img_stride;   // bytes per image in the blurred slab
   long long rec_img_stride;    // records per image in the strip-record slab
-  long long res_frame_stride;  // bytes per frame in the result slab
-  int res_off_kp[2], res_off_desc[2], res_off_matches, res_off_pts, res_off_valid;  // byte offsets in a frame's result
   LevelP lv[VSLAM_MAX_LEVELS];
 };
 
-// Result-slab header (one per frame, first 32 bytes of the frame's result).
+// Per-frame result header.
 struct ResHdr {
   int n_kp[2];
   int n_matches;
   int status;
   int pad[4];
+};
+
+// Results of a chunk, structure-of-arrays over frames: array X of frame f starts at X + f * X_stride bytes.
+// The strides equal the natural [frames][capacity] array strides, so a chunk can be copied with one D2H per array
+// straight into caller arrays of that shape.
+struct FrameLayout {
+  ResHdr* hdr;                 // [frames]
+  unsigned char* kp[2];        // cv::KeyPoint records, 28 B each
+  unsigned char* desc[2];      // 32 B each
+  unsigned char* matches;      // cv::DMatch records, 16 B each
+  unsigned char* pts;          // 3 x f64 per LEFT keypoint
+  unsigned char* valid;        // 1 B per LEFT keypoint
+  long long kp_stride, desc_stride, matches_stride, pts_stride, valid_stride;
+  int cap;                     // per-image keypoint capacity
 };
 
 struct StereoP {

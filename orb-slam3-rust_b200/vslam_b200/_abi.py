@@ -62,6 +62,7 @@ SYMBOLS = [
     "vslam_triangulate", "vslam_descriptor_distance", "vslam_grid_build", "vslam_grid_query",
     "vslam_search_by_projection", "vslam_bf_match_crosscheck", "vslam_level_info", "vslam_debug_level_image",
     "vslam_debug_fast_corners", "vslam_kernel_launches", "vslam_set_profiling", "vslam_last_stage_ms",
+    "vslam_last_batch_ms",
 ]
 
 _lib = None
@@ -102,5 +103,7 @@ def lib():
         L.vslam_kernel_launches.restype = u64
         L.vslam_set_profiling.argtypes = [vp, i32]
         L.vslam_last_stage_ms.argtypes = [vp, vp]
+        L.vslam_last_batch_ms.argtypes = [vp]
+        L.vslam_last_batch_ms.restype = C.c_float
         _lib = L
     return _lib

@@ -352,6 +352,10 @@ class StereoProcessor:
     def set_profiling(self, enabled):
         self._lib.vslam_set_profiling(self._h, int(bool(enabled)))
 
+    def last_batch_ms(self):
+        """Device time (CUDA events on the library's streams) of the last process_batch* call."""
+        return float(self._lib.vslam_last_batch_ms(self._h))
+
     def last_stage_ms(self):
         ms = np.zeros(7, dtype=np.float32)
         self._lib.vslam_last_stage_ms(self._h, _ptr(ms))

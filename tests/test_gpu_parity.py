@@ -1,0 +1,394 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libvslam_b200.so), against the CPU oracle on the
+same inputs.  Bar: bit-exact for keypoints (order, coordinates, octave, angle, response), descriptors, match pairs;
+f64 points within 1e-4 (expected and asserted: exactly equal)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_struct_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp752():
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    p = StereoProcessor(CameraModel(**synth.EUROC_CAMERA), 1200, 752, 480, max_batch=4)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def sp720():
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    p = StereoProcessor(CameraModel(**synth.EUROC_CAMERA), 2000, 1280, 720, max_batch=2)
+    yield p
+    p.close()
+
+
+def check_frame(fr, ref_l, ref_r, oracle, cam):
+    kl, dl = ref_l
+    kr, dr = ref_r
+    assert_struct_equal(fr.left_features.keypoints, kl, "left keypoints")
+    assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
+    assert np.array_equal(fr.left_features.descriptors, dl), "left descriptors"
+    assert np.array_equal(fr.right_features.descriptors, dr), "right descriptors"
+    m = oracle.match_features(kl, dl, kr, dr, cam)
+    assert_struct_equal(fr.matches_lr, m, "matches")
+    pts, valid = oracle.triangulate(kl, kr, m, cam)
+    assert np.array_equal(fr.points_valid, valid)
+    assert np.max(np.abs(fr.points_cam - pts), initial=0.0) <= 1e-4  # north_star tolerance
+    assert np.array_equal(fr.points_cam, pts)  # and in fact exact
+
+
+# ------------------------------------------------------------------ StereoProcessor::process, config 1
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_process_matches_oracle_752x480(sp752, oracle, pairs, camera_dict, seed):
+    l, r = pairs(seed)
+    fr = sp752.process(l, r, 1000 + seed)
+    assert fr.timestamp_ns == 1000 + seed
+    check_frame(fr, oracle.detect_and_compute(l, 1200), oracle.detect_and_compute(r, 1200), oracle, camera_dict)
+
+
+def test_process_matches_cv2_directly(sp752, cv2mod, pairs):
+    """Against the reference's real engine (cv::ORB through cv2), not only its restatement."""
+    from oracle import cv2_ref
+
+    l, r = pairs(4)
+    fr = sp752.process(l, r)
+    for img, fs in ((l, fr.left_features), (r, fr.right_features)):
+        k, d = cv2_ref.detect_and_compute(img, 1200)
+        assert_struct_equal(fs.keypoints, k, "keypoints vs cv2")
+        assert np.array_equal(fs.descriptors, d)
+
+
+def test_process_1280x720_n2000(sp720, oracle, pairs, camera_dict):  # config 3
+    l, r = pairs(3, 1280, 720)
+    fr = sp720.process(l, r)
+    check_frame(fr, oracle.detect_and_compute(l, 2000), oracle.detect_and_compute(r, 2000), oracle, camera_dict)
+
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_golden_fixtures(path, camera_dict):
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    g = np.load(path)
+    h, w = g["left"].shape
+    with StereoProcessor(CameraModel(**camera_dict), int(g["n_features"]), w, h, max_batch=1) as sp:
+        fr = sp.process(g["left"], g["right"])
+        bf = sp.bf_match_crosscheck(g["desc_left"], g["desc_right"])
+    assert_struct_equal(fr.left_features.keypoints, g["kp_left"], "kp_left")
+    assert_struct_equal(fr.right_features.keypoints, g["kp_right"], "kp_right")
+    assert np.array_equal(fr.left_features.descriptors, g["desc_left"])
+    assert np.array_equal(fr.right_features.descriptors, g["desc_right"])
+    assert_struct_equal(fr.matches_lr, g["matches"], "matches")
+    assert np.array_equal(fr.points_valid, g["points_valid"]) and np.array_equal(fr.points_cam, g["points"])
+    assert_struct_equal(bf, g["bf_crosscheck"], "bf_crosscheck")
+
+
+# ------------------------------------------------------------------ stage-level parity (each kernel in isolation)
+def test_stage_pyramid_fast_blur(sp752, oracle, pairs):
+    from vslam_b200 import STAGE_BLURRED, STAGE_PYRAMID
+
+    l, r = pairs(5)
+    sp752.process(l, r)
+    for eye, img in enumerate((l, r)):
+        st = oracle.detect_stages(img, 1200)
+        for lvl in range(8):
+            assert np.array_equal(sp752.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
+            assert np.array_equal(sp752.debug_level_image(STAGE_BLURRED, eye, lvl), st["blurred"][lvl]), f"blur {lvl}"
+            c = sp752.debug_fast_corners(eye, lvl)
+            o = st["fast"][lvl]
+            ref = np.stack([o["x"], o["y"], o["resp"].astype(np.int32)], 1)
+            assert np.array_equal(c, ref), f"fast corners level {lvl} (raster order, scores)"
+
+
+# ------------------------------------------------------------------ batch pipeline (chunks, slots, strides)
+def test_batch_multi_chunk_equals_per_frame(sp752, oracle, pairs, camera_dict):
+    seeds = list(range(20, 31))  # 11 frames, max_batch 4 -> chunks 4/4/3 over 3 slots
+    ls = np.stack([pairs(s)[0] for s in seeds])
+    rs = np.stack([pairs(s)[1] for s in seeds])
+    frs = sp752.process_batch(ls, rs, timestamps_ns=np.arange(len(seeds)) + 5)
+    assert len(frs) == len(seeds)
+    for i, fr in enumerate(frs):
+        assert fr.timestamp_ns == i + 5
+        check_frame(fr, oracle.detect_and_compute(ls[i], 1200), oracle.detect_and_compute(rs[i], 1200), oracle, camera_dict)
+
+
+def test_batch_pinned_direct_output_and_device_input(sp752, oracle, pairs, camera_dict):
+    import torch
+
+    seeds = [40, 41, 42, 43, 44, 45]
+    lh = torch.from_numpy(np.stack([pairs(s)[0] for s in seeds])).pin_memory()
+    rh = torch.from_numpy(np.stack([pairs(s)[1] for s in seeds])).pin_memory()
+    n, cap = len(seeds), sp752.capacity
+    ob = sp752.new_output_buffers(n)
+    # page-locked [n][cap] output arrays -> the library copies D2H straight into them
+    pinned = {}
+    for name, arr in (("kpl", ob.kpl), ("kpr", ob.kpr), ("dl", ob.dl), ("dr", ob.dr), ("m", ob.m), ("pts", ob.pts), ("valid", ob.valid)):
+        t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+        pinned[name] = t
+        setattr(ob, name, t.numpy().view(arr.dtype).reshape(arr.shape))
+    for i in range(n):
+        o = ob.outs[i]
+        o.kp_left, o.kp_right = ob.kpl[i].ctypes.data, ob.kpr[i].ctypes.data
+        o.desc_left, o.desc_right = ob.dl[i].ctypes.data, ob.dr[i].ctypes.data
+        o.matches, o.points_cam, o.points_valid = ob.m[i].ctypes.data, ob.pts[i].ctypes.data, ob.valid[i].ctypes.data
+    frs = sp752.process_batch(lh.numpy(), rh.numpy(), out=ob)
+    refs = [(oracle.detect_and_compute(lh[i].numpy(), 1200), oracle.detect_and_compute(rh[i].numpy(), 1200)) for i in range(n)]
+    for i, fr in enumerate(frs):
+        check_frame(fr, refs[i][0], refs[i][1], oracle, camera_dict)
+    # same frames resident in HBM
+    ld, rd = lh.cuda(), rh.cuda()
+    ob2 = sp752.new_output_buffers(n)
+    sp752.process_batch_device(n, ld.data_ptr(), rd.data_ptr(), 752 * 480, 752, ob2)
+    for i in range(n):
+        check_frame(ob2.frame(i), refs[i][0], refs[i][1], oracle, camera_dict)
+    assert sp752.last_batch_ms() > 0.0
+
+
+def test_row_stride_and_roi_inputs(sp752, oracle, pairs, camera_dict):
+    l, r = pairs(6)
+    big_l = np.zeros((480, 800), np.uint8)
+    big_r = np.zeros((480, 800), np.uint8)
+    big_l[:, :752], big_r[:, :752] = l, r
+    fr = sp752.process(big_l[:, :752], big_r[:, :752])  # borrowed &Mat with a row stride
+    check_frame(fr, oracle.detect_and_compute(l, 1200), oracle.detect_and_compute(r, 1200), oracle, camera_dict)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_blank_and_saturated_images_give_no_features(sp752):
+    z = np.zeros((480, 752), np.uint8)
+    fr = sp752.process(z, np.full((480, 752), 255, np.uint8))
+    assert len(fr.left_features.keypoints) == 0 and len(fr.right_features.keypoints) == 0
+    assert len(fr.matches_lr) == 0 and fr.points_cam.shape == (0, 3)
+
+
+def test_few_features_and_ragged_left_right(sp752, oracle, pairs, camera_dict):
+    # left: texture only in a small window (few corners, fewer than any level quota); right: full texture
+    l, r = pairs(7)
+    l2 = np.full_like(l, 128)
+    l2[200:300, 300:450] = l[200:300, 300:450]
+    fr = sp752.process(l2, r)
+    ref_l = oracle.detect_and_compute(l2, 1200)
+    assert 0 < len(ref_l[0]) < 600
+    check_frame(fr, ref_l, oracle.detect_and_compute(r, 1200), oracle, camera_dict)
+
+
+def test_white_noise_maximum_corner_density(oracle, camera_dict):
+    """Dense corners: exercises the global-memory selection path (more corners than fit in shared memory)."""
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    rng = np.random.default_rng(3)
+    l = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+    r = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+    with StereoProcessor(CameraModel(**camera_dict), 1200, max_batch=1) as sp:
+        fr = sp.process(l, r)
+    check_frame(fr, oracle.detect_and_compute(l, 1200), oracle.detect_and_compute(r, 1200), oracle, camera_dict)
+
+
+def lattice_image():
+    """Identical peaked blobs on a 12-px lattice: hundreds of exactly equal FAST scores and Harris responses."""
+    yy, xx = np.mgrid[0:480, 0:752]
+    dx, dy = np.abs((xx % 12) - 6), np.abs((yy % 12) - 6)
+    return (20 + 200 * np.clip(1 - (dx + dy) / 4.0, 0, 1)).astype(np.uint8)
+
+
+def test_response_ties_overflow_is_reported_not_truncated(camera_dict):
+    """A periodic pattern gives thousands of identical Harris responses: retainBest keeps all ties, which exceeds
+    a deliberately tiny keypoint capacity -> the call must fail loudly with KEYPOINT_OVERFLOW."""
+    from vslam_b200 import CameraModel, StereoProcessor, VslamError
+
+    img = lattice_image()
+    with StereoProcessor(CameraModel(**camera_dict), 100, max_batch=1, keypoint_capacity=110) as sp:
+        with pytest.raises(VslamError) as e:
+            sp.process(img, img)
+        assert e.value.status == 4
+
+
+def test_ties_within_capacity_match_oracle(oracle, camera_dict):
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    img = lattice_image()
+    k, d = oracle.detect_and_compute(img, 100)
+    assert len(k) > 100  # ties at the cut keep more than nfeatures
+    with StereoProcessor(CameraModel(**camera_dict), 100, max_batch=1, keypoint_capacity=len(k) + 8) as sp:
+        fs = sp.detect_features(img)
+    assert_struct_equal(fs.keypoints, k, "keypoints with ties")
+    assert np.array_equal(fs.descriptors, d)
+
+
+def test_invalid_inputs_raise(sp752):
+    from vslam_b200 import VslamError
+
+    with pytest.raises(VslamError):
+        sp752.process(np.zeros((480, 640), np.uint8), np.zeros((480, 752), np.uint8))
+    with pytest.raises(VslamError):
+        sp752.process(np.zeros((480, 752), np.float32), np.zeros((480, 752), np.uint8))
+
+
+# ------------------------------------------------------------------ pieces of process() on oracle inputs
+def test_match_triangulate_hamming_standalone(sp752, oracle, pairs, camera_dict):
+    from vslam_b200 import FeatureSet, descriptor_distance
+
+    l, r = pairs(0)
+    kl, dl = oracle.detect_and_compute(l, 1200)
+    kr, dr = oracle.detect_and_compute(r, 1200)
+    m = oracle.match_features(kl, dl, kr, dr, camera_dict)
+    assert_struct_equal(sp752.match_features(FeatureSet(kl, dl), FeatureSet(kr, dr)), m, "matches")
+    # ragged: fewer right than left keypoints tightens max_u (SURVEY 8.C trap 3); and empty sides
+    for nl, nr in ((1200, 700), (500, 1200), (0, 50), (50, 0)):
+        mm = oracle.match_features(kl[:nl], dl[:nl], kr[:nr], dr[:nr], camera_dict)
+        assert_struct_equal(sp752.match_features(FeatureSet(kl[:nl], dl[:nl]), FeatureSet(kr[:nr], dr[:nr])), mm, f"{nl}x{nr}")
+    pts, valid = oracle.triangulate(kl, kr, m, camera_dict)
+    p2, v2 = sp752.triangulate(FeatureSet(kl, dl), FeatureSet(kr, dr), m)
+    assert np.array_equal(p2, pts) and np.array_equal(v2, valid)
+    got = sp752.descriptor_distances(dl, dr)
+    assert np.array_equal(got, np.array([oracle.descriptor_distance(a, b) for a, b in zip(dl, dr)], np.uint32))
+    # the reference's own known-answer vectors (vocabulary/mod.rs:430-441)
+    a, c = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+    assert descriptor_distance(sp752, a, a) == 0
+    c[0] = 0xFF
+    assert descriptor_distance(sp752, a, c) == 8
+    c[1] = 0x0F
+    assert descriptor_distance(sp752, a, c) == 12
+
+
+def test_match_more_right_keypoints_than_one_smem_chunk(sp752, oracle, camera_dict):
+    """n_right > 1024 forces several shared-memory passes with the (best, second) merge."""
+    from vslam_b200 import FeatureSet
+
+    rng = np.random.default_rng(9)
+    nl, nr = 300, 3000
+    kl = np.zeros(nl, oracle.KP_DTYPE)
+    kr = np.zeros(nr, oracle.KP_DTYPE)
+    kl["x"], kl["y"] = rng.uniform(300, 700, nl).astype(np.float32), rng.integers(40, 60, nl).astype(np.float32)
+    kr["x"], kr["y"] = rng.uniform(0, 700, nr).astype(np.float32), rng.integers(40, 60, nr).astype(np.float32)
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    def noisy(n, bits):
+        d = np.tile(base, (n, 1))
+        for i in range(n):
+            for b in rng.integers(0, 256, bits):
+                d[i, b // 8] ^= 1 << (b % 8)
+        return d
+    dl, dr = noisy(nl, 6), noisy(nr, 20)
+    m = oracle.match_features(kl, dl, kr, dr, camera_dict)
+    assert len(m) > 0
+    assert_struct_equal(sp752.match_features(FeatureSet(kl, dl), FeatureSet(kr, dr)), m, "matches")
+
+
+# ------------------------------------------------------------------ tracking-side searches (rows a7, a8, f1)
+def test_feature_grid_and_queries(sp752, oracle, pairs):
+    from vslam_b200 import FeatureGrid
+
+    kl, _ = oracle.detect_and_compute(pairs(0)[0], 1200)
+    cs, items = sp752.grid_build(kl)
+    ocs, oit = oracle.grid_build(kl)
+    assert np.array_equal(cs, ocs) and np.array_equal(items, oit)
+    rng = np.random.default_rng(5)
+    q = np.c_[rng.uniform(-80, 840, 400), rng.uniform(-80, 560, 400), rng.choice([5.0, 15.0, 50.0], 400)]
+    q[:4] = [[-100, 240, 15], [300, -100, 15], [900, 240, 15], [300, 700, 15]]  # wrap-to-last-column/row and empty
+    got = sp752.grid_query(kl, q)
+    for i in range(len(q)):
+        assert np.array_equal(got[i], oracle.grid_query(ocs, oit, *q[i])), f"query {i} {q[i]}"
+    g = FeatureGrid(sp752, kl)
+    assert np.array_equal(g.get_features_in_area(100.0, 100.0, 15.0), oracle.grid_query(ocs, oit, 100.0, 100.0, 15.0))
+    # keypoints outside the hard-coded 752x480 extent clamp into the last cells (trap 7); NaN/negative saturate to 0
+    k2 = kl.copy()
+    k2["x"][:10] = 2000.0
+    k2["y"][10:20] = -5.0
+    a, b = sp752.grid_build(k2)
+    oa, ob = oracle.grid_build(k2)
+    assert np.array_equal(a, oa) and np.array_equal(b, ob)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_search_by_projection(sp752, oracle, pairs, mode):
+    from vslam_b200 import FeatureSet
+
+    kl, dl = oracle.detect_and_compute(pairs(0)[0], 1200)
+    rng = np.random.default_rng(11 + mode)
+    M = 3000
+    src = rng.integers(0, len(kl), M)
+    uv = np.c_[kl["x"][src] + rng.normal(0, 6, M), kl["y"][src] + rng.normal(0, 6, M)].astype(np.float64)
+    uv[:100] += rng.uniform(-900, 900, (100, 2))  # outside the image: wrap / empty ranges
+    md = dl[src].copy()
+    for i in range(M):
+        for b in rng.integers(0, 256, rng.integers(0, 60)):
+            md[i, b // 8] ^= 1 << (b % 8)
+    gi, gd = sp752.search_by_projection(FeatureSet(kl, dl), uv, md, mode=mode)
+    oi, od = oracle.search_by_projection(kl, dl, uv, md, mode, bound_w=2 * sp752.camera.cx, bound_h=2 * sp752.camera.cy)
+    assert (oi >= 0).sum() > 500
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_bf_match_crosscheck(sp752, oracle, pairs):
+    l, r = pairs(1)
+    _, dl = oracle.detect_and_compute(l, 1200)
+    _, dr = oracle.detect_and_compute(r, 1200)
+    assert_struct_equal(sp752.bf_match_crosscheck(dl, dr), oracle.bf_match_crosscheck(dl, dr), "bf")
+    assert_struct_equal(sp752.bf_match_crosscheck(dl[:37], dr), oracle.bf_match_crosscheck(dl[:37], dr), "bf ragged")
+    assert len(sp752.bf_match_crosscheck(dl[:0], dr)) == 0
+
+
+# ------------------------------------------------------------------ config 4: a short tracked sequence
+def test_tracking_sequence_projection_search(sp752, oracle, camera_dict):
+    """Frame 0's stereo points become the local map; later frames (canvas translated 2 px/frame, i.e. a pure
+    image-plane shift) are searched with exact projected (u, v).  Compared as a map mp -> kp (trap 11)."""
+    from vslam_b200 import Frame, synth
+
+    l0, r0 = synth.make_stereo_pair(50)
+    l0, r0 = l0.numpy(), r0.numpy()
+    f0 = sp752.process(l0, r0)
+    good = np.flatnonzero(f0.points_valid)
+    mp_desc = f0.left_features.descriptors[good]
+    for step in (1, 2, 3):
+        shift = 2 * step
+        l = np.roll(l0, shift, axis=1)
+        r = np.roll(r0, shift, axis=1)
+        fr = sp752.process(l, r)
+        frame = Frame.from_stereo(sp752, fr)
+        uv = np.c_[f0.left_features.keypoints["x"][good].astype(np.float64) + shift,
+                   f0.left_features.keypoints["y"][good].astype(np.float64)]
+        for mode in (0, 1):
+            gi, gd = sp752.search_by_projection(frame.features, uv, mp_desc, mode=mode)
+            oi, od = oracle.search_by_projection(fr.left_features.keypoints, fr.left_features.descriptors, uv, mp_desc,
+                                                 mode, bound_w=2 * sp752.camera.cx, bound_h=2 * sp752.camera.cy)
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+            assert (gi >= 0).sum() > 100
+
+
+# ------------------------------------------------------------------ full-size property checks (config 2 scale)
+def test_large_batch_properties(oracle, camera_dict):
+    """256 device-resident frames: size-independent properties + spot parity on a sample."""
+    import torch
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    n = 256
+    lb, rb = synth.make_stereo_batch(range(100, 132), device="cuda")
+    lb, rb = lb.repeat(n // 32, 1, 1).contiguous(), rb.repeat(n // 32, 1, 1).contiguous()
+    with StereoProcessor(CameraModel(**camera_dict), 1200, max_batch=64) as sp:
+        ob = sp.new_output_buffers(n)
+        sp.process_batch_device(n, lb.data_ptr(), rb.data_ptr(), 752 * 480, 752, ob)
+        frs = [ob.frame(i, copy=False) for i in range(n)]
+        launches = sp.kernel_launches()
+    assert launches > 0
+    for i, fr in enumerate(frs):
+        j = i % 32  # identical inputs -> identical outputs (idempotence across chunks / slots)
+        assert fr.left_features.keypoints.tobytes() == frs[j].left_features.keypoints.tobytes()
+        assert fr.matches_lr.tobytes() == frs[j].matches_lr.tobytes()
+        k = fr.left_features.keypoints
+        assert len(k) <= sp.capacity and np.all(np.diff(k["octave"]) >= 0)  # levels concatenated 0..7
+        assert np.all(np.diff(fr.matches_lr["query_idx"]) > 0)  # ascending, unique left index
+        assert np.all(fr.matches_lr["distance"] < 100)
+        assert fr.points_valid.sum() <= len(fr.matches_lr)
+    lh, rh = lb[:32].cpu().numpy(), rb[:32].cpu().numpy()
+    for i in (0, 7, 31):
+        check_frame(frs[i], oracle.detect_and_compute(lh[i], 1200), oracle.detect_and_compute(rh[i], 1200), oracle, camera_dict)

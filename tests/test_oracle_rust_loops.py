@@ -1,0 +1,100 @@
+"""Behavioural tests of the restated Rust loops (oracle/stereo_oracle.cpp): the quirks SURVEY.md §8.C lists."""
+import numpy as np
+
+from oracle.orb_oracle import DMATCH_DTYPE, KP_DTYPE
+
+CAM = dict(fx=458.654, fy=457.296, cx=367.215, cy=248.375, baseline=0.110074)
+
+
+def kps(xy):
+    k = np.zeros(len(xy), dtype=KP_DTYPE)
+    k["x"] = [p[0] for p in xy]
+    k["y"] = [p[1] for p in xy]
+    k["class_id"] = -1
+    return k
+
+
+def desc_with_bits(n):
+    d = np.zeros(32, np.uint8)
+    for b in range(n):
+        d[b // 8] |= 1 << (b % 8)
+    return d
+
+
+def test_match_first_index_wins_and_ratio(oracle):
+    kl = kps([(300.0, 100.0), (301.0, 100.0)])
+    kr = kps([(280.0, 100.0), (281.0, 101.0)])
+    dl = np.stack([desc_with_bits(0), desc_with_bits(0)])
+    dr = np.stack([desc_with_bits(10), desc_with_bits(10)])  # tie: first right index must win, but ratio fails
+    m = oracle.match_features(kl, dl, kr, dr, CAM)
+    assert len(m) == 0  # best == second == 10 -> 10 < 0.9*10 false and second != 100
+    dr[1] = desc_with_bits(60)
+    m = oracle.match_features(kl, dl, kr, dr, CAM)
+    assert [(int(a["query_idx"]), int(a["train_idx"]), float(a["distance"])) for a in m] == [(0, 0, 10.0), (1, 0, 10.0)]
+
+
+def test_match_gates(oracle):
+    kl = kps([(300.0, 100.0)])
+    dl = np.stack([desc_with_bits(0)])
+    dr = np.stack([desc_with_bits(5)])
+    assert len(oracle.match_features(kl, dl, kps([(280.0, 102.0)]), dr, CAM)) == 1  # |dv| == 2 passes
+    assert len(oracle.match_features(kl, dl, kps([(280.0, 102.5)]), dr, CAM)) == 0  # |dv| > 2
+    assert len(oracle.match_features(kl, dl, kps([(300.0, 100.0)]), dr, CAM)) == 0  # ul <= ur
+    assert len(oracle.match_features(kl, dl, kps([(299.5, 100.0)]), dr, CAM)) == 0  # disparity < min (1.262)
+    dr100 = np.stack([desc_with_bits(100)])
+    assert len(oracle.match_features(kl, dl, kps([(280.0, 100.0)]), dr100, CAM)) == 0  # d < 100 required
+
+
+def test_match_max_u_cap_when_fewer_right(oracle):
+    # stereo.rs:101-102: max_u = min(ul - min_d, nR*ul/nL): with nR < nL the window tightens to ur <= ul*nR/nL
+    kl = kps([(300.0, 100.0), (10.0, 400.0), (20.0, 400.0)])
+    dl = np.stack([desc_with_bits(0)] * 3)
+    kr = kps([(150.0, 100.0)])
+    dr = np.stack([desc_with_bits(3)])
+    assert len(oracle.match_features(kl, dl, kr, dr, CAM)) == 0  # 150 > 300*1/3 = 100
+    kr = kps([(99.0, 100.0)])
+    assert len(oracle.match_features(kl, dl, kr, dr, CAM)) == 1
+
+
+def test_triangulate_small_disparity_is_none(oracle):
+    kl = kps([(300.0, 100.0), (200.0, 50.0)])
+    kr = kps([(299.75, 100.0), (180.0, 50.0)])
+    m = np.zeros(2, dtype=DMATCH_DTYPE)
+    m["query_idx"] = [0, 1]
+    m["train_idx"] = [0, 1]
+    pts, valid = oracle.triangulate(kl, kr, m, CAM)
+    assert list(valid) == [0, 1]
+    z = CAM["fx"] * CAM["baseline"] / 20.0
+    assert pts[1, 2] == z and pts[1, 0] == (200.0 - CAM["cx"]) * z / CAM["fx"]
+
+
+def test_grid_whole_cells_and_negative_wrap(oracle):
+    rng = np.random.default_rng(0)
+    k = kps(list(zip(rng.uniform(0, 752, 500), rng.uniform(0, 480, 500))))
+    cs, items = oracle.grid_build(k)
+    assert cs[-1] == 500 and sorted(items) == list(range(500))
+    # inside a cell ascending index
+    for c in range(64 * 48):
+        seg = items[cs[c]:cs[c + 1]]
+        assert list(seg) == sorted(seg)
+    # query fully left of the image: max cell wraps to the last column -> all 64 columns of the covered rows
+    got = oracle.grid_query(cs, items, -100.0, 240.0, 15.0)
+    rows = range(int(np.floor((240 - 15) * 48 / 480)), int(np.ceil((240 + 15) * 48 / 480)) + 1)
+    exp = [i for r in rows for i in items[cs[r * 64]:cs[r * 64 + 64]]]
+    assert list(got) == exp
+    # right of / below the grid: empty
+    assert len(oracle.grid_query(cs, items, 900.0, 240.0, 15.0)) == 0
+    assert len(oracle.grid_query(cs, items, 300.0, 700.0, 15.0)) == 0
+
+
+def test_search_modes(oracle):
+    k = kps([(100.0, 100.0), (102.0, 101.0), (400.0, 300.0)])
+    d = np.stack([desc_with_bits(0), desc_with_bits(40), desc_with_bits(0)])
+    uv = np.array([[101.0, 100.0], [401.0, 300.0], [-50.0, 300.0]])
+    md = np.stack([desc_with_bits(4), desc_with_bits(101), desc_with_bits(0)])
+    idx, dist = oracle.search_by_projection(k, d, uv, md, 0)
+    # mp0: ratio 4 <= .75*36 passes; mp1: 101 > TH_HIGH; mp2 projects LEFT of the image: the negative max cell wraps
+    # to the last column (SURVEY.md 8.C trap 6), so the whole row band is searched and keypoint 2 (d = 0) is found.
+    assert list(idx) == [0, -1, 2] and dist[0] == 4 and dist[2] == 0
+    idx1, _ = oracle.search_by_projection(k, d, uv, md, 1, bound_w=734.43, bound_h=496.75)
+    assert list(idx1) == [0, -1, -1]  # u<0 is rejected by the motion-model bounds check
