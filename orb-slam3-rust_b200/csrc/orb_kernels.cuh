@@ -4,10 +4,13 @@
 //   k_resize   A1  INTER_LINEAR_EXACT chain (Q8.8 x Q8.8 fixed point), one launch per level, batch in grid.y
 //   k_fast     A2  FAST-9/16 score for every pixel with DPX u16x2 min/max (VIMNMX3.U16x2), NMS, border filter,
 //                  raster-ordered emission per 16-row strip (no atomics on global memory, no sort)
-//   k_select   A3/A4  gather strips -> exact libstdc++ retainBest replay (warp-parallel Hoare passes) ->
-//                  Harris -> retainBest -> intensity-centroid angle
+//   k_select1  A3  gather strips -> exact libstdc++ retainBest(2N) replay on the FAST score (one warp per
+//                  (level, image), warp-parallel Hoare passes, records in shared memory)
+//   k_harris   A3  Harris response of every survivor (one thread per survivor)
+//   k_select2  A3  retainBest(N) replay on the Harris response
 //   k_blur     A5  separable 7-tap float32 FMA Gaussian, reflect-101, round-half-even
-//   k_brief    A6  steered BRIEF (one warp per keypoint, one descriptor byte per lane) + KeyPoint assembly
+//   k_brief    A4/A6  intensity-centroid angle + steered BRIEF (one warp per keypoint, one descriptor byte per
+//                  lane) + KeyPoint assembly
 //
 // Everything is integer / explicitly rounded float: the file is compiled with -fmad=false and uses the
 // __f*_rn intrinsics wherever the rounding sequence is part of the specification.
@@ -27,10 +30,9 @@ __device__ int g_brief_pattern[1024] = {
 #include "brief_pattern.inc"
 };
 
-struct __align__(4) LvlKp {
+struct __align__(8) LvlKp {
   unsigned xy;  // (y<<16)|x in level coordinates
-  float resp;
-  float angle;
+  float resp;   // Harris response
 };
 
 __device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int img, const uint8_t* in_l,
@@ -156,7 +158,7 @@ __host__ inline size_t fast_smem_bytes(int pitch) {
 // grid = (total_fast_strips, n_img), block = 256.
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
-                                              int* __restrict__ strip_cnt, vrec_t* __restrict__ strip_rec) {
+                                              int* __restrict__ strip_cnt, uint32_t* __restrict__ strip_rec) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int strip = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
   int l = 0;
@@ -178,11 +180,12 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
 
   // ---- stage the pixel tile (128-bit loads), clear margins / score tile / bitmask
   const int vpr = pitch >> 4;
-  for (int i = tid; i < (rows + 8) * vpr; i += 256) {
-    int r = i / vpr, c = i - r * vpr;
-    int gy = min(max(ys - 4 + r, 0), L.h - 1);
-    *reinterpret_cast<uint4*>(pix + r * SP + 16 + 16 * c) =
-        *reinterpret_cast<const uint4*>(img_base + (size_t)gy * pitch + 16 * c);
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < rows + 8; r += 8) {
+    const int gy = min(max(ys - 4 + r, 0), L.h - 1);
+    const uint4* srow = reinterpret_cast<const uint4*>(img_base + (size_t)gy * pitch);
+    uint4* drow = reinterpret_cast<uint4*>(pix + r * SP + 16);
+    for (int c = lane; c < vpr; c += 32) drow[c] = srow[c];
   }
   for (int i = tid; i < (rows + 8) * 2; i += 256) {
     int r = i >> 1;
@@ -199,8 +202,9 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   const int gx0 = sx0 >> 2, ngx = ((sx1 - 1) >> 2) - gx0 + 1;
   const int nsr = sy_hi - sy_lo;
   const unsigned t2 = (unsigned)P.fast_threshold * 0x00010001u;
+  const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
   for (int it = tid; it < nsr * ngx; it += 256) {
-    const int ry = it / ngx;
+    const int ry = (int)__umulhi((unsigned)it, inv_ngx);
     const int g = gx0 + (it - ry * ngx);
     const int y = sy_lo + ry;
     const uint8_t* base = pix + (y - (ys - 4)) * SP + 16 + 4 * g;  // centre word of this group
@@ -252,8 +256,9 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
 
   // ---- non-maximum suppression (strictly greater than the 8 neighbours) + runByImageBorder
   const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
+  const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
   for (int it = tid; it < rows * negx; it += 256) {
-    const int ry = it / negx;
+    const int ry = (int)__umulhi((unsigned)it, inv_negx);
     const int g = egx0 + (it - ry * negx);
     const uint8_t* srow = sc + (ry + 1) * SP + 16;
     unsigned word = *reinterpret_cast<const uint32_t*>(srow + 4 * g);
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
     if (tid == 31) s_total = incl;
   }
   __syncthreads();
-  vrec_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
+  uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
   for (int wi = tid; wi < nwords; wi += 256) {
     unsigned bw = bits[wi];
     if (!bw) continue;
@@ -304,9 +309,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
       int b = __ffs(bw) - 1;
       bw &= bw - 1;
       int x = xb + b;
-      int score = (int)sc[(ry + 1) * SP + 16 + x] + P.fast_threshold - 1;  // S - 1
-      unsigned xy = ((unsigned)(ys + ry) << 16) | (unsigned)x;
-      out[off++] = ((vrec_t)__float_as_uint((float)score) << 32) | xy;
+      unsigned score = (unsigned)sc[(ry + 1) * SP + 16 + x] + (unsigned)P.fast_threshold - 1u;  // S - 1 <= 254
+      out[off++] = (score << 24) | ((unsigned)(ys + ry) << 12) | (unsigned)x;
     }
   }
   if (tid == 0) strip_cnt[(long long)img * P.total_fast_strips + strip] = s_total;
@@ -319,27 +323,28 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
 // pass is: two ordered stream compactions (ballot + popc), a count, and a parallel swap.  The cut the serial
 // algorithm returns is min(L_{K+1}, R_K).  (Checked against libstdc++ in tests/test_select_replay.py.)
 // ----------------------------------------------------------------------------------------------------------
-template <typename IdxT>
-__device__ int warp_partition_pivot(vrec_t* rec, int first, int last, IdxT* Ll, IdxT* Rl, int lane) {
+template <typename T, typename IdxT>
+__device__ int warp_partition_pivot(T* rec, int first, int last, IdxT* Ll, IdxT* Rl, int lane) {
   if (lane == 0) vsel::median_to_first(rec, first, first + 1, first + (last - first) / 2, last - 1);
   __syncwarp();
-  const float p = vsel::resp_of(rec[first]);
+  const T pivot = rec[first];
   const unsigned lt = (1u << lane) - 1u;
-  int nR = 0;
-  for (int base = last - 1; base >= first; base -= 32) {  // right stoppers: !(pivot > v[j]), descending j
-    int j = base - lane;
-    bool st = (j >= first) && !(p > vsel::resp_of(rec[j]));
-    unsigned m = __ballot_sync(VSLAM_FULL, st);
-    if (st) Rl[nR + __popc(m & lt)] = (IdxT)j;
-    nR += __popc(m);
-  }
-  int nL = 0;
-  for (int base = first + 1; base < last; base += 32) {  // left stoppers: !(v[i] > pivot), ascending i
-    int i = base + lane;
-    bool st = (i < last) && !(vsel::resp_of(rec[i]) > p);
-    unsigned m = __ballot_sync(VSLAM_FULL, st);
-    if (st) Ll[nL + __popc(m & lt)] = (IdxT)i;
-    nL += __popc(m);
+  int nR = 0, nL = 0;
+  // right stoppers: !(pivot > v[j]), j descending over [first, last);  left stoppers: !(v[i] > pivot), i ascending
+  // over [first+1, last).  Both scans advance in the same iteration so their loads overlap.
+  const int len = last - first;
+  for (int o = 0; o < len; o += 32) {
+    const int j = last - 1 - o - lane;
+    const int i = first + 1 + o + lane;
+    const bool inj = j >= first, ini = i < last;
+    const T vj = inj ? rec[j] : pivot, vi = ini ? rec[i] : pivot;
+    const bool sr = inj && !vsel::comp(pivot, vj);
+    const bool sl = ini && !vsel::comp(vi, pivot);
+    const unsigned mr = __ballot_sync(VSLAM_FULL, sr), ml = __ballot_sync(VSLAM_FULL, sl);
+    if (sr) Rl[nR + __popc(mr & lt)] = (IdxT)j;
+    if (sl) Ll[nL + __popc(ml & lt)] = (IdxT)i;
+    nR += __popc(mr);
+    nL += __popc(ml);
   }
   __syncwarp();
   const int nmin = min(nL, nR);
@@ -356,7 +361,7 @@ __device__ int warp_partition_pivot(vrec_t* rec, int first, int last, IdxT* Ll, 
   if (K > 0) cut = min(cut, (int)Rl[K - 1]);
   for (int k = lane; k < K; k += 32) {
     int a = (int)Ll[k], b = (int)Rl[k];
-    vrec_t t = rec[a];
+    T t = rec[a];
     rec[a] = rec[b];
     rec[b] = t;
   }
@@ -365,8 +370,8 @@ __device__ int warp_partition_pivot(vrec_t* rec, int first, int last, IdxT* Ll, 
 }
 
 // Returns the retained count; rec[0..count) is exactly what std::vector<KeyPoint> holds after retainBest(n_points).
-template <typename IdxT>
-__device__ int warp_retain_best(vrec_t* rec, int n, int n_points, IdxT* Ll, IdxT* Rl, int lane) {
+template <typename T, typename IdxT>
+__device__ int warp_retain_best(T* rec, int n, int n_points, IdxT* Ll, IdxT* Rl, int lane) {
   if (n_points < 0 || n <= n_points) return n;
   if (n_points == 0) return 0;
   const int nth = n_points - 1;
@@ -380,7 +385,7 @@ __device__ int warp_retain_best(vrec_t* rec, int n, int n_points, IdxT* Ll, IdxT
       break;
     }
     --depth;
-    int cut = warp_partition_pivot<IdxT>(rec, first, last, Ll, Rl, lane);
+    int cut = warp_partition_pivot<T, IdxT>(rec, first, last, Ll, Rl, lane);
     if (cut <= nth) first = cut;
     else last = cut;
   }
@@ -388,23 +393,19 @@ __device__ int warp_retain_best(vrec_t* rec, int n, int n_points, IdxT* Ll, IdxT
   __syncwarp();
   // std::partition(v + n_points, end, resp >= thr): the k-th failing element from the left swaps with the k-th
   // passing element from the right while A_k < B_k; only the kept front part is materialised.
-  const float thr = vsel::resp_of(rec[nth]);
+  const T thr = rec[nth];
   const unsigned lt = (1u << lane) - 1u;
-  int nB = 0;
-  for (int base = n - 1; base >= n_points; base -= 32) {
-    int j = base - lane;
-    bool st = (j >= n_points) && (vsel::resp_of(rec[j]) >= thr);
-    unsigned m = __ballot_sync(VSLAM_FULL, st);
-    if (st) Rl[nB + __popc(m & lt)] = (IdxT)j;
-    nB += __popc(m);
-  }
-  int nA = 0;
-  for (int base = n_points; base < n; base += 32) {
-    int i = base + lane;
-    bool st = (i < n) && !(vsel::resp_of(rec[i]) >= thr);
-    unsigned m = __ballot_sync(VSLAM_FULL, st);
-    if (st) Ll[nA + __popc(m & lt)] = (IdxT)i;
-    nA += __popc(m);
+  int nB = 0, nA = 0;
+  for (int o = 0; o < n - n_points; o += 32) {
+    const int j = n - 1 - o - lane, i = n_points + o + lane;
+    const bool inj = j >= n_points, ini = i < n;
+    const bool sb = inj && !vsel::comp(thr, rec[inj ? j : nth]);   // resp >= thr
+    const bool sa = ini && vsel::comp(thr, rec[ini ? i : nth]);    // !(resp >= thr)
+    const unsigned mb = __ballot_sync(VSLAM_FULL, sb), ma = __ballot_sync(VSLAM_FULL, sa);
+    if (sb) Rl[nB + __popc(mb & lt)] = (IdxT)j;
+    if (sa) Ll[nA + __popc(ma & lt)] = (IdxT)i;
+    nB += __popc(mb);
+    nA += __popc(ma);
   }
   __syncwarp();
   const int nmin = min(nA, nB);
@@ -505,123 +506,124 @@ __device__ float ic_angle_warp(const uint8_t* __restrict__ img, int pitch, int x
   return fast_atan2_deg(__int2float_rn(m01), __int2float_rn(m10));
 }
 
-__host__ inline size_t select_smem_bytes(int cap) { return (size_t)cap * (sizeof(vrec_t) + 2 * sizeof(uint16_t)) + 16; }
+__host__ inline size_t select1_smem_bytes(int cap) { return (size_t)cap * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) + 16; }
+__host__ inline size_t select2_smem_bytes(int cap) { return (size_t)cap * (sizeof(vrec_t) + 2 * sizeof(uint16_t)) + 16; }
 
-// One launch per level: grid = (1, n_img), block = 128.  Dynamic smem = select_smem_bytes(P.sel_smem_cap).
-// When a level holds more corners than sel_smem_cap (or than 65535) the replay runs in global memory
-// (in place in the strip-record slab, 32-bit index lists in `glists`).
-__global__ void __launch_bounds__(128) k_select(const __grid_constant__ PyrP P, const int l,
-                                                const uint8_t* __restrict__ in_l,
-                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
-                                                const int* __restrict__ strip_cnt, vrec_t* __restrict__ strip_rec,
-                                                uint32_t* __restrict__ glists, LvlKp* __restrict__ lvl_kp,
-                                                int* __restrict__ lvl_cnt, float harris_scale4,
-                                                const FrameLayout F) {
+// retainBest(2 * N_l) on the FAST score.  grid = (n_img, nlevels) — level 0 (the longest problems) is scheduled
+// first — block = 32 (one warp per problem).  Dynamic smem = select1_smem_bytes(smem_cap).
+// In: per-strip raster-ordered corner lists of k_fast.  Out: sel1[level region][0..m1), sel1_cnt[img][level].
+// A level with more corners than smem_cap (or 65535) is replayed in global memory (sel1 as the work array,
+// 32-bit index lists in glists) — slower, same result.
+__global__ void __launch_bounds__(32) k_select1(const __grid_constant__ PyrP P, int smem_cap,
+                                                const int* __restrict__ strip_cnt,
+                                                const uint32_t* __restrict__ strip_rec, uint32_t* __restrict__ sel1,
+                                                uint32_t* __restrict__ glists, int* __restrict__ sel1_cnt) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ int s_off[128];
-  __shared__ int s_n;
-  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_off[129];
+  const int img = blockIdx.x, l = blockIdx.y, lane = threadIdx.x;
   const LevelP& L = P.lv[l];
   const int* cnt = strip_cnt + (long long)img * P.total_fast_strips + L.fast_strip0;
-  vrec_t* lrec = strip_rec + (long long)img * P.rec_img_stride + L.rec_off;
-
-  // ---- strip offsets (nstrips <= 128 enforced by the host)
-  if (warp == 0) {
-    int run = 0;
-    for (int b = 0; b < L.fast_nstrips; b += 32) {
-      int i = b + lane;
-      int c = i < L.fast_nstrips ? cnt[i] : 0;
-      int incl = c;
+  const uint32_t* lrec = strip_rec + (long long)img * P.rec_img_stride + L.rec_off;
+  uint32_t* out = sel1 + (long long)img * P.rec_img_stride + L.rec_off;
+  // strip offsets (nstrips <= 128)
+  int run = 0;
+  for (int b = 0; b < L.fast_nstrips; b += 32) {
+    int i = b + lane;
+    int c = i < L.fast_nstrips ? cnt[i] : 0;
+    int incl = c;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(VSLAM_FULL, incl, d);
-        if (lane >= d) incl += o;
-      }
-      if (i < L.fast_nstrips) s_off[i] = run + incl - c;
-      run += __shfl_sync(VSLAM_FULL, incl, 31);
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+      if (lane >= d) incl += o;
     }
-    if (lane == 0) s_n = run;
+    if (i < L.fast_nstrips) s_off[i] = run + incl - c;
+    run += __shfl_sync(VSLAM_FULL, incl, 31);
   }
-  __syncthreads();
-  const int n_in = s_n;
-  const bool use_smem = n_in <= P.sel_smem_cap && n_in <= 65535;
-  vrec_t* rec;
+  if (lane == 0) s_off[L.fast_nstrips] = run;
+  __syncwarp();
+  const int n_in = run;
+  const bool use_smem = n_in <= smem_cap && n_in <= 65535;
+  uint32_t* rec = use_smem ? reinterpret_cast<uint32_t*>(smem) : out;
+  // gather: flat index -> strip by binary search over the offsets (every load independent)
+  for (int i = lane; i < n_in; i += 32) {
+    int lo = 0, hi = L.fast_nstrips - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= i) lo = mid;
+      else hi = mid - 1;
+    }
+    rec[i] = lrec[(long long)lo * L.strip_cap + (i - s_off[lo])];
+  }
+  __syncwarp();
+  int m;
   if (use_smem) {
-    rec = reinterpret_cast<vrec_t*>(smem);
-    for (int s = 0; s < L.fast_nstrips; ++s) {
-      const vrec_t* src = lrec + (long long)s * L.strip_cap;
-      const int c = cnt[s], o = s_off[s];
-      for (int i = tid; i < c; i += 128) rec[o + i] = src[i];
-    }
+    uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)smem_cap * sizeof(uint32_t));
+    m = warp_retain_best<uint32_t, uint16_t>(rec, n_in, 2 * L.nfeat, l16, l16 + smem_cap, lane);
+    for (int i = lane; i < m; i += 32) out[i] = rec[i];
   } else {
-    // compact the strips in place, strip by strip (destination never overtakes a later strip's source)
-    rec = lrec;
-    for (int s = 1; s < L.fast_nstrips; ++s) {
-      const vrec_t* src = lrec + (long long)s * L.strip_cap;
-      const int c = cnt[s], o = s_off[s];
-      for (int b = 0; b < c; b += 128) {
-        int i = b + tid;
-        vrec_t v = i < c ? src[i] : 0;
-        __syncthreads();
-        if (i < c) rec[o + i] = v;
-        __syncthreads();
-      }
-    }
+    uint32_t* l32 = glists + 2 * ((long long)img * P.rec_img_stride + L.rec_off);
+    m = warp_retain_best<uint32_t, uint32_t>(rec, n_in, 2 * L.nfeat, l32, l32 + (long long)L.fast_nstrips * L.strip_cap,
+                                             lane);
   }
-  __syncthreads();
+  if (lane == 0) sel1_cnt[(long long)img * P.nlevels + l] = m;
+}
 
-  // ---- retainBest(2 * N_l) on the FAST score
-  uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)P.sel_smem_cap * sizeof(vrec_t));
-  uint16_t* r16 = l16 + P.sel_smem_cap;
-  uint32_t* l32 = glists + 2 * ((long long)img * P.rec_img_stride + L.rec_off);
-  uint32_t* r32 = l32 + (long long)L.fast_nstrips * L.strip_cap;
-  if (warp == 0) {
-    int m = use_smem ? warp_retain_best<uint16_t>(rec, n_in, 2 * L.nfeat, l16, r16, lane)
-                     : warp_retain_best<uint32_t>(rec, n_in, 2 * L.nfeat, l32, r32, lane);
-    if (lane == 0) s_n = m;
-  }
-  __syncthreads();
-  const int m1 = s_n;
-
-  // ---- Harris response of every survivor
+// Harris response of every select1 survivor: grid = (blocks, nlevels, n_img), block = 128, thread per survivor.
+__global__ void __launch_bounds__(128) k_harris(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                                const uint32_t* __restrict__ sel1, const int* __restrict__ sel1_cnt,
+                                                vrec_t* __restrict__ cand, float harris_scale4) {
+  const int l = blockIdx.y, img = blockIdx.z;
+  const int m = sel1_cnt[(long long)img * P.nlevels + l];
+  const LevelP& L = P.lv[l];
   int pitch;
   const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
-  for (int i = tid; i < m1; i += 128) {
-    vrec_t r = rec[i];
-    unsigned xy = (unsigned)r;
-    float h = harris_response(img_base, pitch, (int)(xy & 0xffffu), (int)(xy >> 16), harris_scale4);
-    rec[i] = ((vrec_t)__float_as_uint(h) << 32) | xy;
+  const long long base = (long long)img * P.rec_img_stride + L.rec_off;
+  for (int i = blockIdx.x * 128 + threadIdx.x; i < m; i += gridDim.x * 128) {
+    const uint32_t r = sel1[base + i];
+    const int x = (int)(r & 0xfffu), y = (int)((r >> 12) & 0xfffu);
+    const float h = harris_response(img_base, pitch, x, y, harris_scale4);
+    cand[base + i] = ((vrec_t)__float_as_uint(h) << 32) | ((unsigned)y << 16) | (unsigned)x;
   }
-  __syncthreads();
+}
 
-  // ---- retainBest(N_l) on the Harris response
-  if (warp == 0) {
-    int m = use_smem ? warp_retain_best<uint16_t>(rec, m1, L.nfeat, l16, r16, lane)
-                     : warp_retain_best<uint32_t>(rec, m1, L.nfeat, l32, r32, lane);
-    if (lane == 0) s_n = m;
+// retainBest(N_l) on the Harris response.  grid = (n_img, nlevels), block = 32.  Dynamic smem =
+// select2_smem_bytes(smem_cap).  Out: lvl_kp[img][level][0..m2), lvl_cnt[img][level].
+__global__ void __launch_bounds__(32) k_select2(const __grid_constant__ PyrP P, int smem_cap,
+                                                vrec_t* __restrict__ cand, const int* __restrict__ sel1_cnt,
+                                                uint32_t* __restrict__ glists, LvlKp* __restrict__ lvl_kp,
+                                                int* __restrict__ lvl_cnt, const FrameLayout F) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int img = blockIdx.x, l = blockIdx.y, lane = threadIdx.x;
+  const LevelP& L = P.lv[l];
+  const int m1 = sel1_cnt[(long long)img * P.nlevels + l];
+  vrec_t* gl = cand + (long long)img * P.rec_img_stride + L.rec_off;
+  const bool use_smem = m1 <= smem_cap && m1 <= 65535;
+  vrec_t* rec = use_smem ? reinterpret_cast<vrec_t*>(smem) : gl;
+  if (use_smem)
+    for (int i = lane; i < m1; i += 32) rec[i] = gl[i];
+  __syncwarp();
+  int m2;
+  if (use_smem) {
+    uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)smem_cap * sizeof(vrec_t));
+    m2 = warp_retain_best<vrec_t, uint16_t>(rec, m1, L.nfeat, l16, l16 + smem_cap, lane);
+  } else {
+    uint32_t* l32 = glists + 2 * ((long long)img * P.rec_img_stride + L.rec_off);
+    m2 = warp_retain_best<vrec_t, uint32_t>(rec, m1, L.nfeat, l32, l32 + (long long)L.fast_nstrips * L.strip_cap, lane);
   }
-  __syncthreads();
-  int m2 = s_n;
   if (m2 > P.kp_cap) {  // more ties than the handle was sized for: flag, keep the first kp_cap
-    if (tid == 0) atomicMax(&F.hdr[img / P.eyes].status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
+    if (lane == 0) atomicMax(&F.hdr[img / P.eyes].status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
     m2 = P.kp_cap;
   }
-
-  // ---- orientation, one warp per keypoint
   LvlKp* out = lvl_kp + ((long long)img * P.nlevels + l) * P.kp_cap;
-  for (int i = warp; i < m2; i += 4) {
-    vrec_t r = rec[i];
-    unsigned xy = (unsigned)r;
-    float ang = ic_angle_warp(img_base, pitch, (int)(xy & 0xffffu), (int)(xy >> 16), lane);
-    if (lane == 0) {
-      LvlKp k;
-      k.xy = xy;
-      k.resp = __uint_as_float((unsigned)(r >> 32));
-      k.angle = ang;
-      out[i] = k;
-    }
+  for (int i = lane; i < m2; i += 32) {
+    const vrec_t r = rec[i];
+    LvlKp k;
+    k.xy = (unsigned)r;
+    k.resp = __uint_as_float((unsigned)(r >> 32));
+    out[i] = k;
   }
-  if (tid == 0) lvl_cnt[(long long)img * P.nlevels + l] = m2;
+  if (lane == 0) lvl_cnt[(long long)img * P.nlevels + l] = m2;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -751,9 +753,10 @@ struct __align__(4) KeyPoint28 {
   int octave, class_id;
 };
 
-__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ blur,
-                                               const LvlKp* __restrict__ lvl_kp, const int* __restrict__ lvl_cnt,
-                                               const FrameLayout F) {
+__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                               const uint8_t* __restrict__ blur, const LvlKp* __restrict__ lvl_kp,
+                                               const int* __restrict__ lvl_cnt, const FrameLayout F) {
   const int img = blockIdx.y, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int frame = img / P.eyes, eye = img - frame * P.eyes;
@@ -776,19 +779,22 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   const LevelP& L = P.lv[l];
   const LvlKp kp = lvl_kp[((long long)img * P.nlevels + l) * P.kp_cap + jl];
   const int cx = (int)(kp.xy & 0xffffu), cy = (int)(kp.xy >> 16);
+  int upitch;
+  const uint8_t* unblurred = level_ptr(P, l, img, in_l, in_r, pyr, upitch);
+  const float angle = ic_angle_warp(unblurred, upitch, cx, cy, lane);  // A4, on the un-blurred level
   if (lane == 0) {
     KeyPoint28 o;
     o.x = __fmul_rn(__int2float_rn(cx), L.scale);
     o.y = __fmul_rn(__int2float_rn(cy), L.scale);
     o.size = __fmul_rn(31.0f, L.scale);
-    o.angle = kp.angle;
+    o.angle = angle;
     o.response = kp.resp;
     o.octave = l;
     o.class_id = -1;
     reinterpret_cast<KeyPoint28*>(F.kp[eye] + (long long)frame * F.kp_stride)[j] = o;
   }
   // angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)   (double cos/sin of the f32 angle)
-  const float rad = __fmul_rn(kp.angle, (float)(3.141592653589793238462643383279502884 / 180.0));
+  const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
   const float a = (float)cos((double)rad), b = (float)sin((double)rad);
   const uint8_t* center = blur + (long long)img * P.blur_img_stride + L.blur_off + (size_t)cy * L.pitch + cx;
   const int4* pat = reinterpret_cast<const int4*>(g_brief_pattern) + 8 * lane;  // 32 ints = 16 points per lane

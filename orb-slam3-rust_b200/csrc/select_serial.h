@@ -16,6 +16,10 @@
 
 namespace vsel {
 
+// Two record types are permuted by the replay:
+//   vrec_t   (64 bit)  hi = float bits of the Harris response, lo = (y<<16)|x        -> retainBest(N) on Harris
+//   uint32_t (32 bit)  FAST score (S-1, 8 bit) << 24 | y << 12 | x  (w, h <= 4096)   -> retainBest(2N) on FAST score
+// comp(a,b) := a.response > b.response  (cv::KeypointResponseGreater)
 VSLAM_HD float resp_of(vrec_t r) {
   unsigned u = (unsigned)(r >> 32);
 #if defined(__CUDA_ARCH__)
@@ -26,17 +30,22 @@ VSLAM_HD float resp_of(vrec_t r) {
   return f;
 #endif
 }
-// comp(a,b) := a.response > b.response  (KeypointResponseGreater)
-VSLAM_HD bool comp(vrec_t a, vrec_t b) { return resp_of(a) > resp_of(b); }
+VSLAM_HD unsigned resp_of(uint32_t r) { return r >> 24; }
+template <typename T>
+VSLAM_HD bool comp(T a, T b) {
+  return resp_of(a) > resp_of(b);
+}
 
-VSLAM_HD void swap_rec(vrec_t* v, int i, int j) {
-  vrec_t t = v[i];
+template <typename T>
+VSLAM_HD void swap_rec(T* v, int i, int j) {
+  T t = v[i];
   v[i] = v[j];
   v[j] = t;
 }
 
 // std::__move_median_to_first(result=first, a=first+1, b=mid, c=last-1)
-VSLAM_HD void median_to_first(vrec_t* v, int first, int a, int b, int c) {
+template <typename T>
+VSLAM_HD void median_to_first(T* v, int first, int a, int b, int c) {
   if (comp(v[a], v[b])) {
     if (comp(v[b], v[c])) swap_rec(v, first, b);
     else if (comp(v[a], v[c])) swap_rec(v, first, c);
@@ -47,10 +56,11 @@ VSLAM_HD void median_to_first(vrec_t* v, int first, int a, int b, int c) {
 }
 
 // std::__insertion_sort on [first,last)
-VSLAM_HD void insertion_sort(vrec_t* v, int first, int last) {
+template <typename T>
+VSLAM_HD void insertion_sort(T* v, int first, int last) {
   if (first == last) return;
   for (int i = first + 1; i != last; ++i) {
-    vrec_t val = v[i];
+    T val = v[i];
     if (comp(val, v[first])) {
       for (int k = i; k > first; --k) v[k] = v[k - 1];
       v[first] = val;
@@ -67,7 +77,8 @@ VSLAM_HD void insertion_sort(vrec_t* v, int first, int last) {
 }
 
 // std::__push_heap
-VSLAM_HD void push_heap(vrec_t* v, int hole, int top, vrec_t val) {
+template <typename T>
+VSLAM_HD void push_heap(T* v, int hole, int top, T val) {
   int parent = (hole - 1) / 2;
   while (hole > top && comp(v[parent], val)) {
     v[hole] = v[parent];
@@ -78,7 +89,8 @@ VSLAM_HD void push_heap(vrec_t* v, int hole, int top, vrec_t val) {
 }
 
 // std::__adjust_heap on the heap v[0..len)
-VSLAM_HD void adjust_heap(vrec_t* v, int hole, int len, vrec_t val) {
+template <typename T>
+VSLAM_HD void adjust_heap(T* v, int hole, int len, T val) {
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
@@ -96,14 +108,15 @@ VSLAM_HD void adjust_heap(vrec_t* v, int hole, int len, vrec_t val) {
 }
 
 // std::__heap_select(first, middle, last) followed by iter_swap(first, nth) — the introselect fallback.
-VSLAM_HD void heap_select_fallback(vrec_t* v, int first, int nth, int last) {
-  vrec_t* h = v + first;
+template <typename T>
+VSLAM_HD void heap_select_fallback(T* v, int first, int nth, int last) {
+  T* h = v + first;
   const int middle = nth + 1 - first;  // heap length
   const int n = last - first;
   if (middle >= 2) {  // std::__make_heap
     int parent = (middle - 2) / 2;
     while (true) {
-      vrec_t val = h[parent];
+      T val = h[parent];
       adjust_heap(h, parent, middle, val);
       if (parent == 0) break;
       parent--;
@@ -111,7 +124,7 @@ VSLAM_HD void heap_select_fallback(vrec_t* v, int first, int nth, int last) {
   }
   for (int i = middle; i < n; ++i) {
     if (comp(h[i], h[0])) {  // std::__pop_heap(first, middle, i)
-      vrec_t val = h[i];
+      T val = h[i];
       h[i] = h[0];
       adjust_heap(h, 0, middle, val);
     }

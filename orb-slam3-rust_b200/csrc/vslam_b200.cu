@@ -42,8 +42,11 @@ struct Slot {
   uint8_t* d_pyr = nullptr;
   uint8_t* d_blur = nullptr;
   int* d_strip_cnt = nullptr;
-  vrec_t* d_strip_rec = nullptr;
-  uint32_t* d_glists = nullptr;
+  uint32_t* d_strip_rec = nullptr;  // k_fast: per-strip raster-ordered corners (score<<24 | y<<12 | x)
+  uint32_t* d_sel1 = nullptr;       // k_select1: retainBest(2N) survivors per level
+  int* d_sel1_cnt = nullptr;
+  vrec_t* d_cand = nullptr;         // k_harris: survivors with Harris response
+  uint32_t* d_glists = nullptr;     // index lists of the global-memory selection fallback
   vk::LvlKp* d_lvl_kp = nullptr;
   int* d_lvl_cnt = nullptr;
   unsigned char* d_res = nullptr;  // one block, carved into the SoA result arrays (d_lay)
@@ -74,7 +77,8 @@ struct vslam_handle_s {
   uint32_t* d_coef = nullptr;
   size_t resize_smem[VSLAM_MAX_LEVELS] = {0};
   size_t fast_smem = 0;
-  int sel_cap[VSLAM_MAX_LEVELS] = {0};
+  int sel1_cap = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
+  int harris_blocks = 1;
   size_t in_img_bytes = 0;
   Slot slots[NSLOT];
   std::string err;
@@ -193,11 +197,6 @@ int build_params(vslam_handle h) {
     L.blur_ty = (L.h + VSLAM_BLUR_TH - 1) / VSLAM_BLUR_TH;
     L.blur_tile0 = tile0;
     tile0 += L.blur_tx * L.blur_ty;
-    // selection scratch kept in shared memory up to ~2.5% of the emission pixels (typical corner density < 2%)
-    long long epx = (long long)(L.ex1 - L.ex0) * (L.ey1 - L.ey0);
-    int cap = (int)std::min<long long>(std::max<long long>(epx / 40, 1024), 16000);
-    cap = std::min<int>(cap, (int)std::max<long long>((long long)L.fast_nstrips * L.strip_cap, 64));
-    h->sel_cap[l] = (cap + 7) & ~7;
   }
   P.total_fast_strips = strip0;
   P.total_blur_tiles = tile0;
@@ -234,6 +233,16 @@ int build_params(vslam_handle h) {
     h->resize_smem[l] = (size_t)max_rows * Sx.pitch;
   }
   h->fast_smem = vk::fast_smem_bytes(P.in_pitch);
+  // selection scratch in shared memory: select1 sized for ~3% corner density on the largest level (typical < 2%),
+  // select2 for 2N_l plus ties; anything larger is replayed in global memory.
+  {
+    long long epx0 = (long long)(P.lv[0].ex1 - P.lv[0].ex0) * (P.lv[0].ey1 - P.lv[0].ey0);
+    h->sel1_cap = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 24000) & ~7;
+    int max2n = 0;
+    for (int l = 0; l < P.nlevels; ++l) max2n = std::max(max2n, 2 * P.lv[l].nfeat);
+    h->sel2_cap = std::min((max2n + max2n / 4 + 64 + 7) & ~7, 16000);
+    h->harris_blocks = std::max(1, (max2n + 127) / 128);
+  }
   // HarrisResponses scale: scale = 1/((1<<2)*7*255.f); scale^4 = ((s*s)*s)*s   (f32, one rounding per op)
   {
     volatile float s = 1.f / ((1 << 2) * 7 * 255.f);
@@ -291,7 +300,10 @@ int alloc_slot(vslam_handle h, Slot& s) {
   CU_TRY(h, cudaMalloc(&s.d_pyr, nimg * (size_t)P.pyr_img_stride));
   CU_TRY(h, cudaMalloc(&s.d_blur, nimg * (size_t)P.blur_img_stride));
   CU_TRY(h, cudaMalloc(&s.d_strip_cnt, nimg * std::max(P.total_fast_strips, 1) * sizeof(int)));
-  CU_TRY(h, cudaMalloc(&s.d_strip_rec, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(vrec_t)));
+  CU_TRY(h, cudaMalloc(&s.d_strip_rec, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
+  CU_TRY(h, cudaMalloc(&s.d_sel1, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
+  CU_TRY(h, cudaMalloc(&s.d_sel1_cnt, nimg * P.nlevels * sizeof(int)));
+  CU_TRY(h, cudaMalloc(&s.d_cand, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(vrec_t)));
   CU_TRY(h, cudaMalloc(&s.d_glists, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * 2 * sizeof(uint32_t)));
   CU_TRY(h, cudaMalloc(&s.d_lvl_kp, nimg * P.nlevels * (size_t)h->kp_cap * sizeof(vk::LvlKp)));
   CU_TRY(h, cudaMalloc(&s.d_lvl_cnt, nimg * P.nlevels * sizeof(int)));
@@ -310,6 +322,7 @@ int alloc_slot(vslam_handle h, Slot& s) {
 void free_slot(Slot& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
   cudaFree(s.d_in); cudaFree(s.d_pyr); cudaFree(s.d_blur); cudaFree(s.d_strip_cnt); cudaFree(s.d_strip_rec);
+  cudaFree(s.d_sel1); cudaFree(s.d_sel1_cnt); cudaFree(s.d_cand);
   cudaFree(s.d_glists); cudaFree(s.d_lvl_kp); cudaFree(s.d_lvl_cnt); cudaFree(s.d_res); cudaFree(s.d_ml);
   if (s.h_in) cudaFreeHost(s.h_in);
   if (s.h_res) cudaFreeHost(s.h_res);
@@ -355,13 +368,14 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     h->launches++;
   }
   mark();  // 2
-  for (int l = 0; l < P.nlevels; ++l) {
-    PyrP Pl = P;
-    Pl.sel_smem_cap = h->sel_cap[l];
-    vk::k_select<<<dim3(1, nimg), 128, vk::select_smem_bytes(h->sel_cap[l]), st>>>(
-        Pl, l, in_l, in_r, s.d_pyr, s.d_strip_cnt, s.d_strip_rec, s.d_glists, s.d_lvl_kp, s.d_lvl_cnt,
-        h->harris_scale4, s.d_lay);
-    h->launches++;
+  {
+    vk::k_select1<<<dim3(nimg, P.nlevels), 32, vk::select1_smem_bytes(h->sel1_cap), st>>>(
+        P, h->sel1_cap, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
+    vk::k_harris<<<dim3(h->harris_blocks, P.nlevels, nimg), 128, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_sel1, s.d_sel1_cnt,
+                                                                       s.d_cand, h->harris_scale4);
+    vk::k_select2<<<dim3(nimg, P.nlevels), 32, vk::select2_smem_bytes(h->sel2_cap), st>>>(
+        P, h->sel2_cap, s.d_cand, s.d_sel1_cnt, s.d_glists, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    h->launches += 3;
   }
   mark();  // 3
   {
@@ -372,7 +386,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   mark();  // 4
   {
     dim3 grid((P.kp_cap + 7) / 8, nimg);
-    vk::k_brief<<<grid, 256, 0, st>>>(P, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    vk::k_brief<<<grid, 256, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
     h->launches++;
   }
   mark();  // 5
@@ -513,13 +527,19 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
         const bool pinned = is_pinned_host(src[0]) && is_pinned_host(src[frames - 1]);
         bool contiguous = true;
         for (int f = 1; f < frames && contiguous; ++f) contiguous = src[f] == src[0] + (size_t)f * H * stride;
-        if (pinned && contiguous) {
+        const bool packed = stride == (size_t)P.in_pitch;  // rows already at the device pitch: plain 1-D copies
+        if (pinned && contiguous && packed) {
+          CU_TRY(h, cudaMemcpyAsync(dst, src[0], (size_t)frames * ib, cudaMemcpyHostToDevice, s.stream));
+        } else if (pinned && contiguous) {
           CU_TRY(h, cudaMemcpy2DAsync(dst, P.in_pitch, src[0], stride, W, (size_t)frames * H, cudaMemcpyHostToDevice,
                                       s.stream));
         } else if (pinned) {
-          for (int f = 0; f < frames; ++f)
-            CU_TRY(h, cudaMemcpy2DAsync(dst + (size_t)f * ib, P.in_pitch, src[f], stride, W, H, cudaMemcpyHostToDevice,
-                                        s.stream));
+          for (int f = 0; f < frames; ++f) {
+            if (packed) CU_TRY(h, cudaMemcpyAsync(dst + (size_t)f * ib, src[f], ib, cudaMemcpyHostToDevice, s.stream));
+            else
+              CU_TRY(h, cudaMemcpy2DAsync(dst + (size_t)f * ib, P.in_pitch, src[f], stride, W, H, cudaMemcpyHostToDevice,
+                                          s.stream));
+          }
         } else {
           for (int f = 0; f < frames; ++f) {
             if (stride == (size_t)P.in_pitch) memcpy(hst + (size_t)f * ib, src[f], ib);
@@ -613,7 +633,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (c.edge_threshold == 0) c.edge_threshold = 31;
   if (c.fast_threshold == 0) c.fast_threshold = 20;
   if (c.max_batch == 0) c.max_batch = 64;
-  if (c.width < 64 || c.height < 64 || c.width > 16384 || c.height > 2100)
+  if (c.width < 64 || c.height < 64 || c.width > 4096 || c.height > 2100)  // corner records pack x,y in 12 bits
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "unsupported image size %dx%d", c.width, c.height);
   if (c.n_features < 1 || c.n_features > 60000)
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "n_features out of range");
@@ -665,9 +685,9 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   cudaEventCreate(&h->ev_batch[0]);
   cudaEventCreate(&h->ev_batch[1]);
   // opt in to large dynamic shared memory where needed
-  size_t max_resize = 0, max_sel = 0;
+  size_t max_resize = 0;
   for (int l = 1; l < h->P.nlevels; ++l) max_resize = std::max(max_resize, h->resize_smem[l]);
-  for (int l = 0; l < h->P.nlevels; ++l) max_sel = std::max(max_sel, vk::select_smem_bytes(h->sel_cap[l]));
+  const size_t max_sel = std::max(vk::select1_smem_bytes(h->sel1_cap), vk::select2_smem_bytes(h->sel2_cap));
   const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
   if (h->fast_smem > lim || max_resize > lim || max_sel > lim) {
     fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image too wide for the shared-memory tiles (%zu/%zu/%zu > %zu bytes)",
@@ -676,7 +696,10 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   }
   cudaFuncSetAttribute(vk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem);
   cudaFuncSetAttribute(vk::k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(max_resize, 1024));
-  cudaFuncSetAttribute(vk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_sel);
+  cudaFuncSetAttribute(vk::k_select1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)vk::select1_smem_bytes(h->sel1_cap));
+  cudaFuncSetAttribute(vk::k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)vk::select2_smem_bytes(h->sel2_cap));
   for (int k = 0; k < NSLOT; ++k) {
     rc = alloc_slot(h, h->slots[k]);
     if (rc != VSLAM_OK) return bail(rc == VSLAM_ERR_CUDA ? VSLAM_ERR_OUT_OF_MEMORY : rc);
@@ -835,20 +858,16 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
   CU_TRY(h, cudaMemcpy(cnt.data(), s.d_strip_cnt + (size_t)image * P.total_fast_strips + L.fast_strip0,
                        sizeof(int) * L.fast_nstrips, cudaMemcpyDeviceToHost));
   int n = 0;
-  std::vector<vrec_t> buf(std::max(L.strip_cap, 1));
+  std::vector<uint32_t> buf(std::max(L.strip_cap, 1));
   for (int st = 0; st < L.fast_nstrips; ++st) {
     CU_TRY(h, cudaMemcpy(buf.data(),
                          s.d_strip_rec + (size_t)image * (size_t)P.rec_img_stride + L.rec_off + (size_t)st * L.strip_cap,
-                         sizeof(vrec_t) * cnt[st], cudaMemcpyDeviceToHost));
+                         sizeof(uint32_t) * cnt[st], cudaMemcpyDeviceToHost));
     for (int i = 0; i < cnt[st]; ++i, ++n) {
       if (n >= capacity) continue;
-      unsigned xy = (unsigned)buf[i];
-      unsigned fb = (unsigned)(buf[i] >> 32);
-      float f;
-      memcpy(&f, &fb, 4);
-      xys[3 * n + 0] = (int)(xy & 0xffffu);
-      xys[3 * n + 1] = (int)(xy >> 16);
-      xys[3 * n + 2] = (int)f;
+      xys[3 * n + 0] = (int)(buf[i] & 0xfffu);
+      xys[3 * n + 1] = (int)((buf[i] >> 12) & 0xfffu);
+      xys[3 * n + 2] = (int)(buf[i] >> 24);
     }
   }
   *n_out = n;

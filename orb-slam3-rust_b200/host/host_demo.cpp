@@ -1,0 +1,64 @@
+// Compiled host-side consumer of the C ABI through the C++ mirror of the reference interface
+// (stereo_processor.hpp).  Reads two raw 8-bit images (w*h bytes each), runs StereoProcessor::process and prints a
+// checksum line that tests/test_gpu_host_cpp.py compares with the oracle.  Fails loudly without a GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+#include "stereo_processor.hpp"
+
+static std::vector<uint8_t> read_file(const char* path, size_t n) {
+  std::vector<uint8_t> v(n);
+  std::ifstream f(path, std::ios::binary);
+  if (!f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)n)) {
+    std::fprintf(stderr, "cannot read %zu bytes from %s\n", n, path);
+    std::exit(2);
+  }
+  return v;
+}
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 5) {
+    std::fprintf(stderr, "usage: host_demo left.raw right.raw width height [n_features]\n");
+    return 2;
+  }
+  const int w = std::atoi(argv[3]), h = std::atoi(argv[4]), nf = argc > 5 ? std::atoi(argv[5]) : 1200;
+  auto left = read_file(argv[1], (size_t)w * h), right = read_file(argv[2], (size_t)w * h);
+  vslam::CameraModel cam{458.654, 457.296, 367.215, 248.375, 0.110074};
+  auto sp = vslam::StereoProcessor::create(cam, nf, w, h, 0, 4);
+  if (!sp) {
+    std::fprintf(stderr, "StereoProcessor::create failed (%d): %s\n", sp.error().status, sp.error().message.c_str());
+    return 1;
+  }
+  auto fr = sp.value().process({left.data(), (size_t)w}, {right.data(), (size_t)w}, 42);
+  if (!fr) {
+    std::fprintf(stderr, "process failed (%d): %s\n", fr.error().status, fr.error().message.c_str());
+    return 1;
+  }
+  const vslam::StereoFrame& f = fr.value();
+  uint64_t hk = fnv1a(f.left_features.keypoints.data(), f.left_features.keypoints.size() * sizeof(vslam::KeyPoint));
+  hk = fnv1a(f.right_features.keypoints.data(), f.right_features.keypoints.size() * sizeof(vslam::KeyPoint), hk);
+  uint64_t hd = fnv1a(f.left_features.descriptors.data(), f.left_features.descriptors.size() * 32);
+  hd = fnv1a(f.right_features.descriptors.data(), f.right_features.descriptors.size() * 32, hd);
+  uint64_t hm = fnv1a(f.matches_lr.data(), f.matches_lr.size() * sizeof(vslam::DMatch));
+  size_t valid = 0;
+  for (auto& p : f.points_cam) valid += p.has_value();
+  auto frame = vslam::Frame::from_stereo(sp.value(), f);
+  size_t in_area = 0;
+  if (frame) {
+    auto q = frame.value().grid->get_features_in_area(376.0, 240.0, 15.0);
+    if (q) in_area = q.value().size();
+  }
+  std::printf("n_left=%zu n_right=%zu n_matches=%zu n_points=%zu kp=%016llx desc=%016llx matches=%016llx area=%zu ts=%llu\n",
+              f.left_features.keypoints.size(), f.right_features.keypoints.size(), f.matches_lr.size(), valid,
+              (unsigned long long)hk, (unsigned long long)hd, (unsigned long long)hm, in_area,
+              (unsigned long long)f.timestamp_ns);
+  return 0;
+}

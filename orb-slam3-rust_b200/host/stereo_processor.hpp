@@ -1,0 +1,326 @@
+// C++ host-side mirror of the reference's stereo front-end interface over the C ABI (include/vslam_b200.h).
+//
+// The reference is Rust (no Rust toolchain in the build image), so the compiled host layer is written in C++ and
+// mirrors the reference's public items one to one — same names, argument meaning and error behaviour:
+//
+//   vslam::CameraModel                    <- CameraModel                 src/tracking/frame/camera.rs:3-21
+//   vslam::FeatureSet / StereoFrame       <- FeatureSet / StereoFrame    src/tracking/frame/stereo.rs:15-29
+//   vslam::StereoProcessor::create        <- StereoProcessor::new        stereo.rs:37-50   (Result -> Status + message)
+//   vslam::StereoProcessor::process       <- StereoProcessor::process    stereo.rs:52-66
+//   vslam::StereoProcessor::process_batch <- the caller loop             src/main.rs:66-85 (offline batch form)
+//   vslam::descriptor_distance            <- descriptor_distance         stereo.rs:166-175
+//   vslam::FeatureGrid                    <- FeatureGrid                 src/tracking/tracking_frame.rs:23-128
+//   vslam::Frame::from_stereo             <- Frame::from_stereo          tracking_frame.rs:194-215
+//   vslam::search_by_projection           <- Tracker's inline searches   src/tracking/tracker.rs:863-923, 1093-1158
+//
+// Errors: the reference returns anyhow::Result<T>; here every fallible call returns vslam::Result<T> holding either
+// the value or (status, message) from vslam_last_error().  Nothing here computes on the CPU: without the CUDA
+// library / a B200 every call fails.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <optional>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/vslam_b200.h"
+
+namespace vslam {
+
+constexpr uint32_t TH_HIGH = VSLAM_TH_HIGH;  // stereo.rs:10
+constexpr uint32_t TH_LOW = VSLAM_TH_LOW;    // stereo.rs:11
+constexpr float NN_RATIO = VSLAM_NN_RATIO;   // stereo.rs:12
+
+struct Error {
+  int status = VSLAM_OK;
+  std::string message;
+};
+
+template <typename T>
+class Result {
+ public:
+  Result(T v) : value_(std::move(v)) {}
+  Result(Error e) : error_(std::move(e)) {}
+  bool ok() const { return value_.has_value(); }
+  explicit operator bool() const { return ok(); }
+  T& value() { return *value_; }
+  const T& value() const { return *value_; }
+  const Error& error() const { return error_; }
+
+ private:
+  std::optional<T> value_;
+  Error error_;
+};
+
+struct CameraModel {  // camera.rs:3-10
+  double fx, fy, cx, cy, baseline;
+  // camera.rs:13-21 — k is a row-major 3x3 intrinsic matrix
+  static CameraModel from_k_and_baseline(const double k[9], double baseline) {
+    return CameraModel{k[0], k[4], k[2], k[5], baseline};
+  }
+};
+
+using KeyPoint = vslam_keypoint;  // cv::KeyPoint layout (28 B)
+using DMatch = vslam_dmatch;      // cv::DMatch layout (16 B)
+struct Descriptor {
+  uint8_t bytes[32];
+};
+struct Point3 {
+  double x, y, z;
+};
+
+struct FeatureSet {  // stereo.rs:15-19
+  std::vector<KeyPoint> keypoints;
+  std::vector<Descriptor> descriptors;  // N x 32, CV_8U
+};
+
+struct StereoFrame {  // stereo.rs:21-29
+  FeatureSet left_features, right_features;
+  std::vector<DMatch> matches_lr;
+  std::vector<std::optional<Point3>> points_cam;  // per left keypoint, None without valid depth
+  uint64_t timestamp_ns = 0;
+};
+
+// A borrowed 8UC1 image (the reference's `&Mat`): rows `stride` bytes apart.
+struct ImageView {
+  const uint8_t* data;
+  size_t stride;
+};
+
+class StereoProcessor {
+ public:
+  // StereoProcessor::new(camera, n_features) — plus the image size and device the GPU pipeline is sized for.
+  static Result<StereoProcessor> create(const CameraModel& camera, int n_features, int width = 752, int height = 480,
+                                        int device = 0, int max_batch = 64) {
+    vslam_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = VSLAM_ABI_VERSION;
+    cfg.width = width;
+    cfg.height = height;
+    cfg.n_features = n_features;
+    cfg.camera = vslam_camera{camera.fx, camera.fy, camera.cx, camera.cy, camera.baseline};
+    cfg.device = device;
+    cfg.max_batch = max_batch;
+    vslam_handle h = nullptr;
+    int rc = vslam_create(&cfg, &h);
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(nullptr)};
+    StereoProcessor p;
+    p.h_.reset(h);
+    p.camera_ = camera;
+    p.cap_ = vslam_keypoint_capacity(h);
+    return p;
+  }
+
+  // process(&mut self, left, right, timestamp_ns) -> Result<StereoFrame>
+  Result<StereoFrame> process(ImageView left, ImageView right, uint64_t timestamp_ns) {
+    Buffers b(1, cap_);
+    int rc = vslam_process(h_.get(), left.data, left.stride, right.data, right.stride, timestamp_ns, b.outs.data());
+    if (rc != VSLAM_OK) return err(rc);
+    return b.frame(0);
+  }
+
+  // n independent pairs with one common row stride; frames are pipelined on the GPU.
+  Result<std::vector<StereoFrame>> process_batch(const std::vector<const uint8_t*>& left,
+                                                 const std::vector<const uint8_t*>& right, size_t stride,
+                                                 const std::vector<uint64_t>& timestamps_ns = {}) {
+    if (left.size() != right.size()) return Error{VSLAM_ERR_INVALID_ARGUMENT, "left/right batch sizes differ"};
+    const int n = (int)left.size();
+    Buffers b(n, cap_);
+    int rc = vslam_process_batch(h_.get(), n, left.data(), right.data(), stride,
+                                 timestamps_ns.size() == left.size() ? timestamps_ns.data() : nullptr, b.outs.data());
+    if (rc != VSLAM_OK) return err(rc);
+    std::vector<StereoFrame> out;
+    out.reserve(n);
+    for (int i = 0; i < n; ++i) out.push_back(b.frame(i));
+    return out;
+  }
+
+  // detect_features(&mut self, image) -> Result<FeatureSet>
+  Result<FeatureSet> detect_features(ImageView image) {
+    FeatureSet f;
+    f.keypoints.resize(cap_);
+    f.descriptors.resize(cap_);
+    int n = 0;
+    int rc = vslam_detect_and_compute(h_.get(), image.data, image.stride, f.keypoints.data(),
+                                      reinterpret_cast<uint8_t*>(f.descriptors.data()), cap_, &n);
+    if (rc != VSLAM_OK) return err(rc);
+    f.keypoints.resize(n);
+    f.descriptors.resize(n);
+    return f;
+  }
+
+  // match_features(&self, left, right) -> Result<Vector<DMatch>>
+  Result<std::vector<DMatch>> match_features(const FeatureSet& left, const FeatureSet& right) {
+    std::vector<DMatch> m(left.keypoints.size() + 1);
+    int n = 0;
+    int rc = vslam_match_features(h_.get(), left.keypoints.data(), reinterpret_cast<const uint8_t*>(left.descriptors.data()),
+                                  (int)left.keypoints.size(), right.keypoints.data(),
+                                  reinterpret_cast<const uint8_t*>(right.descriptors.data()), (int)right.keypoints.size(),
+                                  m.data(), &n);
+    if (rc != VSLAM_OK) return err(rc);
+    m.resize(n);
+    return m;
+  }
+
+  const CameraModel& camera() const { return camera_; }
+  vslam_handle raw() const { return h_.get(); }
+  int keypoint_capacity() const { return cap_; }
+
+ private:
+  struct Deleter {
+    void operator()(vslam_handle h) const { vslam_destroy(h); }
+  };
+  struct Buffers {  // caller-owned, capacity-checked output arrays (vslam_frame_out)
+    int n, cap;
+    std::vector<KeyPoint> kpl, kpr;
+    std::vector<Descriptor> dl, dr;
+    std::vector<DMatch> m;
+    std::vector<double> pts;
+    std::vector<uint8_t> valid;
+    std::vector<vslam_frame_out> outs;
+    Buffers(int n_, int cap_)
+        : n(n_), cap(cap_), kpl((size_t)n_ * cap_), kpr((size_t)n_ * cap_), dl((size_t)n_ * cap_), dr((size_t)n_ * cap_),
+          m((size_t)n_ * cap_), pts((size_t)n_ * cap_ * 3), valid((size_t)n_ * cap_), outs(n_) {
+      for (int i = 0; i < n; ++i) {
+        vslam_frame_out& o = outs[i];
+        std::memset(&o, 0, sizeof(o));
+        const size_t k = (size_t)i * cap;
+        o.capacity = cap;
+        o.kp_left = kpl.data() + k;
+        o.kp_right = kpr.data() + k;
+        o.desc_left = reinterpret_cast<uint8_t*>(dl.data() + k);
+        o.desc_right = reinterpret_cast<uint8_t*>(dr.data() + k);
+        o.matches = m.data() + k;
+        o.points_cam = pts.data() + 3 * k;
+        o.points_valid = valid.data() + k;
+      }
+    }
+    StereoFrame frame(int i) const {
+      const vslam_frame_out& o = outs[i];
+      const size_t k = (size_t)i * cap;
+      StereoFrame f;
+      f.left_features.keypoints.assign(kpl.begin() + k, kpl.begin() + k + o.n_left);
+      f.left_features.descriptors.assign(dl.begin() + k, dl.begin() + k + o.n_left);
+      f.right_features.keypoints.assign(kpr.begin() + k, kpr.begin() + k + o.n_right);
+      f.right_features.descriptors.assign(dr.begin() + k, dr.begin() + k + o.n_right);
+      f.matches_lr.assign(m.begin() + k, m.begin() + k + o.n_matches);
+      f.points_cam.resize(o.n_left);
+      for (int j = 0; j < o.n_left; ++j)
+        if (valid[k + j]) f.points_cam[j] = Point3{pts[3 * (k + j)], pts[3 * (k + j) + 1], pts[3 * (k + j) + 2]};
+      f.timestamp_ns = o.timestamp_ns;
+      return f;
+    }
+  };
+  Error err(int rc) const { return Error{rc, vslam_last_error(h_.get())}; }
+
+  std::unique_ptr<vslam_handle_s, Deleter> h_;
+  CameraModel camera_{};
+  int cap_ = 0;
+};
+
+// descriptor_distance(&desc1, &desc2) -> Result<u32>   (stereo.rs:166-175)
+inline Result<uint32_t> descriptor_distance(StereoProcessor& p, const Descriptor& a, const Descriptor& b) {
+  uint32_t d = 0;
+  int rc = vslam_descriptor_distance(p.raw(), a.bytes, b.bytes, 1, &d);
+  if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+  return d;
+}
+
+// FeatureGrid (tracking_frame.rs:23-128): 64 x 48 cells, built and queried on the GPU.
+class FeatureGrid {
+ public:
+  static constexpr int GRID_COLS = VSLAM_GRID_COLS, GRID_ROWS = VSLAM_GRID_ROWS;
+  static Result<FeatureGrid> create(StereoProcessor& p, const std::vector<KeyPoint>& keypoints, double img_width,
+                                    double img_height) {
+    FeatureGrid g;
+    g.p_ = &p;
+    g.kps_ = keypoints;
+    g.w_ = img_width;
+    g.h_ = img_height;
+    g.cell_start_.resize(GRID_COLS * GRID_ROWS + 1);
+    g.cell_items_.resize(keypoints.size() + 1);
+    int rc = vslam_grid_build(p.raw(), keypoints.data(), (int)keypoints.size(), img_width, img_height,
+                              g.cell_start_.data(), g.cell_items_.data());
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+    g.cell_items_.resize(keypoints.size());
+    return g;
+  }
+  // get_features_in_area(x, y, r) -> Vec<usize>: whole cells, no radius filtering (tracking_frame.rs:104-128)
+  Result<std::vector<int32_t>> get_features_in_area(double x, double y, double r) const {
+    const double q[3] = {x, y, r};
+    std::vector<int32_t> items(kps_.size() + 1);
+    int32_t start[2] = {0, 0};
+    int rc = vslam_grid_query(p_->raw(), kps_.data(), (int)kps_.size(), w_, h_, q, 1, start, items.data(), (int)items.size());
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p_->raw())};
+    items.resize(start[1]);
+    return items;
+  }
+  const std::vector<int32_t>& cell_start() const { return cell_start_; }
+  const std::vector<int32_t>& cell_items() const { return cell_items_; }
+
+ private:
+  StereoProcessor* p_ = nullptr;
+  std::vector<KeyPoint> kps_;
+  double w_ = 752.0, h_ = 480.0;
+  std::vector<int32_t> cell_start_, cell_items_;
+};
+
+// Tracking Frame (tracking_frame.rs:172-226)
+struct Frame {
+  uint64_t timestamp_ns = 0;
+  FeatureSet features;
+  std::vector<std::optional<Point3>> points_cam;
+  std::vector<std::optional<uint64_t>> map_point_matches;
+  std::optional<FeatureGrid> grid;
+
+  // EuRoC dimensions are hard-coded in the reference (tracking_frame.rs:194-197)
+  static Result<Frame> from_stereo(StereoProcessor& p, StereoFrame stereo) {
+    return from_stereo_with_size(p, std::move(stereo), 752.0, 480.0);
+  }
+  static Result<Frame> from_stereo_with_size(StereoProcessor& p, StereoFrame stereo, double w, double h) {
+    auto g = FeatureGrid::create(p, stereo.left_features.keypoints, w, h);
+    if (!g) return g.error();
+    Frame f;
+    f.timestamp_ns = stereo.timestamp_ns;
+    f.map_point_matches.assign(stereo.left_features.keypoints.size(), std::nullopt);
+    f.features = std::move(stereo.left_features);
+    f.points_cam = std::move(stereo.points_cam);
+    f.grid = std::move(g.value());
+    return f;
+  }
+  size_t num_features() const { return features.keypoints.size(); }
+};
+
+enum class SearchMode { LocalMap = VSLAM_SEARCH_LOCAL_MAP, MotionModel = VSLAM_SEARCH_MOTION_MODEL };
+
+// The descriptor search of track_local_map (tracker.rs:863-923) / track_with_motion_model (tracker.rs:1093-1158).
+// uv: host-projected pixel coordinates of the map points that passed z > 0 (the nalgebra projection stays with the
+// caller); returns, per map point, the matched keypoint index or -1.
+inline Result<std::vector<int32_t>> search_by_projection(StereoProcessor& p, const FeatureSet& frame_features,
+                                                         const std::vector<std::pair<double, double>>& uv,
+                                                         const std::vector<Descriptor>& mp_desc, SearchMode mode,
+                                                         double radius = 15.0) {
+  if (uv.size() != mp_desc.size()) return Error{VSLAM_ERR_INVALID_ARGUMENT, "uv / descriptor count mismatch"};
+  vslam_search_params sp;
+  sp.mode = (int)mode;
+  sp.radius = radius;
+  sp.th_high = TH_HIGH;
+  sp.nn_ratio = NN_RATIO;
+  sp.img_w = 752.0;
+  sp.img_h = 480.0;
+  sp.bound_w = 2.0 * p.camera().cx;
+  sp.bound_h = 2.0 * p.camera().cy;
+  std::vector<int32_t> idx(uv.size() + 1), dist(uv.size() + 1);
+  int rc = vslam_search_by_projection(p.raw(), frame_features.keypoints.data(),
+                                      reinterpret_cast<const uint8_t*>(frame_features.descriptors.data()),
+                                      (int)frame_features.keypoints.size(), reinterpret_cast<const double*>(uv.data()),
+                                      reinterpret_cast<const uint8_t*>(mp_desc.data()), (int)uv.size(), &sp, idx.data(),
+                                      dist.data());
+  if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+  idx.resize(uv.size());
+  return idx;
+}
+
+}  // namespace vslam

@@ -1,0 +1,64 @@
+//! Raw `extern "C"` bindings of include/vslam_b200.h (ABI version 1).  Plain pointers and sizes only.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+pub const VSLAM_ABI_VERSION: i32 = 1;
+pub const VSLAM_OK: c_int = 0;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct vslam_keypoint { pub x: f32, pub y: f32, pub size: f32, pub angle: f32, pub response: f32, pub octave: i32, pub class_id: i32 }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct vslam_dmatch { pub query_idx: i32, pub train_idx: i32, pub img_idx: i32, pub distance: f32 }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct vslam_camera { pub fx: f64, pub fy: f64, pub cx: f64, pub cy: f64, pub baseline: f64 }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct vslam_config {
+    pub abi_version: i32, pub width: i32, pub height: i32, pub n_features: i32, pub n_levels: i32,
+    pub scale_factor: f32, pub edge_threshold: i32, pub fast_threshold: i32, pub camera: vslam_camera,
+    pub device: i32, pub max_batch: i32, pub keypoint_capacity: i32, pub reserved: [i32; 8],
+}
+
+#[repr(C)]
+pub struct vslam_frame_out {
+    pub capacity: i32,
+    pub kp_left: *mut vslam_keypoint, pub kp_right: *mut vslam_keypoint,
+    pub desc_left: *mut u8, pub desc_right: *mut u8,
+    pub matches: *mut vslam_dmatch, pub points_cam: *mut f64, pub points_valid: *mut u8,
+    pub n_left: i32, pub n_right: i32, pub n_matches: i32, pub status: i32, pub timestamp_ns: u64,
+}
+
+#[repr(C)]
+pub struct vslam_search_params {
+    pub mode: i32, pub radius: f64, pub th_high: u32, pub nn_ratio: f32,
+    pub img_w: f64, pub img_h: f64, pub bound_w: f64, pub bound_h: f64,
+}
+
+#[repr(C)]
+pub struct vslam_handle_s { _private: [u8; 0] }
+pub type vslam_handle = *mut vslam_handle_s;
+
+extern "C" {
+    pub fn vslam_create(cfg: *const vslam_config, out: *mut vslam_handle) -> c_int;
+    pub fn vslam_destroy(h: vslam_handle);
+    pub fn vslam_last_error(h: vslam_handle) -> *const c_char;
+    pub fn vslam_keypoint_capacity(h: vslam_handle) -> c_int;
+    pub fn vslam_process(h: vslam_handle, left: *const u8, left_stride: usize, right: *const u8, right_stride: usize,
+                         timestamp_ns: u64, out: *mut vslam_frame_out) -> c_int;
+    pub fn vslam_process_batch(h: vslam_handle, n: c_int, left: *const *const u8, right: *const *const u8, stride: usize,
+                               timestamps_ns: *const u64, outs: *mut vslam_frame_out) -> c_int;
+    pub fn vslam_descriptor_distance(h: vslam_handle, a: *const u8, b: *const u8, n: c_int, out: *mut u32) -> c_int;
+    pub fn vslam_grid_query(h: vslam_handle, kps: *const vslam_keypoint, n: c_int, img_w: f64, img_h: f64,
+                            xyr: *const f64, nq: c_int, out_start: *mut i32, out_items: *mut i32, out_capacity: c_int) -> c_int;
+    pub fn vslam_search_by_projection(h: vslam_handle, kps: *const vslam_keypoint, desc: *const u8, n: c_int,
+                                      uv: *const f64, mp_desc: *const u8, m: c_int, params: *const vslam_search_params,
+                                      out_idx: *mut i32, out_dist: *mut i32) -> c_int;
+    pub fn vslam_bf_match_crosscheck(h: vslam_handle, query: *const u8, n_query: c_int, train: *const u8, n_train: c_int,
+                                     matches: *mut vslam_dmatch, n_matches: *mut c_int) -> c_int;
+}

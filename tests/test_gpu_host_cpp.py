@@ -1,0 +1,41 @@
+"""The compiled C++ host mirror of the reference interface (orb-slam3-rust_b200/host/stereo_processor.hpp) drives the
+C ABI end to end; its output checksums must equal the oracle's."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "orb-slam3-rust_b200", "host")
+
+
+def fnv1a(data: bytes, h=1469598103934665603):
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_cpp_host_mirror_end_to_end(tmp_path, oracle, pairs, camera_dict):
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    l, r = pairs(0)
+    (tmp_path / "l.raw").write_bytes(l.tobytes())
+    (tmp_path / "r.raw").write_bytes(r.tobytes())
+    out = subprocess.run([os.path.join(HOST, "host_demo"), str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), "752", "480"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = dict(re.findall(r"(\w+)=(\w+)", out.stdout))
+    kl, dl = oracle.detect_and_compute(l, 1200)
+    kr, dr = oracle.detect_and_compute(r, 1200)
+    m = oracle.match_features(kl, dl, kr, dr, camera_dict)
+    _, valid = oracle.triangulate(kl, kr, m, camera_dict)
+    cs, items = oracle.grid_build(kl)
+    assert int(got["n_left"]) == len(kl) and int(got["n_right"]) == len(kr) and int(got["n_matches"]) == len(m)
+    assert int(got["n_points"]) == int(valid.sum()) and int(got["ts"]) == 42
+    assert int(got["kp"], 16) == fnv1a(kr.tobytes(), fnv1a(kl.tobytes()))
+    assert int(got["desc"], 16) == fnv1a(dr.tobytes(), fnv1a(dl.tobytes()))
+    assert int(got["matches"], 16) == fnv1a(m.tobytes())
+    assert int(got["area"]) == len(oracle.grid_query(cs, items, 376.0, 240.0, 15.0))
