@@ -643,18 +643,25 @@ __device__ __forceinline__ float u8_to_f32(unsigned word, int byte) {
   return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
 }
 
+// One word (4 pixels) of an image row with BORDER_REFLECT_101 outside [0, w): aligned 32-bit load in the interior.
+__device__ __forceinline__ unsigned load_word_reflect(const uint8_t* __restrict__ row, int gx, int w) {
+  if (gx >= 0 && gx + 3 < w) return *reinterpret_cast<const uint32_t*>(row + gx);
+  unsigned word = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) word |= (unsigned)row[reflect101(gx + k, w)] << (8 * k);
+  return word;
+}
+
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
   constexpr int TW = VSLAM_BLUR_TW, TH = VSLAM_BLUR_TH;
-  constexpr int IW = TW + 8;  // input tile bytes per row: x0-4 .. x0+TW+3
-  __shared__ __align__(16) uint8_t s_in[(TH + 6) * IW];
   __shared__ __align__(16) float s_row[(TH + 6) * TW];
   const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
-  const int tile = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const int tile = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int l = 0;
-  for (int k = 0; k < P.nlevels; ++k)
-    if (tile >= P.lv[k].blur_tile0 && tile < P.lv[k].blur_tile0 + P.lv[k].blur_tx * P.lv[k].blur_ty) l = k;
+  for (int k = 1; k < P.nlevels; ++k)
+    if (tile >= P.lv[k].blur_tile0) l = k;
   const LevelP& L = P.lv[l];
   const int tl = tile - L.blur_tile0;
   const int ty = tl / L.blur_tx, tx = tl - ty * L.blur_tx;
@@ -663,82 +670,70 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, co
   const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
   uint8_t* dst = blur + (long long)img * P.blur_img_stride + L.blur_off;
 
-  // ---- stage input rows y0-3 .. y0+TH+2 (reflected), columns x0-4 .. x0+TW+3 (reflected)
-  constexpr int WPR = IW / 4;
-  for (int i = tid; i < (TH + 6) * WPR; i += 256) {
-    int r = i / WPR, wq = i - r * WPR;
-    int gy = reflect101(y0 - 3 + r, L.h);
-    int gx = x0 - 4 + 4 * wq;
-    const uint8_t* row = src + (size_t)gy * pitch;
-    unsigned word;
-    if (gx >= 0 && gx + 3 < L.w) {
-      word = *reinterpret_cast<const uint32_t*>(row + gx);
-    } else {
-      word = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) word |= (unsigned)row[reflect101(gx + k, L.w)] << (8 * k);
-    }
-    *reinterpret_cast<uint32_t*>(s_in + r * IW + 4 * wq) = word;
-  }
-  __syncthreads();
-
-  // ---- row pass: 4 outputs per item from 10 input bytes
-  for (int it = tid; it < (TH + 6) * (TW / 4); it += 256) {
-    int r = it / (TW / 4), gq = it - r * (TW / 4);
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(s_in + r * IW + 4 * gq);
-    unsigned w0 = q[0], w1 = q[1], w2 = q[2];
-    float f[10];  // tile bytes 4gq+1 .. 4gq+10  ==  image x = x0+4gq-3 .. x0+4gq+6
-    f[0] = u8_to_f32(w0, 1);
-    f[1] = u8_to_f32(w0, 2);
-    f[2] = u8_to_f32(w0, 3);
-    f[3] = u8_to_f32(w1, 0);
-    f[4] = u8_to_f32(w1, 1);
-    f[5] = u8_to_f32(w1, 2);
-    f[6] = u8_to_f32(w1, 3);
-    f[7] = u8_to_f32(w2, 0);
-    f[8] = u8_to_f32(w2, 1);
-    f[9] = u8_to_f32(w2, 2);
-    float o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float s = __fmul_rn(k0, f[k]);
-      s = __fmaf_rn(f[k + 1], k1, s);
-      s = __fmaf_rn(f[k + 2], k2, s);
-      s = __fmaf_rn(f[k + 3], k3, s);
-      s = __fmaf_rn(f[k + 4], k2, s);
-      s = __fmaf_rn(f[k + 5], k1, s);
-      s = __fmaf_rn(f[k + 6], k0, s);
-      o[k] = s;
-    }
-    *reinterpret_cast<float4*>(s_row + r * TW + 4 * gq) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  __syncthreads();
-
-  // ---- column pass: thread = (4 columns) x (4 rows), 10 row vectors in registers
+  // ---- row pass straight from global memory (L1 serves the 3x word reuse between neighbouring lanes):
+  //      warp = one tile row (reflected), lane = 4 output columns.  Image x of output k: x0 + 4*lane + k.
   {
-    const int cg = tid & 31, rr = tid >> 5;
-    float4 v[10];
+    const int gx = x0 + 4 * lane;
+    for (int r = warp; r < TH + 6; r += 8) {
+      const uint8_t* row = src + (size_t)reflect101(y0 - 3 + r, L.h) * pitch;
+      const unsigned w0 = load_word_reflect(row, gx - 4, L.w);
+      const unsigned w1 = load_word_reflect(row, gx, L.w);
+      const unsigned w2 = load_word_reflect(row, gx + 4, L.w);
+      float f[10];  // image x = gx-3 .. gx+6
+      f[0] = u8_to_f32(w0, 1);
+      f[1] = u8_to_f32(w0, 2);
+      f[2] = u8_to_f32(w0, 3);
+      f[3] = u8_to_f32(w1, 0);
+      f[4] = u8_to_f32(w1, 1);
+      f[5] = u8_to_f32(w1, 2);
+      f[6] = u8_to_f32(w1, 3);
+      f[7] = u8_to_f32(w2, 0);
+      f[8] = u8_to_f32(w2, 1);
+      f[9] = u8_to_f32(w2, 2);
+      float o[4];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) v[j] = *reinterpret_cast<const float4*>(s_row + (4 * rr + j) * TW + 4 * cg);
+      for (int k = 0; k < 4; ++k) {
+        float s = __fmul_rn(k0, f[k]);
+        s = __fmaf_rn(f[k + 1], k1, s);
+        s = __fmaf_rn(f[k + 2], k2, s);
+        s = __fmaf_rn(f[k + 3], k3, s);
+        s = __fmaf_rn(f[k + 4], k2, s);
+        s = __fmaf_rn(f[k + 5], k1, s);
+        s = __fmaf_rn(f[k + 6], k0, s);
+        o[k] = s;
+      }
+      *reinterpret_cast<float4*>(s_row + r * TW + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- column pass: thread = (4 columns) x (4 rows), 10 row vectors in registers; round-half-even via the
+  //      2^23 magic add (0 <= s < 256), 4 pixels packed per 32-bit store.
+  {
+    const int cg = lane, rr = warp;
+    float v[10][4];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(s_row + (4 * rr + j) * TW + 4 * cg);
+      v[j][0] = t.x;
+      v[j][1] = t.y;
+      v[j][2] = t.z;
+      v[j][3] = t.w;
+    }
     const int gx = x0 + 4 * cg;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gy = y0 + 4 * rr + i;
-      unsigned word = 0;
+      unsigned b[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        auto at = [&](int j) -> float {
-          const float4& t = v[i + j];
-          return c == 0 ? t.x : c == 1 ? t.y : c == 2 ? t.z : t.w;
-        };
-        float s = __fmul_rn(k3, at(3));
-        s = __fmaf_rn(__fadd_rn(at(4), at(2)), k2, s);
-        s = __fmaf_rn(__fadd_rn(at(5), at(1)), k1, s);
-        s = __fmaf_rn(__fadd_rn(at(6), at(0)), k0, s);
-        int iv = __float2int_rn(s);
-        iv = min(max(iv, 0), 255);
-        word |= (unsigned)iv << (8 * c);
+        float s = __fmul_rn(k3, v[i + 3][c]);
+        s = __fmaf_rn(__fadd_rn(v[i + 4][c], v[i + 2][c]), k2, s);
+        s = __fmaf_rn(__fadd_rn(v[i + 5][c], v[i + 1][c]), k1, s);
+        s = __fmaf_rn(__fadd_rn(v[i + 6][c], v[i][c]), k0, s);
+        b[c] = __float_as_uint(__fadd_rn(s, 12582912.0f));  // low byte = round-half-even(s)
       }
+      const unsigned word = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
       if (gy < L.h && gx < L.pitch) *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = word;
     }
   }
@@ -753,12 +748,21 @@ struct __align__(4) KeyPoint28 {
   int octave, class_id;
 };
 
+constexpr int kBriefR = 18;                     // max |rotated pattern coordinate| (13*sqrt(2) = 18.38 -> 18)
+constexpr int kBriefRows = 2 * kBriefR + 1;     // 37
+constexpr int kBriefRowWords = 11;              // smem row stride in words (10 loaded + 1 pad; 11 is coprime with 32)
+constexpr int kAngleR = 15;
+constexpr int kAngleRows = 2 * kAngleR + 1;     // 31
+constexpr int kAngleRowWords = 9;               // 31 px + up to 3 alignment bytes = 9 words
+constexpr int kPatchWords = kBriefRows * kBriefRowWords + kAngleRows * kAngleRowWords;
+
 __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                                const uint8_t* __restrict__ blur, const LvlKp* __restrict__ lvl_kp,
                                                const int* __restrict__ lvl_cnt, const FrameLayout F) {
-  const int img = blockIdx.y, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ uint32_t s_patch[8][kPatchWords];
+  const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
   const int frame = img / P.eyes, eye = img - frame * P.eyes;
   const int* cnt = lvl_cnt + (long long)img * P.nlevels;
   int total = 0, l = -1, jl = 0;
@@ -775,13 +779,54 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     hdr->n_kp[eye] = min(total, P.kp_cap);
     if (total > P.kp_cap) atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
   }
-  if (l < 0 || j >= P.kp_cap) return;
+  if (l < 0 || j >= P.kp_cap) return;  // warp-uniform
   const LevelP& L = P.lv[l];
   const LvlKp kp = lvl_kp[((long long)img * P.nlevels + l) * P.kp_cap + jl];
   const int cx = (int)(kp.xy & 0xffffu), cy = (int)(kp.xy >> 16);
+
+  // ---- stage the two patches this keypoint reads with aligned 32-bit loads (2 sectors per row instead of one
+  //      sector per sample): 37x37 of the blurred level (BRIEF) and 31x31 of the un-blurred level (orientation).
+  //      Keypoints are >= 31 px from every edge (runByImageBorder), so both windows are inside the image.
+  uint32_t* sb = s_patch[warp];
+  uint32_t* sa = sb + kBriefRows * kBriefRowWords;
   int upitch;
   const uint8_t* unblurred = level_ptr(P, l, img, in_l, in_r, pyr, upitch);
-  const float angle = ic_angle_warp(unblurred, upitch, cx, cy, lane);  // A4, on the un-blurred level
+  const uint8_t* blurred = blur + (long long)img * P.blur_img_stride + L.blur_off;
+  const int xb0 = (cx - kBriefR) & ~3, xa0 = (cx - kAngleR) & ~3;
+  for (int i = lane; i < kBriefRows * 10; i += 32) {
+    const int r = i / 10, wq = i - r * 10;
+    sb[r * kBriefRowWords + wq] =
+        *reinterpret_cast<const uint32_t*>(blurred + (size_t)(cy - kBriefR + r) * L.pitch + xb0 + 4 * wq);
+  }
+  for (int i = lane; i < kAngleRows * kAngleRowWords; i += 32) {
+    const int r = i / kAngleRowWords, wq = i - r * kAngleRowWords;
+    sa[i] = *reinterpret_cast<const uint32_t*>(unblurred + (size_t)(cy - kAngleR + r) * upitch + xa0 + 4 * wq);
+  }
+  __syncwarp();
+
+  // ---- A4: intensity-centroid angle; lane v+15 sums row v of the disc
+  int m10 = 0, m01 = 0;
+  if (lane < kAngleRows) {
+    const int v = lane - kAngleR;
+    const int av = v < 0 ? -v : v;
+    const int d = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);  // umax[|v|]
+    const uint8_t* row = reinterpret_cast<const uint8_t*>(sa + lane * kAngleRowWords) + (cx - xa0);
+    int sum = 0, su = 0;
+    for (int u = -d; u <= d; ++u) {
+      int val = row[u];
+      sum += val;
+      su += u * val;
+    }
+    m10 = su;
+    m01 = v * sum;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(VSLAM_FULL, m10, o);
+    m01 += __shfl_xor_sync(VSLAM_FULL, m01, o);
+  }
+  const float angle = fast_atan2_deg(__int2float_rn(m01), __int2float_rn(m10));
+
   if (lane == 0) {
     KeyPoint28 o;
     o.x = __fmul_rn(__int2float_rn(cx), L.scale);
@@ -793,10 +838,10 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     o.class_id = -1;
     reinterpret_cast<KeyPoint28*>(F.kp[eye] + (long long)frame * F.kp_stride)[j] = o;
   }
-  // angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)   (double cos/sin of the f32 angle)
+  // ---- A6: angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)  (double cos/sin of the f32)
   const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
   const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-  const uint8_t* center = blur + (long long)img * P.blur_img_stride + L.blur_off + (size_t)cy * L.pitch + cx;
+  const uint8_t* center = reinterpret_cast<const uint8_t*>(sb) + kBriefR * (kBriefRowWords * 4) + (cx - xb0);
   const int4* pat = reinterpret_cast<const int4*>(g_brief_pattern) + 8 * lane;  // 32 ints = 16 points per lane
   unsigned byte = 0;
 #pragma unroll
@@ -807,7 +852,7 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
     int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
     int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
-    int t0 = center[iy0 * L.pitch + ix0], t1 = center[iy1 * L.pitch + ix1];
+    int t0 = center[iy0 * (kBriefRowWords * 4) + ix0], t1 = center[iy1 * (kBriefRowWords * 4) + ix1];
     byte |= (unsigned)(t0 < t1) << q;
   }
   (F.desc[eye] + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -641,8 +642,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "n_levels out of range (1..%d)", VSLAM_MAX_LEVELS);
   if (!(c.scale_factor > 1.0f) || c.scale_factor > 2.0f)
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "scale_factor must be in (1, 2]");
-  if (c.edge_threshold < 19 || c.edge_threshold > 255)
-    return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "edge_threshold must be >= 19 (31-px patch + BRIEF radius)");
+  if (c.edge_threshold < 22 || c.edge_threshold > 255)
+    return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "edge_threshold must be >= 22 (BRIEF radius 18 + aligned patch loads)");
   if (c.fast_threshold < 1 || c.fast_threshold > 254)
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "fast_threshold out of range");
   if (c.max_batch < 1 || c.max_batch > 4096) return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "max_batch out of range");
@@ -694,12 +695,27 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
          h->fast_smem, max_resize, max_sel, lim);
     return bail(VSLAM_ERR_INVALID_ARGUMENT);
   }
-  cudaFuncSetAttribute(vk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem);
-  cudaFuncSetAttribute(vk::k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(max_resize, 1024));
-  cudaFuncSetAttribute(vk::k_select1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)vk::select1_smem_bytes(h->sel1_cap));
-  cudaFuncSetAttribute(vk::k_select2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)vk::select2_smem_bytes(h->sel2_cap));
+  // The opt-in limit is a per-function (not per-handle) attribute: only ever raise it, so that handles created for
+  // smaller images do not shrink what an older handle's launches need.
+  {
+    static std::mutex mu;
+    static size_t cur_dev[64][4] = {{0}};
+    size_t* cur = cur_dev[c.device & 63];
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t want[4] = {h->fast_smem, std::max<size_t>(max_resize, 1024), vk::select1_smem_bytes(h->sel1_cap),
+                            vk::select2_smem_bytes(h->sel2_cap)};
+    const void* fn[4] = {(const void*)vk::k_fast, (const void*)vk::k_resize, (const void*)vk::k_select1,
+                         (const void*)vk::k_select2};
+    for (int i = 0; i < 4; ++i)
+      if (want[i] > cur[i]) {
+        e = cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want[i]);
+        if (e != cudaSuccess) {
+          fail(h, VSLAM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+          return bail(VSLAM_ERR_CUDA);
+        }
+        cur[i] = want[i];
+      }
+  }
   for (int k = 0; k < NSLOT; ++k) {
     rc = alloc_slot(h, h->slots[k]);
     if (rc != VSLAM_OK) return bail(rc == VSLAM_ERR_CUDA ? VSLAM_ERR_OUT_OF_MEMORY : rc);
