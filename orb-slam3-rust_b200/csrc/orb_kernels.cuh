@@ -196,62 +196,124 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   for (int i = tid; i < 2 * VSLAM_FAST_ROWS * BW; i += 256) bits[i] = 0;
   __syncthreads();
 
-  // ---- scores on the emission region dilated by one pixel (clipped to FAST's own 3-px border)
+  // ---- scores on the emission region dilated by one pixel (clipped to FAST's own 3-px border).
+  // Phase A (every group of 4 pixels, byte-SIMD): a necessary condition for a FAST-9 corner — every 9-arc of the
+  //   16-circle contains one of the points {0, 8} and one of {4, 12}, so (|d0|>t or |d8|>t) and (|d4|>t or |d12|>t)
+  //   must hold.  Pairs of pixels that pass are queued per warp.
+  // Phase B (queued pairs only, 32 at a time so every lane is busy): the exact score with DPX min/max.
+  // Pixels that fail phase A keep score 0 — exactly what the full computation would give them.
   const int sx0 = max(3, L.ex0 - 1), sx1 = min(L.w - 3, L.ex1 + 1);
   const int sy_lo = max(3, ys - 1), sy_hi = min(L.h - 3, ye + 1);  // [sy_lo, sy_hi)
   const int gx0 = sx0 >> 2, ngx = ((sx1 - 1) >> 2) - gx0 + 1;
   const int nsr = sy_hi - sy_lo;
-  const unsigned t2 = (unsigned)P.fast_threshold * 0x00010001u;
-  const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
-  for (int it = tid; it < nsr * ngx; it += 256) {
-    const int ry = (int)__umulhi((unsigned)it, inv_ngx);
-    const int g = gx0 + (it - ry * ngx);
-    const int y = sy_lo + ry;
-    const uint8_t* base = pix + (y - (ys - 4)) * SP + 16 + 4 * g;  // centre word of this group
-    unsigned w[7][3];
+  const unsigned t = (unsigned)P.fast_threshold;
+  const unsigned t2 = t * 0x00010001u;
+  // per-byte (v > t): low-7-bit add carries into bit 7; t < 128 also accepts bit 7 of v itself, t >= 128 requires it
+  const unsigned tadd = (t < 128u ? 127u - t : 255u - t) * 0x01010101u;
+  const unsigned lt = (1u << lane) - 1u;
+  __shared__ unsigned short s_queue[8][96];
+  unsigned short* q = s_queue[warp];
+  int qn = 0;  // warp-uniform number of queued pairs
+
+  auto score_pairs = [&](int count) {  // the first `count` (<= 32) queue entries, one pair per lane
+    if (lane < count) {
+      const unsigned code = q[lane];
+      const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
+      const int y = sy_lo + ry;
+      const uint8_t* base = pix + (y - (ys - 4)) * SP + 16 + 4 * g;
+      unsigned w[7][3];
 #pragma unroll
-    for (int dy = -3; dy <= 3; ++dy) {
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(base + dy * SP);
-      w[dy + 3][0] = q[-1];
-      w[dy + 3][1] = q[0];
-      w[dy + 3][2] = q[1];
-    }
+      for (int dy = -3; dy <= 3; ++dy) {
+        const uint32_t* qq = reinterpret_cast<const uint32_t*>(base + dy * SP);
+        w[dy + 3][0] = qq[-1];
+        w[dy + 3][1] = qq[0];
+        w[dy + 3][2] = qq[1];
+      }
 #define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
-    unsigned s[16];
-    s[0] = shifted4<0>(VS_ROW(3));
-    s[1] = shifted4<1>(VS_ROW(3));
-    s[2] = shifted4<2>(VS_ROW(2));
-    s[3] = shifted4<3>(VS_ROW(1));
-    s[4] = shifted4<3>(VS_ROW(0));
-    s[5] = shifted4<3>(VS_ROW(-1));
-    s[6] = shifted4<2>(VS_ROW(-2));
-    s[7] = shifted4<1>(VS_ROW(-3));
-    s[8] = shifted4<0>(VS_ROW(-3));
-    s[9] = shifted4<-1>(VS_ROW(-3));
-    s[10] = shifted4<-2>(VS_ROW(-2));
-    s[11] = shifted4<-3>(VS_ROW(-1));
-    s[12] = shifted4<-3>(VS_ROW(0));
-    s[13] = shifted4<-3>(VS_ROW(1));
-    s[14] = shifted4<-2>(VS_ROW(2));
-    s[15] = shifted4<-1>(VS_ROW(3));
+      unsigned s[16];
+      s[0] = shifted4<0>(VS_ROW(3));
+      s[1] = shifted4<1>(VS_ROW(3));
+      s[2] = shifted4<2>(VS_ROW(2));
+      s[3] = shifted4<3>(VS_ROW(1));
+      s[4] = shifted4<3>(VS_ROW(0));
+      s[5] = shifted4<3>(VS_ROW(-1));
+      s[6] = shifted4<2>(VS_ROW(-2));
+      s[7] = shifted4<1>(VS_ROW(-3));
+      s[8] = shifted4<0>(VS_ROW(-3));
+      s[9] = shifted4<-1>(VS_ROW(-3));
+      s[10] = shifted4<-2>(VS_ROW(-2));
+      s[11] = shifted4<-3>(VS_ROW(-1));
+      s[12] = shifted4<-3>(VS_ROW(0));
+      s[13] = shifted4<-3>(VS_ROW(1));
+      s[14] = shifted4<-2>(VS_ROW(2));
+      s[15] = shifted4<-1>(VS_ROW(3));
 #undef VS_ROW
-    const unsigned cw = w[3][1];
-    unsigned p[16];
+      const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
+      unsigned p[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) p[k] = pair_lo(s[k]);
-    const unsigned xlo = fast_score2(p, pair_lo(cw), t2);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) p[k] = pair_hi(s[k]);
-    const unsigned xhi = fast_score2(p, pair_hi(cw), t2);
-    unsigned word = __byte_perm(xlo, xhi, 0x6420);
-    unsigned mask = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int x = 4 * g + k;
-      if (x >= sx0 && x < sx1) mask |= 0xffu << (8 * k);
+      for (int k = 0; k < 16; ++k) p[k] = __byte_perm(s[k], 0u, sel);
+      const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
+      const int x = 4 * g + 2 * half;
+      unsigned lo8 = (x >= sx0 && x < sx1) ? (xs & 0xffu) : 0u;
+      unsigned hi8 = (x + 1 >= sx0 && x + 1 < sx1) ? ((xs >> 16) & 0xffu) : 0u;
+      *reinterpret_cast<unsigned short*>(sc + (y - (ys - 1)) * SP + 16 + x) = (unsigned short)(lo8 | (hi8 << 8));
     }
-    *reinterpret_cast<uint32_t*>(sc + (y - (ys - 1)) * SP + 16 + 4 * g) = word & mask;
+  };
+
+  const int nitems = nsr * ngx;
+  const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
+  for (int it0 = warp * 32; it0 < nitems; it0 += 256) {
+    const int it = it0 + lane;
+    bool plo = false, phi = false;
+    int ry = 0, g = 0;
+    if (it < nitems) {
+      ry = (int)__umulhi((unsigned)it, inv_ngx);
+      g = gx0 + (it - ry * ngx);
+      const uint8_t* base = pix + (sy_lo + ry - (ys - 4)) * SP + 16 + 4 * g;
+      const uint32_t* rc = reinterpret_cast<const uint32_t*>(base);
+      const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
+      const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + 3 * SP);
+      const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - 3 * SP);
+      const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
+      const unsigned a08 = __vabsdiffu4(p0, cw), b08 = __vabsdiffu4(p8, cw);
+      const unsigned a412 = __vabsdiffu4(p4, cw), b412 = __vabsdiffu4(p12, cw);
+      unsigned f0, f8, f4, f12;
+      if (t < 128u) {
+        f0 = ((a08 & 0x7f7f7f7fu) + tadd) | a08;
+        f8 = ((b08 & 0x7f7f7f7fu) + tadd) | b08;
+        f4 = ((a412 & 0x7f7f7f7fu) + tadd) | a412;
+        f12 = ((b412 & 0x7f7f7f7fu) + tadd) | b412;
+      } else {
+        f0 = ((a08 & 0x7f7f7f7fu) + tadd) & a08;
+        f8 = ((b08 & 0x7f7f7f7fu) + tadd) & b08;
+        f4 = ((a412 & 0x7f7f7f7fu) + tadd) & a412;
+        f12 = ((b412 & 0x7f7f7f7fu) + tadd) & b412;
+      }
+      const unsigned pass = (f0 | f8) & (f4 | f12) & 0x80808080u;
+      plo = (pass & 0x00008080u) != 0u;
+      phi = (pass & 0x80800000u) != 0u;
+    }
+    const unsigned mlo = __ballot_sync(VSLAM_FULL, plo), mhi = __ballot_sync(VSLAM_FULL, phi);
+    const unsigned code = ((unsigned)ry << 11) | ((unsigned)g << 1);
+    if (plo) q[qn + __popc(mlo & lt)] = (unsigned short)code;
+    if (phi) q[qn + __popc(mlo) + __popc(mhi & lt)] = (unsigned short)(code | 1u);
+    qn += __popc(mlo) + __popc(mhi);
+    __syncwarp();
+    while (qn >= 32) {  // at most two rounds: qn < 32 + 64
+      score_pairs(32);
+      __syncwarp();
+      const int rest = qn - 32;
+      unsigned short keep0 = 0, keep1 = 0;
+      if (lane < rest) keep0 = q[32 + lane];
+      if (lane + 32 < rest) keep1 = q[64 + lane];
+      __syncwarp();
+      if (lane < rest) q[lane] = keep0;
+      if (lane + 32 < rest) q[32 + lane] = keep1;
+      qn = rest;
+      __syncwarp();
+    }
   }
+  if (qn > 0) score_pairs(qn);
   __syncthreads();
 
   // ---- non-maximum suppression (strictly greater than the 8 neighbours) + runByImageBorder
@@ -643,19 +705,14 @@ __device__ __forceinline__ float u8_to_f32(unsigned word, int byte) {
   return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
 }
 
-// One word (4 pixels) of an image row with BORDER_REFLECT_101 outside [0, w): aligned 32-bit load in the interior.
-__device__ __forceinline__ unsigned load_word_reflect(const uint8_t* __restrict__ row, int gx, int w) {
-  if (gx >= 0 && gx + 3 < w) return *reinterpret_cast<const uint32_t*>(row + gx);
-  unsigned word = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) word |= (unsigned)row[reflect101(gx + k, w)] << (8 * k);
-  return word;
-}
+// Reflect-101 index for an offset of at most a few pixels outside [0, n) (n >= 16): closed form, no loop.
+__device__ __forceinline__ int reflect101_near(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
   constexpr int TW = VSLAM_BLUR_TW, TH = VSLAM_BLUR_TH;
+  constexpr int NIT = (TH + 6 + 7) / 8;  // row-pass iterations per warp
   __shared__ __align__(16) float s_row[(TH + 6) * TW];
   const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
   const int tile = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -670,26 +727,51 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, co
   const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
   uint8_t* dst = blur + (long long)img * P.blur_img_stride + L.blur_off;
 
-  // ---- row pass straight from global memory (L1 serves the 3x word reuse between neighbouring lanes):
-  //      warp = one tile row (reflected), lane = 4 output columns.  Image x of output k: x0 + 4*lane + k.
+  // ---- row pass straight from global memory: warp = one (reflected) image row per iteration, lane = 4 output
+  //      columns gx..gx+3, which need image x = gx-3 .. gx+6 = three aligned words.  All loads of all iterations are
+  //      issued before the first use (memory-level parallelism).  Borders: the word left of x = 0 is a byte
+  //      permutation of word 0 (reflect-101); lanes whose words reach past the right edge gather bytes.
   {
     const int gx = x0 + 4 * lane;
-    for (int r = warp; r < TH + 6; r += 8) {
-      const uint8_t* row = src + (size_t)reflect101(y0 - 3 + r, L.h) * pitch;
-      const unsigned w0 = load_word_reflect(row, gx - 4, L.w);
-      const unsigned w1 = load_word_reflect(row, gx, L.w);
-      const unsigned w2 = load_word_reflect(row, gx + 4, L.w);
+    const bool fast = gx + 7 < L.w;      // all three words inside the row
+    const bool active = gx < L.w + 3;    // lanes further right produce nothing that is ever read
+    unsigned w0[NIT], w1[NIT], w2[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = warp + 8 * it;
+      w0[it] = w1[it] = w2[it] = 0;
+      if (r < TH + 6 && active) {
+        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);  // clamp: rows past h+2 are never used
+        const uint8_t* row = src + (size_t)gy * pitch;
+        if (fast) {
+          w1[it] = *reinterpret_cast<const uint32_t*>(row + gx);
+          w2[it] = *reinterpret_cast<const uint32_t*>(row + gx + 4);
+          w0[it] = gx > 0 ? *reinterpret_cast<const uint32_t*>(row + gx - 4) : __byte_perm(w1[it], 0u, 0x1230);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            w0[it] |= (unsigned)row[reflect101_near(gx - 4 + k, L.w)] << (8 * k);
+            w1[it] |= (unsigned)row[reflect101_near(min(gx + k, L.w + 3), L.w)] << (8 * k);
+            w2[it] |= (unsigned)row[reflect101_near(min(gx + 4 + k, L.w + 3), L.w)] << (8 * k);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = warp + 8 * it;
+      if (r >= TH + 6) break;
       float f[10];  // image x = gx-3 .. gx+6
-      f[0] = u8_to_f32(w0, 1);
-      f[1] = u8_to_f32(w0, 2);
-      f[2] = u8_to_f32(w0, 3);
-      f[3] = u8_to_f32(w1, 0);
-      f[4] = u8_to_f32(w1, 1);
-      f[5] = u8_to_f32(w1, 2);
-      f[6] = u8_to_f32(w1, 3);
-      f[7] = u8_to_f32(w2, 0);
-      f[8] = u8_to_f32(w2, 1);
-      f[9] = u8_to_f32(w2, 2);
+      f[0] = u8_to_f32(w0[it], 1);
+      f[1] = u8_to_f32(w0[it], 2);
+      f[2] = u8_to_f32(w0[it], 3);
+      f[3] = u8_to_f32(w1[it], 0);
+      f[4] = u8_to_f32(w1[it], 1);
+      f[5] = u8_to_f32(w1[it], 2);
+      f[6] = u8_to_f32(w1[it], 3);
+      f[7] = u8_to_f32(w2[it], 0);
+      f[8] = u8_to_f32(w2[it], 1);
+      f[9] = u8_to_f32(w2[it], 2);
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

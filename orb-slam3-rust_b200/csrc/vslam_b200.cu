@@ -80,6 +80,7 @@ struct vslam_handle_s {
   size_t fast_smem = 0;
   int sel1_cap = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   int harris_blocks = 1;
+  size_t match_rows_smem = 0;  // 0: fall back to k_match + k_match_finalize
   size_t in_img_bytes = 0;
   Slot slots[NSLOT];
   std::string err;
@@ -392,10 +393,15 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 5
   if (eyes == 2) {
-    dim3 grid((P.kp_cap + vk::kMatchLeftPerBlock - 1) / vk::kMatchLeftPerBlock, frames);
-    vk::k_match<<<grid, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
-    vk::k_match_finalize<<<frames, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
-    h->launches += 2;
+    if (h->match_rows_smem) {
+      vk::k_match_rows<<<frames, 1024, h->match_rows_smem, st>>>(s.d_lay, h->S, h->cfg.height);
+      h->launches += 1;
+    } else {
+      dim3 grid((P.kp_cap + vk::kMatchLeftPerBlock - 1) / vk::kMatchLeftPerBlock, frames);
+      vk::k_match<<<grid, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
+      vk::k_match_finalize<<<frames, 256, 0, st>>>(s.d_lay, h->S, s.d_ml);
+      h->launches += 2;
+    }
   }
   mark();  // 6
   CU_TRY(h, cudaGetLastError());
@@ -699,14 +705,19 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   // smaller images do not shrink what an older handle's launches need.
   {
     static std::mutex mu;
-    static size_t cur_dev[64][4] = {{0}};
+    static size_t cur_dev[64][5] = {{0}};
     size_t* cur = cur_dev[c.device & 63];
     std::lock_guard<std::mutex> lock(mu);
-    const size_t want[4] = {h->fast_smem, std::max<size_t>(max_resize, 1024), vk::select1_smem_bytes(h->sel1_cap),
-                            vk::select2_smem_bytes(h->sel2_cap)};
-    const void* fn[4] = {(const void*)vk::k_fast, (const void*)vk::k_resize, (const void*)vk::k_select1,
-                         (const void*)vk::k_select2};
-    for (int i = 0; i < 4; ++i)
+    // row-bucketed fused matcher when its tables fit in shared memory; otherwise the chunked pair of kernels
+    {
+      const size_t need = vk::match_rows_smem_bytes(h->kp_cap, c.height);
+      h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
+    }
+    const size_t want[5] = {h->fast_smem, std::max<size_t>(max_resize, 1024), vk::select1_smem_bytes(h->sel1_cap),
+                            vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
+    const void* fn[5] = {(const void*)vk::k_fast, (const void*)vk::k_resize, (const void*)vk::k_select1,
+                         (const void*)vk::k_select2, (const void*)vk::k_match_rows};
+    for (int i = 0; i < 5; ++i)
       if (want[i] > cur[i]) {
         e = cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want[i]);
         if (e != cudaSuccess) {
