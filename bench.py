@@ -200,7 +200,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from vslam_b200 import CameraModel, StereoProcessor, synth
+    from vslam_b200 import CameraModel, StereoProcessor, shard, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -219,7 +219,7 @@ def main():
     n = args.frames
     nuniq = args.unique or n
     # frames are independent units: rank r owns seeds [r*n, (r+1)*n)  (sharded, no collective on the data path)
-    seeds = [rank * n + (i % nuniq) for i in range(n)]
+    seeds = shard.weak_seeds(rank, n, args.unique)
     t_gen = time.perf_counter()
     left = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
     right = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
@@ -366,16 +366,12 @@ def main():
 
     # ---------------- reduce over ranks: time = max, frames = sum
     def rmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_max(x, dist if world > 1 else None, dev)
 
     dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms = rmax(dev_ms), rmax(wall_ms), rmax(e2e_dev_ms), rmax(e2e_wall_ms)
     total_frames = n * world * args.steps
-    value = total_frames / (dev_ms * 1e-3)
-    e2e_value = total_frames / (e2e_wall_ms * 1e-3)
+    value = shard.throughput(total_frames, dev_ms)
+    e2e_value = shard.throughput(total_frames, e2e_wall_ms)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,

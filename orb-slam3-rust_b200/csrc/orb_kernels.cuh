@@ -26,7 +26,8 @@ namespace vk {
 #define VSLAM_FULL 0xffffffffu
 
 // Global (not __constant__) memory: every lane reads a different test, which the constant cache would serialise.
-__device__ int g_brief_pattern[1024] = {
+// Stored as float (|coordinate| <= 13 is exact): the steering multiplies them by cos/sin in f32.
+__device__ float g_brief_pattern[1024] = {
 #include "brief_pattern.inc"
 };
 
@@ -208,8 +209,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   const int nsr = sy_hi - sy_lo;
   const unsigned t = (unsigned)P.fast_threshold;
   const unsigned t2 = t * 0x00010001u;
-  // per-byte (v > t): low-7-bit add carries into bit 7; t < 128 also accepts bit 7 of v itself, t >= 128 requires it
-  const unsigned tadd = (t < 128u ? 127u - t : 255u - t) * 0x01010101u;
+  const unsigned tadd = (127u - t) * 0x01010101u;  // fast_threshold <= 127 (checked by vslam_create)
   const unsigned lt = (1u << lane) - 1u;
   __shared__ unsigned short s_queue[8][96];
   unsigned short* q = s_queue[warp];
@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
 
   const int nitems = nsr * ngx;
   const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
+  const uint8_t* const pix0 = pix + (sy_lo - (ys - 4)) * SP + 16;  // centre pixel of score row 0, group 0
+  const int SP3 = 3 * SP;
   for (int it0 = warp * 32; it0 < nitems; it0 += 256) {
     const int it = it0 + lane;
     bool plo = false, phi = false;
@@ -269,27 +271,18 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
     if (it < nitems) {
       ry = (int)__umulhi((unsigned)it, inv_ngx);
       g = gx0 + (it - ry * ngx);
-      const uint8_t* base = pix + (sy_lo + ry - (ys - 4)) * SP + 16 + 4 * g;
+      const uint8_t* base = pix0 + ry * SP + 4 * g;
       const uint32_t* rc = reinterpret_cast<const uint32_t*>(base);
       const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
-      const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + 3 * SP);
-      const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - 3 * SP);
+      const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + SP3);
+      const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - SP3);
       const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
-      const unsigned a08 = __vabsdiffu4(p0, cw), b08 = __vabsdiffu4(p8, cw);
-      const unsigned a412 = __vabsdiffu4(p4, cw), b412 = __vabsdiffu4(p12, cw);
-      unsigned f0, f8, f4, f12;
-      if (t < 128u) {
-        f0 = ((a08 & 0x7f7f7f7fu) + tadd) | a08;
-        f8 = ((b08 & 0x7f7f7f7fu) + tadd) | b08;
-        f4 = ((a412 & 0x7f7f7f7fu) + tadd) | a412;
-        f12 = ((b412 & 0x7f7f7f7fu) + tadd) | b412;
-      } else {
-        f0 = ((a08 & 0x7f7f7f7fu) + tadd) & a08;
-        f8 = ((b08 & 0x7f7f7f7fu) + tadd) & b08;
-        f4 = ((a412 & 0x7f7f7f7fu) + tadd) & a412;
-        f12 = ((b412 & 0x7f7f7f7fu) + tadd) & b412;
-      }
-      const unsigned pass = (f0 | f8) & (f4 | f12) & 0x80808080u;
+      const unsigned a0 = __vabsdiffu4(p0, cw), a8 = __vabsdiffu4(p8, cw);
+      const unsigned a4 = __vabsdiffu4(p4, cw), a12 = __vabsdiffu4(p12, cw);
+      // per byte v > t (t <= 127): bit 7 of ((v & 0x7f) + 127 - t) | v
+      const unsigned f08 = ((a0 & 0x7f7f7f7fu) + tadd) | a0 | ((a8 & 0x7f7f7f7fu) + tadd) | a8;
+      const unsigned f412 = ((a4 & 0x7f7f7f7fu) + tadd) | a4 | ((a12 & 0x7f7f7f7fu) + tadd) | a12;
+      const unsigned pass = f08 & f412;
       plo = (pass & 0x00008080u) != 0u;
       phi = (pass & 0x80800000u) != 0u;
     }
@@ -572,51 +565,51 @@ __host__ inline size_t select1_smem_bytes(int cap) { return (size_t)cap * (sizeo
 __host__ inline size_t select2_smem_bytes(int cap) { return (size_t)cap * (sizeof(vrec_t) + 2 * sizeof(uint16_t)) + 16; }
 
 // retainBest(2 * N_l) on the FAST score.  grid = (n_img, nlevels) — level 0 (the longest problems) is scheduled
-// first — block = 32 (one warp per problem).  Dynamic smem = select1_smem_bytes(smem_cap).
+// first — block = 128: four warps gather the strips, then one warp replays.  Dynamic smem =
+// select1_smem_bytes(smem_cap).
 // In: per-strip raster-ordered corner lists of k_fast.  Out: sel1[level region][0..m1), sel1_cnt[img][level].
 // A level with more corners than smem_cap (or 65535) is replayed in global memory (sel1 as the work array,
 // 32-bit index lists in glists) — slower, same result.
-__global__ void __launch_bounds__(32) k_select1(const __grid_constant__ PyrP P, int smem_cap,
-                                                const int* __restrict__ strip_cnt,
-                                                const uint32_t* __restrict__ strip_rec, uint32_t* __restrict__ sel1,
-                                                uint32_t* __restrict__ glists, int* __restrict__ sel1_cnt) {
+__global__ void __launch_bounds__(128) k_select1(const __grid_constant__ PyrP P, int smem_cap,
+                                                 const int* __restrict__ strip_cnt,
+                                                 const uint32_t* __restrict__ strip_rec, uint32_t* __restrict__ sel1,
+                                                 uint32_t* __restrict__ glists, int* __restrict__ sel1_cnt) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_off[129];
-  const int img = blockIdx.x, l = blockIdx.y, lane = threadIdx.x;
+  const int img = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const LevelP& L = P.lv[l];
   const int* cnt = strip_cnt + (long long)img * P.total_fast_strips + L.fast_strip0;
   const uint32_t* lrec = strip_rec + (long long)img * P.rec_img_stride + L.rec_off;
   uint32_t* out = sel1 + (long long)img * P.rec_img_stride + L.rec_off;
   // strip offsets (nstrips <= 128)
-  int run = 0;
-  for (int b = 0; b < L.fast_nstrips; b += 32) {
-    int i = b + lane;
-    int c = i < L.fast_nstrips ? cnt[i] : 0;
-    int incl = c;
+  if (tid < 32) {
+    int run = 0;
+    for (int b = 0; b < L.fast_nstrips; b += 32) {
+      int i = b + lane;
+      int c = i < L.fast_nstrips ? cnt[i] : 0;
+      int incl = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(VSLAM_FULL, incl, d);
-      if (lane >= d) incl += o;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (i < L.fast_nstrips) s_off[i] = run + incl - c;
+      run += __shfl_sync(VSLAM_FULL, incl, 31);
     }
-    if (i < L.fast_nstrips) s_off[i] = run + incl - c;
-    run += __shfl_sync(VSLAM_FULL, incl, 31);
+    if (lane == 0) s_off[L.fast_nstrips] = run;
   }
-  if (lane == 0) s_off[L.fast_nstrips] = run;
-  __syncwarp();
-  const int n_in = run;
+  __syncthreads();
+  const int n_in = s_off[L.fast_nstrips];
   const bool use_smem = n_in <= smem_cap && n_in <= 65535;
   uint32_t* rec = use_smem ? reinterpret_cast<uint32_t*>(smem) : out;
-  // gather: flat index -> strip by binary search over the offsets (every load independent)
-  for (int i = lane; i < n_in; i += 32) {
-    int lo = 0, hi = L.fast_nstrips - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (s_off[mid] <= i) lo = mid;
-      else hi = mid - 1;
-    }
-    rec[i] = lrec[(long long)lo * L.strip_cap + (i - s_off[lo])];
+  // gather with all 128 threads: one warp per strip at a time, so every load is independent and coalesced
+  for (int s0 = tid >> 5; s0 < L.fast_nstrips; s0 += 4) {
+    const uint32_t* src = lrec + (long long)s0 * L.strip_cap;
+    const int o = s_off[s0], c = s_off[s0 + 1] - o;
+    for (int i = lane; i < c; i += 32) rec[o + i] = src[i];
   }
-  __syncwarp();
+  __syncthreads();
+  if (tid >= 32) return;  // the replay itself is one warp; no block barrier below this line
   int m;
   if (use_smem) {
     uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)smem_cap * sizeof(uint32_t));
@@ -730,29 +723,47 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, co
   // ---- row pass straight from global memory: warp = one (reflected) image row per iteration, lane = 4 output
   //      columns gx..gx+3, which need image x = gx-3 .. gx+6 = three aligned words.  All loads of all iterations are
   //      issued before the first use (memory-level parallelism).  Borders: the word left of x = 0 is a byte
-  //      permutation of word 0 (reflect-101); lanes whose words reach past the right edge gather bytes.
+  //      permutation of word 0 (reflect-101); tiles that touch the right edge take the byte-gather path.
   {
     const int gx = x0 + 4 * lane;
-    const bool fast = gx + 7 < L.w;      // all three words inside the row
-    const bool active = gx < L.w + 3;    // lanes further right produce nothing that is ever read
     unsigned w0[NIT], w1[NIT], w2[NIT];
+    if (x0 + TW + 4 <= L.w) {  // block-uniform: every word of every lane lies inside the row
+      const uint8_t* colp = src + gx;
+      const int lofs = gx > 0 ? -4 : 0;
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int r = warp + 8 * it;
-      w0[it] = w1[it] = w2[it] = 0;
-      if (r < TH + 6 && active) {
-        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);  // clamp: rows past h+2 are never used
-        const uint8_t* row = src + (size_t)gy * pitch;
-        if (fast) {
-          w1[it] = *reinterpret_cast<const uint32_t*>(row + gx);
-          w2[it] = *reinterpret_cast<const uint32_t*>(row + gx + 4);
-          w0[it] = gx > 0 ? *reinterpret_cast<const uint32_t*>(row + gx - 4) : __byte_perm(w1[it], 0u, 0x1230);
-        } else {
+      for (int it = 0; it < NIT; ++it) {
+        const int r = warp + 8 * it;
+        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);
+        const uint8_t* row = colp + (size_t)gy * pitch;
+        w1[it] = *reinterpret_cast<const uint32_t*>(row);
+        w2[it] = *reinterpret_cast<const uint32_t*>(row + 4);
+        w0[it] = *reinterpret_cast<const uint32_t*>(row + lofs);
+      }
+      if (gx == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            w0[it] |= (unsigned)row[reflect101_near(gx - 4 + k, L.w)] << (8 * k);
-            w1[it] |= (unsigned)row[reflect101_near(min(gx + k, L.w + 3), L.w)] << (8 * k);
-            w2[it] |= (unsigned)row[reflect101_near(min(gx + 4 + k, L.w + 3), L.w)] << (8 * k);
+        for (int it = 0; it < NIT; ++it) w0[it] = __byte_perm(w1[it], 0u, 0x1230);
+      }
+    } else {
+      const bool fast = gx + 7 < L.w;      // all three words inside the row
+      const bool active = gx < L.w + 3;    // lanes further right produce nothing that is ever read
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int r = warp + 8 * it;
+        w0[it] = w1[it] = w2[it] = 0;
+        if (r < TH + 6 && active) {
+          const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);  // rows past h+2 are never used
+          const uint8_t* row = src + (size_t)gy * pitch;
+          if (fast) {
+            w1[it] = *reinterpret_cast<const uint32_t*>(row + gx);
+            w2[it] = *reinterpret_cast<const uint32_t*>(row + gx + 4);
+            w0[it] = gx > 0 ? *reinterpret_cast<const uint32_t*>(row + gx - 4) : __byte_perm(w1[it], 0u, 0x1230);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              w0[it] |= (unsigned)row[reflect101_near(gx - 4 + k, L.w)] << (8 * k);
+              w1[it] |= (unsigned)row[reflect101_near(min(gx + k, L.w + 3), L.w)] << (8 * k);
+              w2[it] |= (unsigned)row[reflect101_near(min(gx + 4 + k, L.w + 3), L.w)] << (8 * k);
+            }
           }
         }
       }
@@ -875,14 +886,27 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   const uint8_t* unblurred = level_ptr(P, l, img, in_l, in_r, pyr, upitch);
   const uint8_t* blurred = blur + (long long)img * P.blur_img_stride + L.blur_off;
   const int xb0 = (cx - kBriefR) & ~3, xa0 = (cx - kAngleR) & ~3;
-  for (int i = lane; i < kBriefRows * 10; i += 32) {
-    const int r = i / 10, wq = i - r * 10;
-    sb[r * kBriefRowWords + wq] =
-        *reinterpret_cast<const uint32_t*>(blurred + (size_t)(cy - kBriefR + r) * L.pitch + xb0 + 4 * wq);
-  }
-  for (int i = lane; i < kAngleRows * kAngleRowWords; i += 32) {
-    const int r = i / kAngleRowWords, wq = i - r * kAngleRowWords;
-    sa[i] = *reinterpret_cast<const uint32_t*>(unblurred + (size_t)(cy - kAngleR + r) * upitch + xa0 + 4 * wq);
+  {
+    // three rows per step: lanes 0-9 / 10-19 / 20-29 load the 10 words of a BRIEF row, lanes 0-8 / 9-17 / 18-26 the
+    // 9 words of an orientation row; every load is issued before the first store.
+    const int rb = lane / 10, wb = lane - 10 * rb;
+    const int ra = lane / 9, wa = lane - 9 * ra;
+    const uint8_t* pb = blurred + (size_t)(cy - kBriefR + rb) * L.pitch + xb0 + 4 * wb;
+    const uint8_t* pa = unblurred + (size_t)(cy - kAngleR + ra) * upitch + xa0 + 4 * wa;
+    constexpr int NB = (kBriefRows + 2) / 3, NA = (kAngleRows + 2) / 3;  // 13, 11
+    unsigned vb[NB], va[NA];
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      vb[k] = (lane < 30 && rb + 3 * k < kBriefRows) ? *reinterpret_cast<const uint32_t*>(pb + (size_t)(3 * k) * L.pitch) : 0u;
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+      va[k] = (lane < 27 && ra + 3 * k < kAngleRows) ? *reinterpret_cast<const uint32_t*>(pa + (size_t)(3 * k) * upitch) : 0u;
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      if (lane < 30 && rb + 3 * k < kBriefRows) sb[(rb + 3 * k) * kBriefRowWords + wb] = vb[k];
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+      if (lane < 27 && ra + 3 * k < kAngleRows) sa[(ra + 3 * k) * kAngleRowWords + wa] = va[k];
   }
   __syncwarp();
 
@@ -924,17 +948,18 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
   const float a = (float)cos((double)rad), b = (float)sin((double)rad);
   const uint8_t* center = reinterpret_cast<const uint8_t*>(sb) + kBriefR * (kBriefRowWords * 4) + (cx - xb0);
-  const int4* pat = reinterpret_cast<const int4*>(g_brief_pattern) + 8 * lane;  // 32 ints = 16 points per lane
+  const float4* pat = reinterpret_cast<const float4*>(g_brief_pattern) + 8 * lane;  // 32 values = 16 points per lane
+  // cvRound of a value in (-32, 32): adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits
+  auto rnd = [](float v) -> int { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; };
   unsigned byte = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    int4 t = pat[q];  // one test: (x0,y0,x1,y1)
-    float px0 = __int2float_rn(t.x), py0 = __int2float_rn(t.y), px1 = __int2float_rn(t.z), py1 = __int2float_rn(t.w);
-    int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
-    int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
-    int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
-    int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
-    int t0 = center[iy0 * (kBriefRowWords * 4) + ix0], t1 = center[iy1 * (kBriefRowWords * 4) + ix1];
+    const float4 t = pat[q];  // one test: (x0,y0,x1,y1)
+    const int ix0 = rnd(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
+    const int iy0 = rnd(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
+    const int ix1 = rnd(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
+    const int iy1 = rnd(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
+    const int t0 = center[iy0 * (kBriefRowWords * 4) + ix0], t1 = center[iy1 * (kBriefRowWords * 4) + ix1];
     byte |= (unsigned)(t0 < t1) << q;
   }
   (F.desc[eye] + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;

@@ -371,7 +371,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 2
   {
-    vk::k_select1<<<dim3(nimg, P.nlevels), 32, vk::select1_smem_bytes(h->sel1_cap), st>>>(
+    vk::k_select1<<<dim3(nimg, P.nlevels), 128, vk::select1_smem_bytes(h->sel1_cap), st>>>(
         P, h->sel1_cap, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
     vk::k_harris<<<dim3(h->harris_blocks, P.nlevels, nimg), 128, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_sel1, s.d_sel1_cnt,
                                                                        s.d_cand, h->harris_scale4);
@@ -650,7 +650,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "scale_factor must be in (1, 2]");
   if (c.edge_threshold < 22 || c.edge_threshold > 255)
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "edge_threshold must be >= 22 (BRIEF radius 18 + aligned patch loads)");
-  if (c.fast_threshold < 1 || c.fast_threshold > 254)
+  if (c.fast_threshold < 1 || c.fast_threshold > 127)
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "fast_threshold out of range");
   if (c.max_batch < 1 || c.max_batch > 4096) return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "max_batch out of range");
   int ndev = 0;
