@@ -33,6 +33,28 @@ W, H, NFEAT = 752, 480, 1200
 LEVEL_PIXELS = 1_117_367  # sum of the 8 pyramid levels at 752x480
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr for the rest of the run (NCCL and other native libraries print banners to stdout); the one
+    JSON line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,7 +162,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------- clocks sampler
@@ -190,6 +212,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------- the B200 arm
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -391,7 +414,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "parity": parity, "data_gen_s": round(t_gen, 1),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     sp.close()
     if world > 1:
         dist.destroy_process_group()
