@@ -744,28 +744,44 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, co
         for (int it = 0; it < NIT; ++it) w0[it] = __byte_perm(w1[it], 0u, 0x1230);
       }
     } else {
-      const bool fast = gx + 7 < L.w;      // all three words inside the row
-      const bool active = gx < L.w + 3;    // lanes further right produce nothing that is ever read
+      // Right-edge tiles.  Reflect-101 mirrors x = e + k onto e - k (e = w - 1), so every byte a lane needs beyond the
+      // edge is one of the last four pixels of the row.  Per lane and word a PRMT selector (fixed for the whole tile)
+      // picks each byte either from the lane's own (address-clamped) word or from the strip S = pixels e-3 .. e.
+      const int e = L.w - 1;
+      const int xs = (e - 3) & ~3;                    // aligned word holding pixel e-3 (w >= 32)
+      const int sh = 8 * ((e - 3) & 3);
+      const int xs2 = sh ? xs + 4 : xs;               // second strip word only when the strip straddles two words
+      const int xmax = e & ~3;                        // last aligned word that starts inside the row
+      int xo[3];
+      unsigned sel[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int xk = gx - 4 + 4 * k;
+        xo[k] = min(max(xk, 0), xmax);
+        unsigned sk = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int d = xk + b - e;                   // > 0: beyond the edge -> strip byte 3 - d
+          const unsigned nib = d <= 0 ? (unsigned)b : (d <= 3 ? (unsigned)(7 - d) : 0u);
+          sk |= nib << (4 * b);
+        }
+        sel[k] = sk;
+      }
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         const int r = warp + 8 * it;
-        w0[it] = w1[it] = w2[it] = 0;
-        if (r < TH + 6 && active) {
-          const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);  // rows past h+2 are never used
-          const uint8_t* row = src + (size_t)gy * pitch;
-          if (fast) {
-            w1[it] = *reinterpret_cast<const uint32_t*>(row + gx);
-            w2[it] = *reinterpret_cast<const uint32_t*>(row + gx + 4);
-            w0[it] = gx > 0 ? *reinterpret_cast<const uint32_t*>(row + gx - 4) : __byte_perm(w1[it], 0u, 0x1230);
-          } else {
+        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);
+        const uint8_t* row = src + (size_t)gy * pitch;
+        const unsigned sA = *reinterpret_cast<const uint32_t*>(row + xs);
+        const unsigned sB = *reinterpret_cast<const uint32_t*>(row + xs2);
+        const unsigned S = __funnelshift_r(sA, sB, sh);
+        w0[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[0]), S, sel[0]);
+        w1[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[1]), S, sel[1]);
+        w2[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[2]), S, sel[2]);
+      }
+      if (gx == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              w0[it] |= (unsigned)row[reflect101_near(gx - 4 + k, L.w)] << (8 * k);
-              w1[it] |= (unsigned)row[reflect101_near(min(gx + k, L.w + 3), L.w)] << (8 * k);
-              w2[it] |= (unsigned)row[reflect101_near(min(gx + 4 + k, L.w + 3), L.w)] << (8 * k);
-            }
-          }
-        }
+        for (int it = 0; it < NIT; ++it) w0[it] = __byte_perm(w1[it], 0u, 0x1230);
       }
     }
 #pragma unroll
@@ -893,20 +909,34 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     const int ra = lane / 9, wa = lane - 9 * ra;
     const uint8_t* pb = blurred + (size_t)(cy - kBriefR + rb) * L.pitch + xb0 + 4 * wb;
     const uint8_t* pa = unblurred + (size_t)(cy - kAngleR + ra) * upitch + xa0 + 4 * wa;
-    constexpr int NB = (kBriefRows + 2) / 3, NA = (kAngleRows + 2) / 3;  // 13, 11
-    unsigned vb[NB], va[NA];
+    constexpr int NB = (kBriefRows + 2) / 3, NA = (kAngleRows + 2) / 3;  // 13, 11 steps of three rows
+    const bool lb = lane < 30, la = lane < 27;
+    const size_t stepb = (size_t)3 * L.pitch, stepa = (size_t)3 * upitch;
+    unsigned* qb = sb + rb * kBriefRowWords + wb;
+    unsigned* qa = sa + ra * kAngleRowWords + wa;
+    // groups of six loads in flight (small arrays stay in registers)
 #pragma unroll
-    for (int k = 0; k < NB; ++k)
-      vb[k] = (lane < 30 && rb + 3 * k < kBriefRows) ? *reinterpret_cast<const uint32_t*>(pb + (size_t)(3 * k) * L.pitch) : 0u;
+    for (int k0 = 0; k0 < NB; k0 += 6) {
+      unsigned v[6];
 #pragma unroll
-    for (int k = 0; k < NA; ++k)
-      va[k] = (lane < 27 && ra + 3 * k < kAngleRows) ? *reinterpret_cast<const uint32_t*>(pa + (size_t)(3 * k) * upitch) : 0u;
+      for (int k = 0; k < 6; ++k)
+        v[k] = (k0 + k < NB && lb && rb + 3 * (k0 + k) < kBriefRows)
+                   ? *reinterpret_cast<const uint32_t*>(pb + (size_t)(k0 + k) * stepb) : 0u;
 #pragma unroll
-    for (int k = 0; k < NB; ++k)
-      if (lane < 30 && rb + 3 * k < kBriefRows) sb[(rb + 3 * k) * kBriefRowWords + wb] = vb[k];
+      for (int k = 0; k < 6; ++k)
+        if (k0 + k < NB && lb && rb + 3 * (k0 + k) < kBriefRows) qb[3 * (k0 + k) * kBriefRowWords] = v[k];
+    }
 #pragma unroll
-    for (int k = 0; k < NA; ++k)
-      if (lane < 27 && ra + 3 * k < kAngleRows) sa[(ra + 3 * k) * kAngleRowWords + wa] = va[k];
+    for (int k0 = 0; k0 < NA; k0 += 6) {
+      unsigned v[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        v[k] = (k0 + k < NA && la && ra + 3 * (k0 + k) < kAngleRows)
+                   ? *reinterpret_cast<const uint32_t*>(pa + (size_t)(k0 + k) * stepa) : 0u;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k0 + k < NA && la && ra + 3 * (k0 + k) < kAngleRows) qa[3 * (k0 + k) * kAngleRowWords] = v[k];
+    }
   }
   __syncwarp();
 

@@ -165,7 +165,7 @@ int build_params(vslam_handle h) {
     L.scale = scale;
     L.w = cv_roundf((float)c.width * inv);
     L.h = cv_roundf((float)c.height * inv);
-    if (L.w < 16 || L.h < 16) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "pyramid level %d is too small (%dx%d)", l, L.w, L.h);
+    if (L.w < 32 || L.h < 32) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "pyramid level %d is too small (%dx%d)", l, L.w, L.h);
     L.pitch = l == 0 ? P.in_pitch : (int)align_up((size_t)L.w, 16);
     if (l > 0) {
       L.pyr_off = (int)pyr_off;
