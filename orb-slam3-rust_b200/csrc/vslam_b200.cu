@@ -38,7 +38,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // blur runs here, concurrently with the FAST -> selection chain
   cudaEvent_t done = nullptr;
+  cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
   uint8_t* d_in = nullptr;
   uint8_t* d_pyr = nullptr;
   uint8_t* d_blur = nullptr;
@@ -297,7 +299,10 @@ int alloc_slot(vslam_handle h, Slot& s) {
   const PyrP& P = h->P;
   const size_t nimg = 2 * (size_t)h->max_batch, nfr = (size_t)h->max_batch;
   CU_TRY(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CU_TRY(h, cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
   CU_TRY(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  CU_TRY(h, cudaEventCreateWithFlags(&s.ev_pyr, cudaEventDisableTiming));
+  CU_TRY(h, cudaEventCreateWithFlags(&s.ev_blur, cudaEventDisableTiming));
   CU_TRY(h, cudaMalloc(&s.d_in, nimg * h->in_img_bytes));
   CU_TRY(h, cudaMalloc(&s.d_pyr, nimg * (size_t)P.pyr_img_stride));
   CU_TRY(h, cudaMalloc(&s.d_blur, nimg * (size_t)P.blur_img_stride));
@@ -329,6 +334,9 @@ void free_slot(Slot& s) {
   if (s.h_in) cudaFreeHost(s.h_in);
   if (s.h_res) cudaFreeHost(s.h_res);
   if (s.done) cudaEventDestroy(s.done);
+  if (s.ev_pyr) cudaEventDestroy(s.ev_pyr);
+  if (s.ev_blur) cudaEventDestroy(s.ev_blur);
+  if (s.stream2) cudaStreamDestroy(s.stream2);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
 }
@@ -363,6 +371,18 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     h->launches++;
   }
   mark();  // 1
+  // The blur only needs the pyramid: outside profiling it runs on the slot's second stream, overlapping the
+  // latency-bound selection chain (k_select1/k_harris/k_select2 keep the SMs mostly idle).
+  const bool fork = !prof;
+  cudaStream_t sb = fork ? s.stream2 : st;
+  if (fork) {
+    CU_TRY(h, cudaEventRecord(s.ev_pyr, st));
+    CU_TRY(h, cudaStreamWaitEvent(sb, s.ev_pyr, 0));
+    dim3 grid(P.total_blur_tiles, nimg);
+    vk::k_blur<<<grid, 256, 0, sb>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
+    h->launches++;
+    CU_TRY(h, cudaEventRecord(s.ev_blur, sb));
+  }
   if (P.total_fast_strips > 0) {
     dim3 grid(P.total_fast_strips, nimg);
     vk::k_fast<<<grid, 256, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)), st>>>(P, in_l, in_r, s.d_pyr,
@@ -380,10 +400,12 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     h->launches += 3;
   }
   mark();  // 3
-  {
+  if (!fork) {
     dim3 grid(P.total_blur_tiles, nimg);
     vk::k_blur<<<grid, 256, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
+  } else {
+    CU_TRY(h, cudaStreamWaitEvent(st, s.ev_blur, 0));
   }
   mark();  // 4
   {
