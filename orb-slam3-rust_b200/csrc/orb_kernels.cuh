@@ -31,6 +31,19 @@ __device__ float g_brief_pattern[1024] = {
 #include "brief_pattern.inc"
 };
 
+// Orientation tables (filled by the host at handle creation, see upload_angle_tables in vslam_b200.cu):
+//   g_angle_mask[o][r][j]  byte b = 0xff iff pixel u = 4j + b - (15 + o) of patch row r lies inside the 31-px disc
+//   g_angle_u[o][j]        byte b = (int8) u
+// o = (cx - 15) & 3 is the alignment of the staged patch; with them a patch row is reduced by 9 x 2 dp4a.
+__device__ unsigned g_angle_mask[4][31][9];
+__device__ unsigned g_angle_u[4][9];
+
+__device__ __forceinline__ int dp4a_u8_s8(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 struct __align__(8) LvlKp {
   unsigned xy;  // (y<<16)|x in level coordinates
   float resp;   // Harris response
@@ -178,6 +191,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   uint32_t* bits = reinterpret_cast<uint32_t*>(sc + (VSLAM_FAST_ROWS + 2) * SP);  // rows x BW corner bitmask
   uint32_t* woff = bits + VSLAM_FAST_ROWS * BW;          // rows x BW exclusive corner offsets
   __shared__ int s_total;
+  __shared__ int s_cn;  // number of pre-NMS corners pushed to the sparse-NMS list
+  if (tid == 0) s_cn = 0;  // ordered before the first push by the __syncthreads() that ends the staging
 
   // ---- stage the pixel tile (128-bit loads), clear margins / score tile / bitmask
   const int vpr = pitch >> 4;
@@ -211,105 +226,131 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   const unsigned t2 = t * 0x00010001u;
   const unsigned tadd = (127u - t) * 0x01010101u;  // fast_threshold <= 127 (checked by vslam_create)
   const unsigned lt = (1u << lane) - 1u;
-  __shared__ unsigned short s_queue[8][96];
+  constexpr int kCornerList = 2048;  // pre-NMS corners of a strip kept for the sparse NMS pass (else: full scan)
+  __shared__ unsigned s_clist[kCornerList];
+  __shared__ unsigned short s_queue[8][128];  // per-warp ring of queued pairs: (score row << 11) | (group << 1) | half
   unsigned short* q = s_queue[warp];
-  int qn = 0;  // warp-uniform number of queued pairs
-
-  auto score_pairs = [&](int count) {  // the first `count` (<= 32) queue entries, one pair per lane
-    if (lane < count) {
-      const unsigned code = q[lane];
-      const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
-      const int y = sy_lo + ry;
-      const uint8_t* base = pix + (y - (ys - 4)) * SP + 16 + 4 * g;
-      unsigned w[7][3];
-#pragma unroll
-      for (int dy = -3; dy <= 3; ++dy) {
-        const uint32_t* qq = reinterpret_cast<const uint32_t*>(base + dy * SP);
-        w[dy + 3][0] = qq[-1];
-        w[dy + 3][1] = qq[0];
-        w[dy + 3][2] = qq[1];
-      }
-#define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
-      unsigned s[16];
-      s[0] = shifted4<0>(VS_ROW(3));
-      s[1] = shifted4<1>(VS_ROW(3));
-      s[2] = shifted4<2>(VS_ROW(2));
-      s[3] = shifted4<3>(VS_ROW(1));
-      s[4] = shifted4<3>(VS_ROW(0));
-      s[5] = shifted4<3>(VS_ROW(-1));
-      s[6] = shifted4<2>(VS_ROW(-2));
-      s[7] = shifted4<1>(VS_ROW(-3));
-      s[8] = shifted4<0>(VS_ROW(-3));
-      s[9] = shifted4<-1>(VS_ROW(-3));
-      s[10] = shifted4<-2>(VS_ROW(-2));
-      s[11] = shifted4<-3>(VS_ROW(-1));
-      s[12] = shifted4<-3>(VS_ROW(0));
-      s[13] = shifted4<-3>(VS_ROW(1));
-      s[14] = shifted4<-2>(VS_ROW(2));
-      s[15] = shifted4<-1>(VS_ROW(3));
-#undef VS_ROW
-      const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
-      unsigned p[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) p[k] = __byte_perm(s[k], 0u, sel);
-      const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
-      const int x = 4 * g + 2 * half;
-      unsigned lo8 = (x >= sx0 && x < sx1) ? (xs & 0xffu) : 0u;
-      unsigned hi8 = (x + 1 >= sx0 && x + 1 < sx1) ? ((xs >> 16) & 0xffu) : 0u;
-      *reinterpret_cast<unsigned short*>(sc + (y - (ys - 1)) * SP + 16 + x) = (unsigned short)(lo8 | (hi8 << 8));
-    }
-  };
-
+  int qn = 0, qhead = 0;  // warp-uniform
   const int nitems = nsr * ngx;
   const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
   const uint8_t* const pix0 = pix + (sy_lo - (ys - 4)) * SP + 16;  // centre pixel of score row 0, group 0
+  uint8_t* const sc0 = sc + (sy_lo - (ys - 1)) * SP + 16;
   const int SP3 = 3 * SP;
-  for (int it0 = warp * 32; it0 < nitems; it0 += 256) {
-    const int it = it0 + lane;
-    bool plo = false, phi = false;
-    int ry = 0, g = 0;
-    if (it < nitems) {
-      ry = (int)__umulhi((unsigned)it, inv_ngx);
-      g = gx0 + (it - ry * ngx);
-      const uint8_t* base = pix0 + ry * SP + 4 * g;
-      const uint32_t* rc = reinterpret_cast<const uint32_t*>(base);
-      const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
-      const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + SP3);
-      const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - SP3);
-      const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
-      const unsigned a0 = __vabsdiffu4(p0, cw), a8 = __vabsdiffu4(p8, cw);
-      const unsigned a4 = __vabsdiffu4(p4, cw), a12 = __vabsdiffu4(p12, cw);
-      // per byte v > t (t <= 127): bit 7 of ((v & 0x7f) + 127 - t) | v
-      const unsigned f08 = ((a0 & 0x7f7f7f7fu) + tadd) | a0 | ((a8 & 0x7f7f7f7fu) + tadd) | a8;
-      const unsigned f412 = ((a4 & 0x7f7f7f7fu) + tadd) | a4 | ((a12 & 0x7f7f7f7fu) + tadd) | a12;
-      const unsigned pass = f08 & f412;
-      plo = (pass & 0x00008080u) != 0u;
-      phi = (pass & 0x80800000u) != 0u;
+  int it0 = warp * 32;
+#pragma unroll 1
+  while (true) {
+    if (qn >= 32 || (it0 >= nitems && qn > 0)) {
+      // ---- phase B: exact score of up to 32 queued pairs, one pair per lane
+      bool c_lo = false, c_hi = false;
+      unsigned c_code = 0;
+      if (lane < qn) {
+        const unsigned code = q[(qhead + lane) & 127];
+        const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
+        const uint8_t* base = pix0 + ry * SP + 4 * g;
+        unsigned w[7][3];
+#pragma unroll
+        for (int dy = -3; dy <= 3; ++dy) {
+          const uint32_t* qq = reinterpret_cast<const uint32_t*>(base + dy * SP);
+          w[dy + 3][0] = qq[-1];
+          w[dy + 3][1] = qq[0];
+          w[dy + 3][2] = qq[1];
+        }
+#define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
+        unsigned sv[16];
+        sv[0] = shifted4<0>(VS_ROW(3));
+        sv[1] = shifted4<1>(VS_ROW(3));
+        sv[2] = shifted4<2>(VS_ROW(2));
+        sv[3] = shifted4<3>(VS_ROW(1));
+        sv[4] = shifted4<3>(VS_ROW(0));
+        sv[5] = shifted4<3>(VS_ROW(-1));
+        sv[6] = shifted4<2>(VS_ROW(-2));
+        sv[7] = shifted4<1>(VS_ROW(-3));
+        sv[8] = shifted4<0>(VS_ROW(-3));
+        sv[9] = shifted4<-1>(VS_ROW(-3));
+        sv[10] = shifted4<-2>(VS_ROW(-2));
+        sv[11] = shifted4<-3>(VS_ROW(-1));
+        sv[12] = shifted4<-3>(VS_ROW(0));
+        sv[13] = shifted4<-3>(VS_ROW(1));
+        sv[14] = shifted4<-2>(VS_ROW(2));
+        sv[15] = shifted4<-1>(VS_ROW(3));
+#undef VS_ROW
+        const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
+        unsigned p[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
+        const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
+        const int x = 4 * g + 2 * half;
+        unsigned out16 = __byte_perm(xs, 0u, 0x4420);            // (lane0, lane1) low bytes -> one u16
+        if (x < sx0 || x >= sx1) out16 &= 0xff00u;                // pixels outside the scored columns stay 0
+        if (x + 1 < sx0 || x + 1 >= sx1) out16 &= 0x00ffu;
+        *reinterpret_cast<unsigned short*>(sc0 + ry * SP + x) = (unsigned short)out16;
+        // remember non-zero scores inside the emission region for the sparse NMS pass
+        const int y = sy_lo + ry;
+        const bool rowin = y >= ys && y < ye;
+        c_lo = rowin && (out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1;
+        c_hi = rowin && (out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1;
+        c_code = ((unsigned)(y - ys) << 12) | (unsigned)x;
+      }
+      {
+        const unsigned blo = __ballot_sync(VSLAM_FULL, c_lo), bhi = __ballot_sync(VSLAM_FULL, c_hi);
+        const int nadd = __popc(blo) + __popc(bhi);
+        if (nadd) {
+          int basep = 0;
+          if (lane == 0) basep = atomicAdd(&s_cn, nadd);
+          basep = __shfl_sync(VSLAM_FULL, basep, 0);
+          const int plo = basep + __popc(blo & lt), phi = basep + __popc(blo) + __popc(bhi & lt);
+          if (c_lo && plo < kCornerList) s_clist[plo] = c_code;
+          if (c_hi && phi < kCornerList) s_clist[phi] = c_code + 1u;
+        }
+      }
+      const int done = min(qn, 32);
+      qhead = (qhead + done) & 127;
+      qn -= done;
+      __syncwarp();
+      continue;
     }
-    const unsigned mlo = __ballot_sync(VSLAM_FULL, plo), mhi = __ballot_sync(VSLAM_FULL, phi);
+    if (it0 >= nitems) break;
+    // ---- phase A: necessary condition on a group of 4 pixels (byte SIMD), queue the pairs that pass
+    const int it = min(it0 + lane, nitems - 1);
+    const int ry = (int)__umulhi((unsigned)it, inv_ngx);
+    const int g = gx0 + (it - ry * ngx);
+    const uint8_t* base = pix0 + ry * SP + 4 * g;
+    const uint32_t* rc = reinterpret_cast<const uint32_t*>(base);
+    const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
+    const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + SP3);
+    const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - SP3);
+    const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
+    const unsigned a0 = __vabsdiffu4(p0, cw), a8 = __vabsdiffu4(p8, cw);
+    const unsigned a4 = __vabsdiffu4(p4, cw), a12 = __vabsdiffu4(p12, cw);
+    // per byte v > t (t <= 127): bit 7 of ((v & 0x7f) + 127 - t) | v
+    const unsigned f08 = ((a0 & 0x7f7f7f7fu) + tadd) | a0 | ((a8 & 0x7f7f7f7fu) + tadd) | a8;
+    const unsigned f412 = ((a4 & 0x7f7f7f7fu) + tadd) | a4 | ((a12 & 0x7f7f7f7fu) + tadd) | a12;
+    const unsigned pass = (it0 + lane < nitems) ? (f08 & f412) : 0u;
+    const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
+    const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
     const unsigned code = ((unsigned)ry << 11) | ((unsigned)g << 1);
-    if (plo) q[qn + __popc(mlo & lt)] = (unsigned short)code;
-    if (phi) q[qn + __popc(mlo) + __popc(mhi & lt)] = (unsigned short)(code | 1u);
+    const int tail = qhead + qn;
+    if (mlo & (1u << lane)) q[(tail + __popc(mlo & lt)) & 127] = (unsigned short)code;
+    if (mhi & (1u << lane)) q[(tail + __popc(mlo) + __popc(mhi & lt)) & 127] = (unsigned short)(code | 1u);
     qn += __popc(mlo) + __popc(mhi);
+    it0 += 256;
     __syncwarp();
-    while (qn >= 32) {  // at most two rounds: qn < 32 + 64
-      score_pairs(32);
-      __syncwarp();
-      const int rest = qn - 32;
-      unsigned short keep0 = 0, keep1 = 0;
-      if (lane < rest) keep0 = q[32 + lane];
-      if (lane + 32 < rest) keep1 = q[64 + lane];
-      __syncwarp();
-      if (lane < rest) q[lane] = keep0;
-      if (lane + 32 < rest) q[32 + lane] = keep1;
-      qn = rest;
-      __syncwarp();
-    }
   }
-  if (qn > 0) score_pairs(qn);
   __syncthreads();
 
   // ---- non-maximum suppression (strictly greater than the 8 neighbours) + runByImageBorder
+  const int ncorn = s_cn;
+  if (ncorn <= kCornerList) {
+    for (int i = tid; i < ncorn; i += 256) {
+      const unsigned code = s_clist[i];
+      const int ry = (int)(code >> 12), x = (int)(code & 0xfffu);
+      const uint8_t* c = sc + (ry + 1) * SP + 16 + x;
+      const int v = c[0];
+      const bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
+                        v > c[SP] && v > c[SP + 1];
+      if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+    }
+  } else {
   const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
   const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
   for (int it = tid; it < rows * negx; it += 256) {
@@ -328,6 +369,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
                   v > c[SP] && v > c[SP + 1];
       if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
     }
+  }
   }
   __syncthreads();
 
@@ -940,21 +982,22 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   }
   __syncwarp();
 
-  // ---- A4: intensity-centroid angle; lane v+15 sums row v of the disc
+  // ---- A4: intensity-centroid angle; lane v+15 reduces row v of the disc with dp4a (masked words x {1, u})
   int m10 = 0, m01 = 0;
   if (lane < kAngleRows) {
-    const int v = lane - kAngleR;
-    const int av = v < 0 ? -v : v;
-    const int d = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);  // umax[|v|]
-    const uint8_t* row = reinterpret_cast<const uint8_t*>(sa + lane * kAngleRowWords) + (cx - xa0);
+    const int o = (cx - kAngleR) & 3;
+    const unsigned* mrow = g_angle_mask[o][lane];
+    const unsigned* urow = g_angle_u[o];
+    const unsigned* prow = sa + lane * kAngleRowWords;
     int sum = 0, su = 0;
-    for (int u = -d; u <= d; ++u) {
-      int val = row[u];
-      sum += val;
-      su += u * val;
+#pragma unroll
+    for (int j = 0; j < kAngleRowWords; ++j) {
+      const unsigned wv = prow[j] & mrow[j];
+      sum = dp4a_u8_s8(wv, 0x01010101u, sum);
+      su = dp4a_u8_s8(wv, urow[j], su);
     }
     m10 = su;
-    m01 = v * sum;
+    m01 = (lane - kAngleR) * sum;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
