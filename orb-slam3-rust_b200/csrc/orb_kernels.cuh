@@ -894,6 +894,37 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, co
 // A6 — steered BRIEF + KeyPoint assembly.  grid = (ceil(kp_cap / 8), n_img), block = 256 (8 warps, one keypoint
 // each); lane b computes descriptor byte b (16 rotated pattern points).  Output order: levels 0..n-1 concatenated.
 // ----------------------------------------------------------------------------------------------------------
+// (float)cos((double)x), (float)sin((double)x) for 0 <= x < 2*pi + eps, as OpenCV's steering computes them with the
+// host libm.  Double-precision evaluation (Cody-Waite reduction by pi/2, Cephes minimax kernels, <= ~1 ulp(double))
+// so that the value rounded to float equals the correctly rounded one except with probability ~1e-8 per call.
+// Written out instead of calling cos()/sin(): the CUDA library versions keep their coefficient table in local
+// memory, which cost 112 B of stack stores per thread at kernel entry.
+__device__ __forceinline__ void sincos_f64_to_f32(float xf, float& cf, float& sf) {
+  const double x = (double)xf;
+  const double q = rint(x * 6.36619772367581382433e-01);
+  double t = fma(-q, 1.57079632679489655800e+00, x);
+  t = fma(-q, 6.12323399573676603587e-17, t);
+  const double z = t * t;
+  double ps = 1.58962301576546568060e-10;
+  ps = fma(ps, z, -2.50507477628578072866e-8);
+  ps = fma(ps, z, 2.75573136213857245213e-6);
+  ps = fma(ps, z, -1.98412698295895385996e-4);
+  ps = fma(ps, z, 8.33333333332211858878e-3);
+  ps = fma(ps, z, -1.66666666666666307295e-1);
+  const double sn = fma(t * z, ps, t);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-9);
+  pc = fma(pc, z, -2.75573143513906633035e-7);
+  pc = fma(pc, z, 2.48015872894767294178e-5);
+  pc = fma(pc, z, -1.38888888888741095749e-3);
+  pc = fma(pc, z, 4.16666666666666019037e-2);
+  const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const int iq = (int)q;
+  const double s1 = (iq & 1) ? cs : sn, c1 = (iq & 1) ? sn : cs;
+  sf = (float)((iq & 2) ? -s1 : s1);
+  cf = (float)(((iq + 1) & 2) ? -c1 : c1);
+}
+
 struct __align__(4) KeyPoint28 {
   float x, y, size, angle, response;
   int octave, class_id;
@@ -1015,11 +1046,13 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     o.response = kp.resp;
     o.octave = l;
     o.class_id = -1;
-    reinterpret_cast<KeyPoint28*>(F.kp[eye] + (long long)frame * F.kp_stride)[j] = o;
+    unsigned char* kpbase = eye ? F.kp[1] : F.kp[0];  // no dynamic indexing of the by-value parameter struct
+    reinterpret_cast<KeyPoint28*>(kpbase + (long long)frame * F.kp_stride)[j] = o;
   }
   // ---- A6: angle *= (float)(CV_PI/180.f); a = (float)cos(angle); b = (float)sin(angle)  (double cos/sin of the f32)
   const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
-  const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+  float a, b;
+  sincos_f64_to_f32(rad, a, b);
   const uint8_t* center = reinterpret_cast<const uint8_t*>(sb) + kBriefR * (kBriefRowWords * 4) + (cx - xb0);
   const float4* pat = reinterpret_cast<const float4*>(g_brief_pattern) + 8 * lane;  // 32 values = 16 points per lane
   // cvRound of a value in (-32, 32): adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits
@@ -1035,7 +1068,8 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
     const int t0 = center[iy0 * (kBriefRowWords * 4) + ix0], t1 = center[iy1 * (kBriefRowWords * 4) + ix1];
     byte |= (unsigned)(t0 < t1) << q;
   }
-  (F.desc[eye] + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
+  unsigned char* descbase = eye ? F.desc[1] : F.desc[0];
+  (descbase + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
 }
 
 }  // namespace vk

@@ -28,7 +28,7 @@ struct KpXY {  // first 8 bytes of cv::KeyPoint
 };
 
 __device__ __forceinline__ const float* kp_ptr(const FrameLayout& F, int frame, int eye, int i) {
-  return reinterpret_cast<const float*>(F.kp[eye] + (long long)frame * F.kp_stride + (size_t)i * 28);
+  return reinterpret_cast<const float*>((eye ? F.kp[1] : F.kp[0]) + (long long)frame * F.kp_stride + (size_t)i * 28);
 }
 
 // grid = (ceil(cap / 64), frames), block = 256.  ml[frame*cap + li] = (right idx or -1, best distance).
