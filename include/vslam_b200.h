@@ -16,6 +16,9 @@
  *   vslam_grid_build / vslam_grid_query <- FeatureGrid::{new,get_features_in_area}  src/tracking/tracking_frame.rs:52-128
  *   vslam_search_by_projection          <- the two inline searches in Tracker       src/tracking/tracker.rs:863-923, 1093-1158
  *   vslam_bf_match_crosscheck           <- BFMatcher(NORM_HAMMING,true).train_match src/tracking/tracker.rs:1001-1010
+ *   vslam_fuse_search                   <- descriptor search of fuse_points_into_keyframes
+ *                                          src/local_mapping/search_in_neighbors.rs:303-340 (+ keyframe.rs:408-446)
+ *   vslam_distinctive_descriptors       <- Map::compute_distinctive_descriptors       src/atlas/map/map.rs:917-937
  *
  * All pixel/descriptor arithmetic runs in hand-written CUDA kernels for sm_100a.  There is NO CPU fallback:
  * every call fails with VSLAM_ERR_CUDA when no usable device is present.
@@ -191,6 +194,19 @@ int vslam_search_by_projection(vslam_handle h, const vslam_keypoint* kps, const 
 /* BFMatcher(NORM_HAMMING, crossCheck=true).train_match(query, train): matches[n_query], ascending query index. */
 int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query, const uint8_t* train, int n_train,
                               vslam_dmatch* matches, int* n_matches);
+
+/* ---- keyframe-rate Hamming consumers --------------------------------------------------- */
+/* Fusion search of local mapping: for each query q = (u, v, radius) (host-projected map point, radius already clamped
+ * by the caller) scan ALL n keyframe keypoints, keep those with du*du + dv*dv <= radius*radius (f64, as
+ * KeyFrame::get_features_in_area), and return the first minimum Hamming distance below desc_threshold.
+ * uvr[M][3] f64; mp_desc[M][32]; out_idx[M] = keypoint index or -1; out_dist[M] = distance or -1. */
+int vslam_fuse_search(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, const double* uvr,
+                      const uint8_t* mp_desc, int M, uint32_t desc_threshold, int32_t* out_idx, int32_t* out_dist);
+
+/* Distinctive ("median") descriptor of M map points: descriptors of map point m are rows offsets[m]..offsets[m+1]-1 of
+ * desc; out_idx[m] = position (within the group) of the descriptor whose maximum distance to the others is smallest
+ * (first minimum), 0 for a single descriptor, -1 for none. */
+int vslam_distinctive_descriptors(vslam_handle h, const uint8_t* desc, const int32_t* offsets, int M, int32_t* out_idx);
 
 /* ---- introspection for parity tests and profiling ---------------------------------------------------------- */
 enum {

@@ -263,3 +263,24 @@ def bf_match_crosscheck(query, train):
     out = np.zeros(max(len(q), 1), dtype=DMATCH_DTYPE)
     n = lib().orc_bf_match_crosscheck(_p(q), len(q), _p(t), len(t), _p(out))
     return out[:n].copy()
+
+
+def fuse_search(kp, desc, uvr, mp_desc, desc_threshold=50):
+    kp = np.ascontiguousarray(kp, dtype=KP_DTYPE)
+    desc = np.ascontiguousarray(desc, dtype=np.uint8)
+    uvr = np.ascontiguousarray(uvr, dtype=np.float64).reshape(-1, 3)
+    mp_desc = np.ascontiguousarray(mp_desc, dtype=np.uint8).reshape(-1, 32)
+    M = len(uvr)
+    idx = np.full(max(M, 1), -1, dtype=np.int32)
+    dist = np.full(max(M, 1), -1, dtype=np.int32)
+    lib().orc_fuse_search(_p(kp), _p(desc), len(kp), _p(uvr), _p(mp_desc), M, C.c_uint32(desc_threshold), _p(idx), _p(dist))
+    return idx[:M], dist[:M]
+
+
+def distinctive_descriptors(desc, offsets):
+    desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    M = len(offsets) - 1
+    out = np.full(max(M, 1), -1, dtype=np.int32)
+    lib().orc_distinctive_descriptors(_p(desc), _p(offsets), M, _p(out))
+    return out[:M]

@@ -8,6 +8,9 @@
 //   local-map search      /root/reference/src/tracking/tracker.rs:863-923
 //   motion-model search   /root/reference/src/tracking/tracker.rs:1093-1158
 //   ref-KF BFMatcher      /root/reference/src/tracking/tracker.rs:1001-1010 (cv::BFMatcher(NORM_HAMMING, crossCheck))
+//   fusion search         /root/reference/src/local_mapping/search_in_neighbors.rs:303-340 with the linear-scan
+//                         KeyFrame::get_features_in_area of src/atlas/map/keyframe.rs:408-446      
+//   distinctive descriptor /root/reference/src/atlas/map/map.rs:917-937 (min over i of max_j Hamming)   (row f2)
 //
 // PARITY UNPINNED for this file: the reference cannot be built here (no Rust toolchain) and holds no test
 // for these functions; the only related known-answer vectors are the popcount twins at
@@ -274,6 +277,62 @@ int orc_bf_match_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt, 
     }
   }
   return n;
+}
+
+// search_in_neighbors.rs:303-340: for every (map point, target keyframe) query (u, v, radius) the candidates are ALL
+// keyframe keypoints inside the true disc (keyframe.rs:436-443: du*du + dv*dv <= r*r in f64, ascending index); the
+// match is the first minimum with dist < desc_threshold.  out_idx[q] = keypoint index or -1.
+void orc_fuse_search(const OrcKeyPoint* kp, const uint8_t* desc, int n, const double* uvr, const uint8_t* mp_desc, int M,
+                     uint32_t desc_threshold, int* out_idx, int* out_dist) {
+  for (int q = 0; q < M; ++q) {
+    const double u = uvr[3 * q], v = uvr[3 * q + 1], radius = uvr[3 * q + 2];
+    const double radius_sq = radius * radius;
+    uint32_t best = 0xFFFFFFFFu;
+    int best_idx = -1;
+    for (int i = 0; i < n; ++i) {
+      double du = (double)kp[i].x - u, dv = (double)kp[i].y - v;
+      double dist_sq = du * du + dv * dv;
+      if (!(dist_sq <= radius_sq)) continue;
+      uint32_t d = orc_descriptor_distance(mp_desc + (size_t)q * 32, 32, desc + (size_t)i * 32, 32);
+      if (d < best && d < desc_threshold) {
+        best = d;
+        best_idx = i;
+      }
+    }
+    out_idx[q] = best_idx;
+    out_dist[q] = best_idx >= 0 ? (int)best : -1;
+  }
+}
+
+// map.rs:917-937: per map point, the descriptor whose maximum distance to the others is smallest (first minimum in
+// the given order); one descriptor -> index 0, none -> -1.  offsets: M+1 CSR offsets into desc rows.
+void orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int M, int* out_idx) {
+  for (int m = 0; m < M; ++m) {
+    const int b = offsets[m], e = offsets[m + 1], k = e - b;
+    if (k <= 0) {
+      out_idx[m] = -1;
+      continue;
+    }
+    if (k == 1) {
+      out_idx[m] = 0;
+      continue;
+    }
+    int best_idx = 0;
+    uint32_t best_max = 0xFFFFFFFFu;
+    for (int i = 0; i < k; ++i) {
+      uint32_t mx = 0;
+      for (int j = 0; j < k; ++j)
+        if (i != j) {
+          uint32_t d = orc_descriptor_distance(desc + (size_t)(b + i) * 32, 32, desc + (size_t)(b + j) * 32, 32);
+          if (d > mx) mx = d;
+        }
+      if (mx < best_max) {
+        best_max = mx;
+        best_idx = i;
+      }
+    }
+    out_idx[m] = best_idx;
+  }
 }
 
 }  // extern "C"

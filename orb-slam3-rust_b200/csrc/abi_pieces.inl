@@ -292,4 +292,60 @@ int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query,
   return VSLAM_OK;
 }
 
+int vslam_fuse_search(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, const double* uvr,
+                      const uint8_t* mp_desc, int M, uint32_t desc_threshold, int32_t* out_idx, int32_t* out_dist) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n < 0 || M < 0 || (n > 0 && (!kps || !desc)) || (M > 0 && (!uvr || !mp_desc || !out_idx || !out_dist)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (M == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nn = (size_t)std::max(n, 1), mm = (size_t)M;
+  int rc = arena_begin(h, pad256(nn * 28) + pad256(nn * 32) + pad256(mm * 24) + pad256(mm * 32) + 2 * pad256(mm * 4));
+  if (rc) return rc;
+  unsigned char* dk = arena_take<unsigned char>(h, nn * 28);
+  unsigned* dd = arena_take<unsigned>(h, nn * 8);
+  double* dq = arena_take<double>(h, mm * 3);
+  unsigned* dmd = arena_take<unsigned>(h, mm * 8);
+  int* doi = arena_take<int>(h, mm);
+  int* dod = arena_take<int>(h, mm);
+  if (n > 0) {
+    CU_TRY(h, cudaMemcpyAsync(dk, kps, (size_t)n * 28, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  }
+  CU_TRY(h, cudaMemcpyAsync(dq, uvr, mm * 24, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(dmd, mp_desc, mm * 32, cudaMemcpyHostToDevice, st));
+  vk::k_fuse_search<<<(M * 32 + 255) / 256, 256, 0, st>>>(dk, dd, n, dq, dmd, M, desc_threshold, doi, dod);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(out_idx, doi, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out_dist, dod, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
+int vslam_distinctive_descriptors(vslam_handle h, const uint8_t* desc, const int32_t* offsets, int M, int32_t* out_idx) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (M < 0 || (M > 0 && (!offsets || !out_idx))) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (M == 0) return VSLAM_OK;
+  const int total = offsets[M];
+  if (offsets[0] != 0 || total < 0 || (total > 0 && !desc)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad offsets");
+  for (int m = 0; m < M; ++m)
+    if (offsets[m + 1] < offsets[m]) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t tt = (size_t)std::max(total, 1), mm = (size_t)M;
+  int rc = arena_begin(h, pad256(tt * 32) + pad256((mm + 1) * 4) + pad256(mm * 4));
+  if (rc) return rc;
+  unsigned* dd = arena_take<unsigned>(h, tt * 8);
+  int* dof = arena_take<int>(h, mm + 1);
+  int* dout = arena_take<int>(h, mm);
+  if (total > 0) CU_TRY(h, cudaMemcpyAsync(dd, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(dof, offsets, (mm + 1) * 4, cudaMemcpyHostToDevice, st));
+  vk::k_distinctive<<<(M * 32 + 255) / 256, 256, 0, st>>>(dd, dof, M, dout);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(out_idx, dout, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
 }  // extern "C"

@@ -3,6 +3,8 @@
 //   k_grid_count/fill   FeatureGrid::get_features_in_area   tracking_frame.rs:104-128
 //   k_search            the two projection searches in Tracker   src/tracking/tracker.rs:863-923, 1093-1158
 //   k_nearest/k_cross   BFMatcher(NORM_HAMMING, crossCheck=true) src/tracking/tracker.rs:1001-1010
+//   k_fuse_search       fusion search of local mapping          src/local_mapping/search_in_neighbors.rs:303-340
+//   k_distinctive       Map::compute_distinctive_descriptors    src/atlas/map/map.rs:917-937
 //
 // Rust cast semantics reproduced explicitly: f64 -> usize / i32 `as` saturates (NaN -> 0); i32 -> usize `as`
 // sign-extends, so a negative max cell clamps to the LAST column/row (SURVEY.md §8.C trap 6).
@@ -329,6 +331,76 @@ __global__ void __launch_bounds__(256) k_cross(const int* __restrict__ sidx, con
     __syncthreads();
   }
   if (tid == 0) *n_out = s_base;
+}
+
+// Fusion search: one warp per query, lanes stride over ALL keyframe keypoints (the reference's linear scan).
+// kps: cv::KeyPoint records (28 B); desc [n][32]; uvr [M][3] f64 (u, v, radius).
+__global__ void __launch_bounds__(256) k_fuse_search(const unsigned char* __restrict__ kps,
+                                                     const unsigned* __restrict__ desc, int n,
+                                                     const double* __restrict__ uvr, const unsigned* __restrict__ mp_desc,
+                                                     int M, unsigned desc_threshold, int* __restrict__ out_idx,
+                                                     int* __restrict__ out_dist) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= M) return;
+  const double u = uvr[3 * q], v = uvr[3 * q + 1], radius = uvr[3 * q + 2];
+  const double radius_sq = __dmul_rn(radius, radius);
+  unsigned md[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) md[k] = mp_desc[(size_t)q * 8 + k];
+  unsigned long long best = ~0ull;  // (dist << 32) | index: first minimum == smallest key
+  for (int i = lane; i < n; i += 32) {
+    const float* k = reinterpret_cast<const float*>(kps + (size_t)i * 28);
+    const double du = __dsub_rn((double)k[0], u), dv = __dsub_rn((double)k[1], v);
+    const double dist_sq = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
+    if (!(dist_sq <= radius_sq)) continue;
+    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)i * 8);
+    const uint4 a = dp[0], b = dp[1];
+    const unsigned d = __popc(md[0] ^ a.x) + __popc(md[1] ^ a.y) + __popc(md[2] ^ a.z) + __popc(md[3] ^ a.w) +
+                       __popc(md[4] ^ b.x) + __popc(md[5] ^ b.y) + __popc(md[6] ^ b.z) + __popc(md[7] ^ b.w);
+    if (d >= desc_threshold) continue;
+    const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)i;
+    best = key < best ? key : best;
+  }
+  const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+  const unsigned dmin = __reduce_min_sync(VSLAM_FULL, hi);
+  const unsigned imin = __reduce_min_sync(VSLAM_FULL, hi == dmin ? lo : 0xffffffffu);
+  if (lane == 0) {
+    const bool found = dmin != 0xffffffffu;
+    out_idx[q] = found ? (int)imin : -1;
+    out_dist[q] = found ? (int)dmin : -1;
+  }
+}
+
+// Distinctive descriptor: one warp per map point; for each i the lanes take max_j d(i, j), lane 0 keeps the first
+// minimum of those maxima.
+__global__ void __launch_bounds__(256) k_distinctive(const unsigned* __restrict__ desc, const int* __restrict__ offsets,
+                                                     int M, int* __restrict__ out_idx) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int b = offsets[m], k = offsets[m + 1] - b;
+  int best_idx = k <= 0 ? -1 : 0;
+  if (k > 1) {
+    unsigned best_max = 0xffffffffu;
+    for (int i = 0; i < k; ++i) {
+      const uint4* pi = reinterpret_cast<const uint4*>(desc + (size_t)(b + i) * 8);
+      const uint4 a0 = pi[0], a1 = pi[1];
+      unsigned mx = 0;
+      for (int j = lane; j < k; j += 32) {
+        if (j == i) continue;
+        const uint4* pj = reinterpret_cast<const uint4*>(desc + (size_t)(b + j) * 8);
+        const uint4 c0 = pj[0], c1 = pj[1];
+        const unsigned d = __popc(a0.x ^ c0.x) + __popc(a0.y ^ c0.y) + __popc(a0.z ^ c0.z) + __popc(a0.w ^ c0.w) +
+                           __popc(a1.x ^ c1.x) + __popc(a1.y ^ c1.y) + __popc(a1.z ^ c1.z) + __popc(a1.w ^ c1.w);
+        mx = max(mx, d);
+      }
+      mx = __reduce_max_sync(VSLAM_FULL, mx);
+      if (mx < best_max) {
+        best_max = mx;
+        best_idx = i;
+      }
+    }
+  }
+  if (lane == 0) out_idx[m] = best_idx;
 }
 
 }  // namespace vk

@@ -320,6 +320,33 @@ class StereoProcessor:
             self._raise(rc)
         return m[: n.value].copy()
 
+    # -- keyframe-rate consumers
+    def fuse_search(self, features: FeatureSet, uvr, mp_desc, desc_threshold=TH_LOW):
+        """Descriptor search of fuse_points_into_keyframes (search_in_neighbors.rs:303-340): uvr = (u, v, radius)."""
+        kp = np.ascontiguousarray(features.keypoints, dtype=KP_DTYPE)
+        d = np.ascontiguousarray(features.descriptors, dtype=np.uint8)
+        q = np.ascontiguousarray(uvr, dtype=np.float64).reshape(-1, 3)
+        md = np.ascontiguousarray(mp_desc, dtype=np.uint8).reshape(-1, 32)
+        M = len(q)
+        idx = np.full(max(M, 1), -1, dtype=np.int32)
+        dist = np.full(max(M, 1), -1, dtype=np.int32)
+        rc = self._lib.vslam_fuse_search(self._h, _ptr(kp), _ptr(d), len(kp), _ptr(q), _ptr(md), M, int(desc_threshold),
+                                         _ptr(idx), _ptr(dist))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return idx[:M], dist[:M]
+
+    def distinctive_descriptors(self, desc, offsets):
+        """Map::compute_distinctive_descriptors (map.rs:917-937) for many map points at once (CSR groups)."""
+        d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        M = len(off) - 1
+        out = np.full(max(M, 1), -1, dtype=np.int32)
+        rc = self._lib.vslam_distinctive_descriptors(self._h, _ptr(d), _ptr(off), M, _ptr(out))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return out[:M]
+
     # -- introspection (parity tests / profiling)
     def level_info(self, level):
         w, h, s, n = C.c_int(), C.c_int(), C.c_float(), C.c_int()

@@ -392,3 +392,44 @@ def test_large_batch_properties(oracle, camera_dict):
     lh, rh = lb[:32].cpu().numpy(), rb[:32].cpu().numpy()
     for i in (0, 7, 31):
         check_frame(frs[i], oracle.detect_and_compute(lh[i], 1200), oracle.detect_and_compute(rh[i], 1200), oracle, camera_dict)
+
+
+# ------------------------------------------------------------------ keyframe-rate consumers
+def test_fuse_search(sp752, oracle, pairs):
+    from vslam_b200 import FeatureSet
+
+    kl, dl = oracle.detect_and_compute(pairs(2)[0], 1200)
+    rng = np.random.default_rng(21)
+    M = 2500
+    src = rng.integers(0, len(kl), M)
+    uvr = np.c_[kl["x"][src] + rng.normal(0, 8, M), kl["y"][src] + rng.normal(0, 8, M), rng.uniform(10.0, 50.0, M)]
+    uvr[:5, 2] = [0.0, 1e-9, 10.0, 50.0, 1e6]
+    md = dl[src].copy()
+    for i in range(M):
+        for b in rng.integers(0, 256, rng.integers(0, 40)):
+            md[i, b // 8] ^= 1 << (b % 8)
+    for thr in (50, 100):
+        gi, gd = sp752.fuse_search(FeatureSet(kl, dl), uvr, md, thr)
+        oi, od = oracle.fuse_search(kl, dl, uvr, md, thr)
+        assert (oi >= 0).sum() > 300
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    gi, _ = sp752.fuse_search(FeatureSet(kl[:0], dl[:0]), uvr[:3], md[:3])
+    assert list(gi) == [-1, -1, -1]
+
+
+def test_distinctive_descriptors(sp752, oracle, pairs):
+    _, dl = oracle.detect_and_compute(pairs(2)[0], 1200)
+    rng = np.random.default_rng(22)
+    groups, offsets = [], [0]
+    for m in range(600):
+        k = int(rng.choice([0, 1, 2, 3, 5, 8, 13, 40, 70]))
+        base = dl[rng.integers(0, len(dl))]
+        g = np.tile(base, (k, 1))
+        for i in range(k):
+            for b in rng.integers(0, 256, rng.integers(0, 30)):
+                g[i, b // 8] ^= 1 << (b % 8)
+        groups.append(g)
+        offsets.append(offsets[-1] + k)
+    desc = np.concatenate(groups)
+    off = np.array(offsets, np.int32)
+    assert np.array_equal(sp752.distinctive_descriptors(desc, off), oracle.distinctive_descriptors(desc, off))

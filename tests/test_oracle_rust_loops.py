@@ -98,3 +98,27 @@ def test_search_modes(oracle):
     assert list(idx) == [0, -1, 2] and dist[0] == 4 and dist[2] == 0
     idx1, _ = oracle.search_by_projection(k, d, uv, md, 1, bound_w=734.43, bound_h=496.75)
     assert list(idx1) == [0, -1, -1]  # u<0 is rejected by the motion-model bounds check
+
+
+def test_fuse_search_true_disc_and_threshold(oracle):
+    # keyframe.rs:436-443: candidates are inside the TRUE disc (unlike FeatureGrid's whole cells); d < threshold, first min
+    k = kps([(100.0, 100.0), (110.0, 100.0), (100.0, 110.5), (100.0, 100.0)])
+    d = np.stack([desc_with_bits(10), desc_with_bits(4), desc_with_bits(0), desc_with_bits(10)])
+    md = np.stack([desc_with_bits(0)] * 3)
+    uvr = np.array([[100.0, 100.0, 10.0], [100.0, 100.0, 10.6], [500.0, 100.0, 10.0]])
+    idx, dist = oracle.fuse_search(k, d, uvr, md, 50)
+    assert list(idx) == [1, 2, -1] and list(dist) == [4, 0, -1]  # (110,100) is exactly on the r=10 circle: included
+    idx, _ = oracle.fuse_search(k, d, uvr[:1], md[:1], 4)          # strict d < threshold
+    assert list(idx) == [-1]
+    idx, _ = oracle.fuse_search(k[[0, 3]], d[[0, 3]], uvr[:1], md[:1], 50)  # tie: first index wins
+    assert list(idx) == [0]
+
+
+def test_distinctive_descriptor_minmax_first_wins(oracle):
+    a, b, c = desc_with_bits(0), desc_with_bits(10), desc_with_bits(20)
+    desc = np.stack([a, c, b, b, a])  # group 0: [a, c, b] -> b has max dist 10 (a: 20, c: 20); group 1: [b]; group 3: [a, a]? see offsets
+    offsets = np.array([0, 3, 4, 4, 5], np.int32)
+    out = oracle.distinctive_descriptors(desc, offsets)
+    assert list(out) == [2, 0, -1, 0]
+    # all equal maxima -> first index
+    assert list(oracle.distinctive_descriptors(np.stack([a, b]), np.array([0, 2], np.int32))) == [0]
