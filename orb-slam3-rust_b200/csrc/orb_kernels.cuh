@@ -82,11 +82,15 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ PyrP P, 
   const int sy1 = min((int)(yc[y0 + rows - 1] & 0xffffu) + 1, S.h - 1);
   const int nrows = sy1 - sy0 + 1;
   const int vpr = spitch >> 4;
-  for (int i = threadIdx.x; i < nrows * vpr; i += 256) {
-    int r = i / vpr, c = i - r * vpr;
-    reinterpret_cast<uint4*>(smem)[i] = *reinterpret_cast<const uint4*>(src + (size_t)(sy0 + r) * spitch + 16 * c);
+  for (int r = threadIdx.x >> 5; r < nrows; r += 8) {
+    const uint4* srow = reinterpret_cast<const uint4*>(src + (size_t)(sy0 + r) * spitch);
+    uint4* drow = reinterpret_cast<uint4*>(smem + r * spitch);
+    for (int c = threadIdx.x & 31; c < vpr; c += 32) drow[c] = srow[c];
   }
   __syncthreads();
+  // Each thread owns 4 destination columns and walks down the strip's rows.  (Re-using the horizontal interpolation
+  // of a shared source row between consecutive destination rows was measured slower: the loop-carried registers and
+  // the extra branches cost more than the saved multiplies.)
   const int ngroups = D.pitch >> 2;
   for (int g = threadIdx.x; g < ngroups; g += 256) {
     int ox[4], ox1[4];

@@ -261,7 +261,7 @@ int build_params(vslam_handle h) {
       int sy1 = std::min((int)(yc[y0 + rows - 1] & 0xffffu) + 1, Sx.h - 1);
       max_rows = std::max(max_rows, sy1 - sy0 + 1);
     }
-    h->resize_smem[l] = (size_t)max_rows * Sx.pitch;
+    h->resize_smem[l] = (size_t)max_rows * Sx.pitch + 16;  // + spare bytes: the kernel reads p[ox + 1] unconditionally
   }
   h->fast_smem = vk::fast_smem_bytes(P.in_pitch);
   // selection scratch in shared memory: select1 sized for ~3% corner density on the largest level (typical < 2%),
@@ -393,7 +393,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   mark();  // 0
   for (int l = 1; l < P.nlevels; ++l) {
     dim3 grid((P.lv[l].h + VSLAM_RESIZE_ROWS - 1) / VSLAM_RESIZE_ROWS, nimg);
-    size_t smem = l == 1 ? (h->resize_smem[l] / (size_t)h->P.lv[0].pitch) * (size_t)pitch : h->resize_smem[l];
+    size_t smem = l == 1 ? ((h->resize_smem[l] - 16) / (size_t)h->P.lv[0].pitch) * (size_t)pitch + 16 : h->resize_smem[l];
     vk::k_resize<<<grid, 256, smem, st>>>(P, l, in_l, in_r, s.d_pyr, h->d_coef);
     h->launches++;
   }
