@@ -245,8 +245,6 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   while (true) {
     if (qn >= 32 || (it0 >= nitems && qn > 0)) {
       // ---- phase B: exact score of up to 32 queued pairs, one pair per lane
-      bool c_lo = false, c_hi = false;
-      unsigned c_code = 0;
       if (lane < qn) {
         const unsigned code = q[(qhead + lane) & 127];
         const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
@@ -288,23 +286,19 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
         if (x < sx0 || x >= sx1) out16 &= 0xff00u;                // pixels outside the scored columns stay 0
         if (x + 1 < sx0 || x + 1 >= sx1) out16 &= 0x00ffu;
         *reinterpret_cast<unsigned short*>(sc0 + ry * SP + x) = (unsigned short)out16;
-        // remember non-zero scores inside the emission region for the sparse NMS pass
+        // remember non-zero scores inside the emission region for the sparse NMS pass (a few per warp call; ptxas
+        // aggregates the same-address shared atomics of a warp)
         const int y = sy_lo + ry;
-        const bool rowin = y >= ys && y < ye;
-        c_lo = rowin && (out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1;
-        c_hi = rowin && (out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1;
-        c_code = ((unsigned)(y - ys) << 12) | (unsigned)x;
-      }
-      {
-        const unsigned blo = __ballot_sync(VSLAM_FULL, c_lo), bhi = __ballot_sync(VSLAM_FULL, c_hi);
-        const int nadd = __popc(blo) + __popc(bhi);
-        if (nadd) {
-          int basep = 0;
-          if (lane == 0) basep = atomicAdd(&s_cn, nadd);
-          basep = __shfl_sync(VSLAM_FULL, basep, 0);
-          const int plo = basep + __popc(blo & lt), phi = basep + __popc(blo) + __popc(bhi & lt);
-          if (c_lo && plo < kCornerList) s_clist[plo] = c_code;
-          if (c_hi && phi < kCornerList) s_clist[phi] = c_code + 1u;
+        if (y >= ys && y < ye) {
+          const unsigned ccode = ((unsigned)(y - ys) << 12) | (unsigned)x;
+          if ((out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1) {
+            const int pos = atomicAdd(&s_cn, 1);
+            if (pos < kCornerList) s_clist[pos] = ccode;
+          }
+          if ((out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1) {
+            const int pos = atomicAdd(&s_cn, 1);
+            if (pos < kCornerList) s_clist[pos] = ccode + 1u;
+          }
         }
       }
       const int done = min(qn, 32);

@@ -392,6 +392,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   CU_TRY(h, cudaMemsetAsync(s.d_lay.hdr, 0, sizeof(ResHdr) * (size_t)frames, st));
   mark();  // 0
   for (int l = 1; l < P.nlevels; ++l) {
+    // (a variant without shared-memory staging, four __ldg taps per pixel, measured 1.7x slower: 9.9 vs 5.8 ms/step)
     dim3 grid((P.lv[l].h + VSLAM_RESIZE_ROWS - 1) / VSLAM_RESIZE_ROWS, nimg);
     size_t smem = l == 1 ? ((h->resize_smem[l] - 16) / (size_t)h->P.lv[0].pitch) * (size_t)pitch + 16 : h->resize_smem[l];
     vk::k_resize<<<grid, 256, smem, st>>>(P, l, in_l, in_r, s.d_pyr, h->d_coef);
