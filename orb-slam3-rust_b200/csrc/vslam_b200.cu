@@ -5,8 +5,8 @@
 // match_features}, triangulate, descriptor_distance) and the tracking-side searches
 // (src/tracking/tracking_frame.rs:52-128, src/tracking/tracker.rs:863-923, 1001-1010, 1093-1158).
 //
-// Design: a handle owns NSLOT pipeline slots, each with its own CUDA stream, device scratch for `max_batch`
-// stereo frames and pinned host staging.  A batch is cut into chunks; chunk c runs on slot c % NSLOT so the
+// Design: a handle owns `nslot` (default 4) pipeline slots, each with its own CUDA stream, device scratch for `max_batch`
+// stereo frames and pinned host staging.  A batch is cut into chunks; chunk c runs on slot c % nslot so the
 // H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c.  Every kernel takes the
 // whole chunk (grid.y = images), so launch latency is amortised over the chunk.  No CPU fallback anywhere.
 #include <cuda_runtime.h>
@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int NSLOT = 3;
+constexpr int MAX_SLOTS = 6;
 thread_local std::string g_create_error;
 
 inline int cv_roundf(float v) { return (int)nearbyintf(v); }
@@ -84,7 +84,8 @@ struct vslam_handle_s {
   int harris_blocks = 1;
   size_t match_rows_smem = 0;  // 0: fall back to k_match + k_match_finalize
   size_t in_img_bytes = 0;
-  Slot slots[NSLOT];
+  Slot slots[MAX_SLOTS];
+  int nslot = 4;  // pipeline slots in use (VSLAM_SLOTS overrides, 2..6)
   std::string err;
   uint64_t launches = 0;
   bool profiling = false;
@@ -268,7 +269,12 @@ int build_params(vslam_handle h) {
   // select2 for 2N_l plus ties; anything larger is replayed in global memory.
   {
     long long epx0 = (long long)(P.lv[0].ex1 - P.lv[0].ex0) * (P.lv[0].ey1 - P.lv[0].ey0);
-    h->sel1_cap = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 24000) & ~7;
+    // Capped at 4096 records (32 KB): k_select1 is latency-bound (one warp per problem), so what matters is that its
+    // blocks leave shared memory free for the dense kernels of the other pipeline slots to co-reside; measured
+    // +6 % frames/s against a 9000-record (72 KB) budget even though the largest problems then replay in global memory.
+    h->sel1_cap = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 4096) & ~7;
+    if (const char* ev = getenv("VSLAM_SEL1_CAP")) h->sel1_cap = std::max(256, atoi(ev)) & ~7;  // tuning knob
+
     int max2n = 0;
     for (int l = 0; l < P.nlevels; ++l) max2n = std::max(max2n, 2 * P.lv[l].nfeat);
     h->sel2_cap = std::min((max2n + max2n / 4 + 64 + 7) & ~7, 16000);
@@ -563,7 +569,7 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
   CU_TRY(h, cudaEventRecord(h->ev_batch[0], h->slots[0].stream));
   for (int f0 = 0; f0 < n; f0 += h->max_batch, ++chunk) {
     const int frames = std::min(h->max_batch, n - f0);
-    Slot& s = h->slots[chunk % NSLOT];
+    Slot& s = h->slots[chunk % h->nslot];
     int rc = retire_slot(h, s, outs, ts, &first_error);
     if (rc != VSLAM_OK) return rc;
     const uint8_t *in_l, *in_r;
@@ -638,16 +644,16 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
     s.busy = true;
     s.frames = frames;
     s.first_frame = f0;
-    h->last_slot = chunk % NSLOT;
+    h->last_slot = chunk % h->nslot;
     h->last_frames = frames;
   }
   // join every slot's stream into slot 0's and close the device-time bracket of this batch
-  for (int k = 1; k < NSLOT; ++k)
+  for (int k = 1; k < h->nslot; ++k)
     if (h->slots[k].busy) CU_TRY(h, cudaStreamWaitEvent(h->slots[0].stream, h->slots[k].done, 0));
   CU_TRY(h, cudaEventRecord(h->ev_batch[1], h->slots[0].stream));
   // drain in submission order
-  for (int k = 0; k < NSLOT; ++k) {
-    Slot& s = h->slots[(chunk + k) % NSLOT];
+  for (int k = 0; k < h->nslot; ++k) {
+    Slot& s = h->slots[(chunk + k) % h->nslot];
     int rc = retire_slot(h, s, outs, ts, &first_error);
     if (rc != VSLAM_OK) return rc;
   }
@@ -778,7 +784,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
         cur[i] = want[i];
       }
   }
-  for (int k = 0; k < NSLOT; ++k) {
+  if (const char* ev = getenv("VSLAM_SLOTS")) h->nslot = std::min(std::max(atoi(ev), 2), MAX_SLOTS);
+  for (int k = 0; k < h->nslot; ++k) {
     rc = alloc_slot(h, h->slots[k]);
     if (rc != VSLAM_OK) return bail(rc == VSLAM_ERR_CUDA ? VSLAM_ERR_OUT_OF_MEMORY : rc);
   }
@@ -794,7 +801,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
 void vslam_destroy(vslam_handle h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  for (int k = 0; k < NSLOT; ++k) free_slot(h->slots[k]);
+  for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
   cudaFree(h->d_coef);
   cudaFree(h->arena_base);
   for (int i = 0; i < 8; ++i)
