@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   const unsigned tadd = (127u - t) * 0x01010101u;  // fast_threshold <= 127 (checked by vslam_create)
   const unsigned lt = (1u << lane) - 1u;
   constexpr int kCornerList = 2048;  // pre-NMS corners of a strip kept for the sparse NMS pass (else: full scan)
-  __shared__ unsigned s_clist[kCornerList];
+  __shared__ unsigned short s_clist[kCornerList];  // (emission row << 12) | x   (row < 16, x < 4096)
   __shared__ unsigned short s_queue[8][128];  // per-warp ring of queued pairs: (score row << 11) | (group << 1) | half
   unsigned short* q = s_queue[warp];
   int qn = 0, qhead = 0;  // warp-uniform
@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
           const unsigned ccode = ((unsigned)(y - ys) << 12) | (unsigned)x;
           if ((out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1) {
             const int pos = atomicAdd(&s_cn, 1);
-            if (pos < kCornerList) s_clist[pos] = ccode;
+            if (pos < kCornerList) s_clist[pos] = (unsigned short)ccode;
           }
           if ((out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1) {
             const int pos = atomicAdd(&s_cn, 1);
-            if (pos < kCornerList) s_clist[pos] = ccode + 1u;
+            if (pos < kCornerList) s_clist[pos] = (unsigned short)(ccode + 1u);
           }
         }
       }
