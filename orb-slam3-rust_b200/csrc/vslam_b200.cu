@@ -80,7 +80,7 @@ struct vslam_handle_s {
   uint32_t* d_coef = nullptr;
   size_t resize_smem[VSLAM_MAX_LEVELS] = {0};
   size_t fast_smem = 0;
-  int sel1_cap = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
+  int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   int harris_blocks = 1;
   size_t match_rows_smem = 0;  // 0: fall back to k_match + k_match_finalize
   size_t in_img_bytes = 0;
@@ -269,12 +269,14 @@ int build_params(vslam_handle h) {
   // select2 for 2N_l plus ties; anything larger is replayed in global memory.
   {
     long long epx0 = (long long)(P.lv[0].ex1 - P.lv[0].ex0) * (P.lv[0].ey1 - P.lv[0].ey0);
-    // Capped at 4096 records (32 KB): k_select1 is latency-bound (one warp per problem), so what matters is that its
-    // blocks leave shared memory free for the dense kernels of the other pipeline slots to co-reside; measured
-    // +6 % frames/s against a 9000-record (72 KB) budget even though the largest problems then replay in global memory.
-    h->sel1_cap = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 4096) & ~7;
+    // Two budgets for k_select1's records in shared memory.  Large chunks: 4096 records (32 KB) — the kernel is
+    // latency-bound (one warp per problem), so what matters is that its blocks leave shared memory free for the dense
+    // kernels of the other pipeline slots to co-reside (measured +6 % frames/s against a 72 KB budget even though the
+    // largest problems then replay in global memory).  Small chunks (single pairs): ~3 % corner density of level 0, so
+    // that every problem replays in shared memory (single-pair latency 0.29 ms instead of 0.40 ms).
+    h->sel1_cap_latency = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 24000) & ~7;
+    h->sel1_cap = std::min(h->sel1_cap_latency, 4096);
     if (const char* ev = getenv("VSLAM_SEL1_CAP")) h->sel1_cap = std::max(256, atoi(ev)) & ~7;  // tuning knob
-
     int max2n = 0;
     for (int l = 0; l < P.nlevels; ++l) max2n = std::max(max2n, 2 * P.lv[l].nfeat);
     h->sel2_cap = std::min((max2n + max2n / 4 + 64 + 7) & ~7, 16000);
@@ -425,8 +427,9 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 2
   {
-    vk::k_select1<<<dim3(nimg, P.nlevels), 128, vk::select1_smem_bytes(h->sel1_cap), st>>>(
-        P, h->sel1_cap, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
+    const int cap1 = nimg >= 32 ? h->sel1_cap : std::max(h->sel1_cap, h->sel1_cap_latency);
+    vk::k_select1<<<dim3(nimg, P.nlevels), 128, vk::select1_smem_bytes(cap1), st>>>(
+        P, cap1, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
     vk::k_harris<<<dim3(h->harris_blocks, P.nlevels, nimg), 128, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_sel1, s.d_sel1_cnt,
                                                                        s.d_cand, h->harris_scale4);
     vk::k_select2<<<dim3(nimg, P.nlevels), 32, vk::select2_smem_bytes(h->sel2_cap), st>>>(
@@ -751,7 +754,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   // opt in to large dynamic shared memory where needed
   size_t max_resize = 0;
   for (int l = 1; l < h->P.nlevels; ++l) max_resize = std::max(max_resize, h->resize_smem[l]);
-  const size_t max_sel = std::max(vk::select1_smem_bytes(h->sel1_cap), vk::select2_smem_bytes(h->sel2_cap));
+  const size_t max_sel1 = vk::select1_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency));
+  const size_t max_sel = std::max(max_sel1, vk::select2_smem_bytes(h->sel2_cap));
   const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
   if (h->fast_smem > lim || max_resize > lim || max_sel > lim) {
     fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image too wide for the shared-memory tiles (%zu/%zu/%zu > %zu bytes)",
@@ -770,7 +774,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
       const size_t need = vk::match_rows_smem_bytes(h->kp_cap, c.height);
       h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
     }
-    const size_t want[5] = {h->fast_smem, std::max<size_t>(max_resize, 1024), vk::select1_smem_bytes(h->sel1_cap),
+    const size_t want[5] = {h->fast_smem, std::max<size_t>(max_resize, 1024), max_sel1,
                             vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
     const void* fn[5] = {(const void*)vk::k_fast, (const void*)vk::k_resize, (const void*)vk::k_select1,
                          (const void*)vk::k_select2, (const void*)vk::k_match_rows};
