@@ -25,17 +25,18 @@ namespace vk {
 
 #define VSLAM_FULL 0xffffffffu
 
-// Global (not __constant__) memory: every lane reads a different test, which the constant cache would serialise.
-// Stored as float (|coordinate| <= 13 is exact): the steering multiplies them by cos/sin in f32.
-__device__ float g_brief_pattern[1024] = {
-#include "brief_pattern.inc"
-};
+// rBRIEF pattern in global (not __constant__) memory: every lane reads a different test, which the constant cache would
+// serialise.  Stored as float (|coordinate| <= 13 is exact) and TRANSPOSED for coalescing: lane b evaluates tests
+// 8b .. 8b+7, so g_brief_pattern_t[q][b] = test 8b + q = (x0, y0, x1, y1); one LDG.128 per q then touches 4 cache lines
+// instead of 32.  Filled by the host at handle creation (upload_tables in vslam_b200.cu) from brief_pattern.inc.
+__device__ float4 g_brief_pattern_t[8][32];
 
-// Orientation tables (filled by the host at handle creation, see upload_angle_tables in vslam_b200.cu):
-//   g_angle_mask[o][r][j]  byte b = 0xff iff pixel u = 4j + b - (15 + o) of patch row r lies inside the 31-px disc
+// Orientation tables (filled by the host at handle creation, see upload_tables in vslam_b200.cu):
+//   g_angle_mask[o][j][r]  byte b = 0xff iff pixel u = 4j + b - (15 + o) of patch row r lies inside the 31-px disc
+//                          (row index innermost: lane r reads consecutive words -> one cache line per load)
 //   g_angle_u[o][j]        byte b = (int8) u
 // o = (cx - 15) & 3 is the alignment of the staged patch; with them a patch row is reduced by 9 x 2 dp4a.
-__device__ unsigned g_angle_mask[4][31][9];
+__device__ unsigned g_angle_mask[4][9][32];
 __device__ unsigned g_angle_u[4][9];
 
 __device__ __forceinline__ int dp4a_u8_s8(unsigned a, unsigned b, int c) {
@@ -1015,13 +1016,12 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   int m10 = 0, m01 = 0;
   if (lane < kAngleRows) {
     const int o = (cx - kAngleR) & 3;
-    const unsigned* mrow = g_angle_mask[o][lane];
     const unsigned* urow = g_angle_u[o];
     const unsigned* prow = sa + lane * kAngleRowWords;
     int sum = 0, su = 0;
 #pragma unroll
     for (int j = 0; j < kAngleRowWords; ++j) {
-      const unsigned wv = prow[j] & mrow[j];
+      const unsigned wv = prow[j] & g_angle_mask[o][j][lane];
       sum = dp4a_u8_s8(wv, 0x01010101u, sum);
       su = dp4a_u8_s8(wv, urow[j], su);
     }
@@ -1052,13 +1052,13 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   float a, b;
   sincos_f64_to_f32(rad, a, b);
   const uint8_t* center = reinterpret_cast<const uint8_t*>(sb) + kBriefR * (kBriefRowWords * 4) + (cx - xb0);
-  const float4* pat = reinterpret_cast<const float4*>(g_brief_pattern) + 8 * lane;  // 32 values = 16 points per lane
+
   // cvRound of a value in (-32, 32): adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits
   auto rnd = [](float v) -> int { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; };
   unsigned byte = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 t = pat[q];  // one test: (x0,y0,x1,y1)
+    const float4 t = g_brief_pattern_t[q][lane];  // test 8*lane + q: (x0,y0,x1,y1)
     const int ix0 = rnd(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
     const int iy0 = rnd(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
     const int ix1 = rnd(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));

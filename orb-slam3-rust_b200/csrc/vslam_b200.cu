@@ -145,28 +145,36 @@ void linear_exact_coeffs(int src, int dst, uint32_t* out) {
   }
 }
 
-// Orientation tables of k_brief (see orb_kernels.cuh): disc masks and packed int8 column offsets per patch alignment.
-int upload_angle_tables(vslam_handle h) {
+// Tables of k_brief (see orb_kernels.cuh): transposed float rBRIEF pattern, disc masks and packed int8 column offsets.
+int upload_tables(vslam_handle h) {
+  static const int pattern[1024] = {
+#include "brief_pattern.inc"
+  };
   static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-  static unsigned mask[4][31][9], uu[4][9];
+  static float pat_t[8][32][4];
+  static unsigned mask[4][9][32], uu[4][9];
+  for (int b = 0; b < 32; ++b)
+    for (int q = 0; q < 8; ++q)
+      for (int c = 0; c < 4; ++c) pat_t[q][b][c] = (float)pattern[4 * (8 * b + q) + c];
   for (int o = 0; o < 4; ++o) {
     for (int j = 0; j < 9; ++j) {
       unsigned w = 0;
       for (int b = 0; b < 4; ++b) w |= (unsigned)(uint8_t)(int8_t)(4 * j + b - (15 + o)) << (8 * b);
       uu[o][j] = w;
-    }
-    for (int r = 0; r < 31; ++r) {
-      const int d = umax[r < 15 ? 15 - r : r - 15];
-      for (int j = 0; j < 9; ++j) {
-        unsigned w = 0;
-        for (int b = 0; b < 4; ++b) {
-          const int u = 4 * j + b - (15 + o);
-          if (u >= -d && u <= d) w |= 0xffu << (8 * b);
+      for (int r = 0; r < 32; ++r) {
+        unsigned m = 0;
+        if (r < 31) {
+          const int d = umax[r < 15 ? 15 - r : r - 15];
+          for (int b = 0; b < 4; ++b) {
+            const int u = 4 * j + b - (15 + o);
+            if (u >= -d && u <= d) m |= 0xffu << (8 * b);
+          }
         }
-        mask[o][r][j] = w;
+        mask[o][j][r] = m;
       }
     }
   }
+  CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_t, pat_t, sizeof(pat_t)));
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_mask, mask, sizeof(mask)));
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_u, uu, sizeof(uu)));
   return VSLAM_OK;
@@ -747,7 +755,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     fail(h, VSLAM_ERR_CUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return bail(VSLAM_ERR_CUDA);
   }
-  if (upload_angle_tables(h) != VSLAM_OK) return bail(VSLAM_ERR_CUDA);
+  if (upload_tables(h) != VSLAM_OK) return bail(VSLAM_ERR_CUDA);
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   cudaEventCreate(&h->ev_batch[0]);
   cudaEventCreate(&h->ev_batch[1]);
