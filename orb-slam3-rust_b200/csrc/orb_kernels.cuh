@@ -89,33 +89,62 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ PyrP P, 
     for (int c = threadIdx.x & 31; c < vpr; c += 32) drow[c] = srow[c];
   }
   __syncthreads();
-  // Each thread owns 4 destination columns and walks down the strip's rows.  (Re-using the horizontal interpolation
-  // of a shared source row between consecutive destination rows was measured slower: the loop-carried registers and
-  // the extra branches cost more than the saved multiplies.)
+  // Each thread owns 4 destination columns and walks down the strip's rows.  The kernel is bound by shared-memory
+  // wavefronts, not by issue slots, so the taps are fetched as aligned words: the (at most 8) source bytes the four
+  // pixels need start at ox[0]; three LDS.32 + two funnel shifts bring them to bytes 0..7 of (v0, v1), a per-thread
+  // PRMT selector picks each pixel's (p[ox], p[ox+1]) pair and DP2A forms alpha0*p0 + alpha1*p1 in one instruction
+  // (16 byte loads per row pair -> 6 word loads).  Threads whose window is wider than 8 bytes (scale factors near 2)
+  // use byte loads.
   const int ngroups = D.pitch >> 2;
   for (int g = threadIdx.x; g < ngroups; g += 256) {
-    int ox[4], ox1[4];
-    unsigned a1[4];
+    int ox[4];
+    unsigned a01[4];  // alpha0 | alpha1 << 16
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      unsigned c = xc[min(4 * g + k, D.w - 1)];
+      const unsigned c = xc[min(4 * g + k, D.w - 1)];
       ox[k] = (int)(c & 0xffffu);
-      ox1[k] = min(ox[k] + 1, S.w - 1);
-      a1[k] = c >> 16;
+      const unsigned a1 = c >> 16;
+      a01[k] = (256u - a1) | (a1 << 16);
+    }
+    const bool wide = ox[3] + 1 - ox[0] > 7;
+    const int wbase = ox[0] & ~3;
+    const unsigned sh = 8u * (unsigned)(ox[0] & 3);
+    unsigned sel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned e = (unsigned)(ox[k] - ox[0]) & 7u;  // byte offset of p[ox[k]] inside (v0, v1)
+      sel[k] = e | (((e + 1u) & 7u) << 4) | 0x4400u;      // bytes 2,3 of the result are don't-care (DP2A.LO ignores them)
     }
     for (int r = 0; r < rows; ++r) {
-      unsigned yy = yc[y0 + r];
-      int o = (int)(yy & 0xffffu);
-      unsigned b1 = yy >> 16, b0 = 256u - b1;
+      const unsigned yy = yc[y0 + r];
+      const int o = (int)(yy & 0xffffu);
+      const unsigned b1 = yy >> 16, b0 = 256u - b1;
       const uint8_t* r0 = smem + (o - sy0) * spitch;
       const uint8_t* r1 = smem + (min(o + 1, S.h - 1) - sy0) * spitch;
+      unsigned h0[4], h1[4];
+      if (!wide) {
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(r0 + wbase);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(r1 + wbase);
+        const unsigned u0 = q0[0], u1 = q0[1], u2 = q0[2], t0 = q1[0], t1 = q1[1], t2 = q1[2];
+        const unsigned v00 = __funnelshift_r(u0, u1, sh), v01 = __funnelshift_r(u1, u2, sh);
+        const unsigned v10 = __funnelshift_r(t0, t1, sh), v11 = __funnelshift_r(t1, t2, sh);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h0[k] = __dp2a_lo(a01[k], __byte_perm(v00, v01, sel[k]), 0u);
+          h1[k] = __dp2a_lo(a01[k], __byte_perm(v10, v11, sel[k]), 0u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned a0 = a01[k] & 0xffffu, a1 = a01[k] >> 16;
+          h0[k] = a0 * r0[ox[k]] + a1 * r0[ox[k] + 1];
+          h1[k] = a0 * r1[ox[k]] + a1 * r1[ox[k] + 1];
+        }
+      }
       unsigned word = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        unsigned a0 = 256u - a1[k];
-        unsigned h0 = a0 * r0[ox[k]] + a1[k] * r0[ox1[k]];
-        unsigned h1 = a0 * r1[ox[k]] + a1[k] * r1[ox1[k]];
-        unsigned v = b0 * h0 + b1 * h1;
+        const unsigned v = b0 * h0[k] + b1 * h1[k];
         word |= ((v + 32768u) >> 16) << (8 * k);
       }
       *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * D.pitch + 4 * g) = word;
