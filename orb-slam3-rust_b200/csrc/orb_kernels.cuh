@@ -755,165 +755,177 @@ __global__ void __launch_bounds__(32) k_select2(const __grid_constant__ PyrP P, 
 // A5 — the blur cv::ORB applies to each level: separable 7-tap float32 Gaussian (sigma 2) as OpenCV's AVX2
 // sepFilter2D evaluates it: row pass s = k0*x0, s = fma(x_j, k_j, s); column pass s = k3*r3,
 // s = fma(r_{3+j} + r_{3-j}, k_{3+j}, s); BORDER_REFLECT_101; round-half-even to u8.
-// grid = (total_blur_tiles, n_img), block = 256, tile = 128 x 32.
+//
+// Register-resident sliding window, no shared memory, no barriers.  One LANE owns an 8-column x (<= 64)-row item of
+// one level and walks down its rows: per row it loads the 16 source bytes x-4 .. x+11 (four aligned words), converts
+// them to f32, evaluates the row pass for its 8 columns and pushes the result into a 7-row window held in registers;
+// the column pass of output row y-3 reads that window.  All float work is PACKED f32x2 (FFMA2 / FMUL2 / FADD2, two
+// IEEE-rounded operations per instruction): a pair is (column k, column k+4), k = 0..3, so the row-pass operands
+// (f[a], f[a+4]) and the column-pass operands stay aligned in the same 64-bit registers from conversion to store.
+// grid = (ceil(total_blur_items / 128), n_img), block = 128; a level's items are padded to a multiple of 32, so a
+// warp never spans two levels.  Items are numbered column-group fastest: adjacent lanes read adjacent 8-byte chunks.
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
   while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
   return i;
 }
-__device__ __forceinline__ float u8_to_f32(unsigned word, int byte) {
-  // exact: place the byte in the mantissa of 2^23 and subtract 2^23
-  unsigned sel = 0x7540u | (unsigned)byte;
-  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.0f);
+
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2_t pk2u(unsigned lo, unsigned hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2u(f32x2_t v, unsigned& lo, unsigned& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
-// Reflect-101 index for an offset of at most a few pixels outside [0, n) (n >= 16): closed form, no loop.
-__device__ __forceinline__ int reflect101_near(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
-
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+__global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
-  constexpr int TW = VSLAM_BLUR_TW, TH = VSLAM_BLUR_TH;
-  constexpr int NIT = (TH + 6 + 7) / 8;  // row-pass iterations per warp
-  __shared__ __align__(16) float s_row[(TH + 6) * TW];
-  const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
-  const int tile = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.y;
+  const int item = blockIdx.x * 128 + threadIdx.x;
   int l = 0;
   for (int k = 1; k < P.nlevels; ++k)
-    if (tile >= P.lv[k].blur_tile0) l = k;
+    if (item >= P.lv[k].blur_item0) l = k;  // warp-uniform
   const LevelP& L = P.lv[l];
-  const int tl = tile - L.blur_tile0;
-  const int ty = tl / L.blur_tx, tx = tl - ty * L.blur_tx;
-  const int x0 = tx * TW, y0 = ty * TH;
-  int pitch;
-  const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
-  uint8_t* dst = blur + (long long)img * P.blur_img_stride + L.blur_off;
+  const int li = item - L.blur_item0;
+  const int strip = li / L.blur_ncg, cg = li - strip * L.blur_ncg;
+  if (strip >= L.blur_nstr) return;  // padding lanes (no warp collectives below)
+  const int x = 8 * cg, y0 = strip * L.blur_rs;
+  const int rs = min(L.blur_rs, L.h - y0);  // output rows of this item
+  const int nblk = (L.blur_rs + 6) / 7;     // main-loop trips of 7 output rows (warp-uniform)
+  int spitch;
+  const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, spitch);
+  uint8_t* dst = blur + (long long)img * P.blur_img_stride + L.blur_off + (size_t)y0 * L.pitch + x;
 
-  // ---- row pass straight from global memory: warp = one (reflected) image row per iteration, lane = 4 output
-  //      columns gx..gx+3, which need image x = gx-3 .. gx+6 = three aligned words.  All loads of all iterations are
-  //      issued before the first use (memory-level parallelism).  Borders: the word left of x = 0 is a byte
-  //      permutation of word 0 (reflect-101); tiles that touch the right edge take the byte-gather path.
-  {
-    const int gx = x0 + 4 * lane;
-    unsigned w0[NIT], w1[NIT], w2[NIT];
-    if (x0 + TW + 4 <= L.w) {  // block-uniform: every word of every lane lies inside the row
-      const uint8_t* colp = src + gx;
-      const int lofs = gx > 0 ? -4 : 0;
+  // ---- per-lane window geometry.  Word k nominally holds pixels x-4+4k .. x-1+4k.  Bytes left of pixel 0 are
+  //      reflected out of word 0 (pixels 0..3: the address clamp loads exactly that word); bytes right of the last
+  //      pixel e are reflected out of the strip S = pixels e-3 .. e.  One PRMT per word applies both (identity
+  //      selector for interior lanes: the integer pipe has slack, a divergent branch would cost more).
+  const int e = L.w - 1, xlast = e & ~3;
+  const uint8_t* pw[4];
+  unsigned sel[4];
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int r = warp + 8 * it;
-        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);
-        const uint8_t* row = colp + (size_t)gy * pitch;
-        w1[it] = *reinterpret_cast<const uint32_t*>(row);
-        w2[it] = *reinterpret_cast<const uint32_t*>(row + 4);
-        w0[it] = *reinterpret_cast<const uint32_t*>(row + lofs);
-      }
-      if (gx == 0) {
+  for (int k = 0; k < 4; ++k) {
+    const int xk = x - 4 + 4 * k;
+    pw[k] = src + min(max(xk, 0), xlast);
+    unsigned sk = 0;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) w0[it] = __byte_perm(w1[it], 0u, 0x1230);
-      }
-    } else {
-      // Right-edge tiles.  Reflect-101 mirrors x = e + k onto e - k (e = w - 1), so every byte a lane needs beyond the
-      // edge is one of the last four pixels of the row.  Per lane and word a PRMT selector (fixed for the whole tile)
-      // picks each byte either from the lane's own (address-clamped) word or from the strip S = pixels e-3 .. e.
-      const int e = L.w - 1;
-      const int xs = (e - 3) & ~3;                    // aligned word holding pixel e-3 (w >= 32)
-      const int sh = 8 * ((e - 3) & 3);
-      const int xs2 = sh ? xs + 4 : xs;               // second strip word only when the strip straddles two words
-      const int xmax = e & ~3;                        // last aligned word that starts inside the row
-      int xo[3];
-      unsigned sel[3];
+    for (int b = 0; b < 4; ++b) {
+      const int px = xk + b, d = px - e;
+      const unsigned nib = px < 0 ? (unsigned)(-px) & 3u : (d <= 0 ? (unsigned)b : (d <= 3 ? (unsigned)(7 - d) : 0u));
+      sk |= nib << (4 * b);
+    }
+    sel[k] = sk;
+  }
+  const bool redge = x + 11 > e;
+  const unsigned sh = 8u * (unsigned)((e - 3) & 3);
+  const uint8_t* ps = src + ((e - 3) & ~3);
+  const int ps2 = sh ? 4 : 0;
+  const int hm1 = L.h - 1;
+
+  auto load_row = [&](int t, unsigned (&w)[4]) {
+    // reflect-101 of yy = y0 - 3 + t (|yy| mirrors the top, (h-1) - |(h-1) - .| the bottom), clamped for the rows
+    // past the mirror that feed no stored output
+    const int gy = max(hm1 - abs(hm1 - abs(y0 - 3 + t)), 0);
+    const unsigned ro = (unsigned)gy * (unsigned)spitch;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int xk = gx - 4 + 4 * k;
-        xo[k] = min(max(xk, 0), xmax);
-        unsigned sk = 0;
+    for (int k = 0; k < 4; ++k) w[k] = *reinterpret_cast<const uint32_t*>(pw[k] + ro);
+    unsigned S = 0;
+    if (redge) S = __funnelshift_r(*reinterpret_cast<const uint32_t*>(ps + ro),
+                                   *reinterpret_cast<const uint32_t*>(ps + ro + ps2), sh);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int d = xk + b - e;                   // > 0: beyond the edge -> strip byte 3 - d
-          const unsigned nib = d <= 0 ? (unsigned)b : (d <= 3 ? (unsigned)(7 - d) : 0u);
-          sk |= nib << (4 * b);
-        }
-        sel[k] = sk;
-      }
+    for (int k = 0; k < 4; ++k) w[k] = __byte_perm(w[k], S, sel[k]);
+  };
+
+  const f32x2_t K0 = pk2(0x1.1f5f62p-4f, 0x1.1f5f62p-4f), K1 = pk2(0x1.0c70fcp-3f, 0x1.0c70fcp-3f);
+  const f32x2_t K2 = pk2(0x1.869472p-3f, 0x1.869472p-3f), K3 = pk2(0x1.ba95c0p-3f, 0x1.ba95c0p-3f);
+  const f32x2_t NEG23 = pk2(-8388608.0f, -8388608.0f), MAGIC = pk2(12582912.0f, 12582912.0f);
+
+  // Row pass of one source row (window words w) into r[0..3].
+  // u8 -> f32: the byte goes into the mantissa of 2^23, then (2^23 + b) - 2^23 is exact.  f[a] = pixel x-3+a is
+  // byte a+1 of the window; pair a = (f[a], f[a+4]).
+  auto row_pass = [&](const unsigned (&w)[4], f32x2_t (&r)[4]) {
+    f32x2_t p[10];
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int r = warp + 8 * it;
-        const int gy = min(max(reflect101_near(y0 - 3 + r, L.h), 0), L.h - 1);
-        const uint8_t* row = src + (size_t)gy * pitch;
-        const unsigned sA = *reinterpret_cast<const uint32_t*>(row + xs);
-        const unsigned sB = *reinterpret_cast<const uint32_t*>(row + xs2);
-        const unsigned S = __funnelshift_r(sA, sB, sh);
-        w0[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[0]), S, sel[0]);
-        w1[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[1]), S, sel[1]);
-        w2[it] = __byte_perm(*reinterpret_cast<const uint32_t*>(row + xo[2]), S, sel[2]);
-      }
-      if (gx == 0) {
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) w0[it] = __byte_perm(w1[it], 0u, 0x1230);
-      }
+    for (int a = 0; a < 10; ++a) {
+      const unsigned s4 = 0x7540u | (unsigned)((a + 1) & 3);
+      const unsigned lo = __byte_perm(w[(a + 1) >> 2], 0x4B000000u, s4);
+      const unsigned hi = __byte_perm(w[(a + 5) >> 2], 0x4B000000u, s4);
+      p[a] = add2(pk2u(lo, hi), NEG23);
     }
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int r = warp + 8 * it;
-      if (r >= TH + 6) break;
-      float f[10];  // image x = gx-3 .. gx+6
-      f[0] = u8_to_f32(w0[it], 1);
-      f[1] = u8_to_f32(w0[it], 2);
-      f[2] = u8_to_f32(w0[it], 3);
-      f[3] = u8_to_f32(w1[it], 0);
-      f[4] = u8_to_f32(w1[it], 1);
-      f[5] = u8_to_f32(w1[it], 2);
-      f[6] = u8_to_f32(w1[it], 3);
-      f[7] = u8_to_f32(w2[it], 0);
-      f[8] = u8_to_f32(w2[it], 1);
-      f[9] = u8_to_f32(w2[it], 2);
-      float o[4];
+    for (int k = 0; k < 4; ++k) {
+      f32x2_t s = mul2(p[k], K0);
+      s = fma2(p[k + 1], K1, s);
+      s = fma2(p[k + 2], K2, s);
+      s = fma2(p[k + 3], K3, s);
+      s = fma2(p[k + 4], K2, s);
+      s = fma2(p[k + 5], K1, s);
+      s = fma2(p[k + 6], K0, s);
+      r[k] = s;
+    }
+  };
+
+  f32x2_t win[7][4];  // row-pass results of the last 7 source rows; every index is a compile-time constant
+  unsigned cw[4];
+  load_row(0, cw);
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {  // fill the window: source rows 0..5 of the item
+    unsigned nw[4];
+    load_row(t + 1, nw);
+    row_pass(cw, win[t]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cw[k] = nw[k];
+  }
+#pragma unroll 1
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int tb = 6 + 7 * blk;
+#pragma unroll
+    for (int ph = 0; ph < 7; ++ph) {
+      const int t = tb + ph;          // source row of the item; window slot (6 + ph) % 7
+      constexpr int kSlot0 = 6;
+      unsigned nw[4];
+      load_row(t + 1, nw);            // software prefetch of the next source row
+      row_pass(cw, win[(kSlot0 + ph) % 7]);
+      // column pass of output row t - 6: source rows t-6 .. t live in slots (ph + j) % 7, j = 0..6
+      unsigned b[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float s = __fmul_rn(k0, f[k]);
-        s = __fmaf_rn(f[k + 1], k1, s);
-        s = __fmaf_rn(f[k + 2], k2, s);
-        s = __fmaf_rn(f[k + 3], k3, s);
-        s = __fmaf_rn(f[k + 4], k2, s);
-        s = __fmaf_rn(f[k + 5], k1, s);
-        s = __fmaf_rn(f[k + 6], k0, s);
-        o[k] = s;
+        f32x2_t s = mul2(win[(ph + 3) % 7][k], K3);
+        s = fma2(add2(win[(ph + 4) % 7][k], win[(ph + 2) % 7][k]), K2, s);
+        s = fma2(add2(win[(ph + 5) % 7][k], win[(ph + 1) % 7][k]), K1, s);
+        s = fma2(add2(win[(ph + 6) % 7][k], win[(ph + 0) % 7][k]), K0, s);
+        upk2u(add2(s, MAGIC), b[k], b[k + 4]);  // low byte = round-half-even(s), 0 <= s < 256
       }
-      *reinterpret_cast<float4*>(s_row + r * TW + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-  }
-  __syncthreads();
-
-  // ---- column pass: thread = (4 columns) x (4 rows), 10 row vectors in registers; round-half-even via the
-  //      2^23 magic add (0 <= s < 256), 4 pixels packed per 32-bit store.
-  {
-    const int cg = lane, rr = warp;
-    float v[10][4];
+      uint2 o;
+      o.x = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+      o.y = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
+      if (t - 6 < rs) *reinterpret_cast<uint2*>(dst + (unsigned)(t - 6) * (unsigned)L.pitch) = o;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      const float4 t = *reinterpret_cast<const float4*>(s_row + (4 * rr + j) * TW + 4 * cg);
-      v[j][0] = t.x;
-      v[j][1] = t.y;
-      v[j][2] = t.z;
-      v[j][3] = t.w;
-    }
-    const int gx = x0 + 4 * cg;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gy = y0 + 4 * rr + i;
-      unsigned b[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float s = __fmul_rn(k3, v[i + 3][c]);
-        s = __fmaf_rn(__fadd_rn(v[i + 4][c], v[i + 2][c]), k2, s);
-        s = __fmaf_rn(__fadd_rn(v[i + 5][c], v[i + 1][c]), k1, s);
-        s = __fmaf_rn(__fadd_rn(v[i + 6][c], v[i][c]), k0, s);
-        b[c] = __float_as_uint(__fadd_rn(s, 12582912.0f));  // low byte = round-half-even(s)
-      }
-      const unsigned word = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
-      if (gy < L.h && gx < L.pitch) *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = word;
+      for (int k = 0; k < 4; ++k) cw[k] = nw[k];
     }
   }
 }

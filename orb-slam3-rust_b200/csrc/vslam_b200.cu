@@ -233,13 +233,14 @@ int build_params(vslam_handle h) {
     strip0 += L.fast_nstrips;
     L.rec_off = (int)rec_off;
     rec_off += (long long)L.fast_nstrips * L.strip_cap;
-    L.blur_tx = (L.w + VSLAM_BLUR_TW - 1) / VSLAM_BLUR_TW;
-    L.blur_ty = (L.h + VSLAM_BLUR_TH - 1) / VSLAM_BLUR_TH;
-    L.blur_tile0 = tile0;
-    tile0 += L.blur_tx * L.blur_ty;
+    L.blur_ncg = (L.w + 7) / 8;
+    L.blur_nstr = (L.h + VSLAM_BLUR_ROWS - 1) / VSLAM_BLUR_ROWS;
+    L.blur_rs = (L.h + L.blur_nstr - 1) / L.blur_nstr;
+    L.blur_item0 = tile0;
+    tile0 += (L.blur_ncg * L.blur_nstr + 31) & ~31;
   }
   P.total_fast_strips = strip0;
-  P.total_blur_tiles = tile0;
+  P.total_blur_items = tile0;
   P.pyr_img_stride = (long long)align_up(std::max<size_t>(pyr_off, 256), 256);
   P.blur_img_stride = (long long)align_up(blur_off, 256);
   P.rec_img_stride = (rec_off + 1) & ~1LL;
@@ -422,8 +423,8 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   if (fork) {
     CU_TRY(h, cudaEventRecord(s.ev_pyr, st));
     CU_TRY(h, cudaStreamWaitEvent(sb, s.ev_pyr, 0));
-    dim3 grid(P.total_blur_tiles, nimg);
-    vk::k_blur<<<grid, 256, 0, sb>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
+    dim3 grid((P.total_blur_items + 127) / 128, nimg);
+    vk::k_blur<<<grid, 128, 0, sb>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
     CU_TRY(h, cudaEventRecord(s.ev_blur, sb));
   }
@@ -446,8 +447,8 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 3
   if (!fork) {
-    dim3 grid(P.total_blur_tiles, nimg);
-    vk::k_blur<<<grid, 256, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
+    dim3 grid((P.total_blur_items + 127) / 128, nimg);
+    vk::k_blur<<<grid, 128, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
   } else {
     CU_TRY(h, cudaStreamWaitEvent(st, s.ev_blur, 0));

@@ -6,8 +6,7 @@
 #define VSLAM_MAX_LEVELS 12
 #define VSLAM_FAST_ROWS 16      // emission rows per FAST strip
 #define VSLAM_RESIZE_ROWS 8     // dst rows per resize strip
-#define VSLAM_BLUR_TW 128       // blur tile width
-#define VSLAM_BLUR_TH 32        // blur tile height
+#define VSLAM_BLUR_ROWS 64      // max output rows of one blur lane item (8 columns wide)
 #define VSLAM_DESC_BYTES 32
 
 // 8-byte corner record permuted by the selection replay: hi = float bits of the response, lo = (y<<16)|x.
@@ -24,7 +23,8 @@ struct LevelP {
   int fast_strip0, fast_nstrips;   // strips of VSLAM_FAST_ROWS emission rows
   int strip_cap;          // corner records per strip (worst case after NMS)
   int rec_off;            // record offset of this level inside the per-image strip-record slab
-  int blur_tile0, blur_tx, blur_ty;  // first tile index, tiles in x, tiles in y
+  int blur_item0, blur_ncg, blur_nstr, blur_rs;  // blur lane items: first item (multiple of 32), 8-column groups,
+                                                 // row strips, rows per strip
 };
 
 struct PyrP {
@@ -33,7 +33,7 @@ struct PyrP {
   int in_pitch;           // row pitch of level-0 images
   int fast_threshold;
   int total_fast_strips;
-  int total_blur_tiles;
+  int total_blur_items;
   int kp_cap;             // per-image keypoint capacity
   int sel_smem_cap;       // records the selection kernel can hold in shared memory
   long long in_frame_stride;   // bytes between consecutive frames in the input (per eye base)
