@@ -45,6 +45,11 @@ __device__ __forceinline__ int dp4a_u8_s8(unsigned a, unsigned b, int c) {
   return d;
 }
 
+// Non-blocking prefetch of the 32-byte sector at p into L2 (no register, no scoreboard): the register-resident
+// streaming kernels below keep only 1-2 rows of loads in flight per lane, which covers the L2 latency but not a DRAM
+// miss; the row that will be loaded a few iterations later is requested from DRAM here.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct __align__(8) LvlKp {
   unsigned xy;  // (y<<16)|x in level coordinates
   float resp;   // Harris response
@@ -62,93 +67,104 @@ __device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int im
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// A1 — pyramid level l from level l-1.  grid = (ceil(h_l / VSLAM_RESIZE_ROWS), n_img), block = 256.
-// coef[] holds per destination column/row (src offset | alpha1 << 16), computed on the host in f64.
+// A1 — pyramid level l from level l-1 (INTER_LINEAR_EXACT: Q8.8 x Q8.8 fixed point).  coef[] holds per destination
+// column / row (src offset | alpha1 << 16), computed on the host in f64.
+//
+// Register-resident, no shared memory, no barriers: one LANE owns 4 destination columns x (<= rs) destination rows
+// and walks down.  The x coefficients, PRMT selectors and word offsets of its columns are set up once per item; the
+// horizontal interpolation h(s) of a source row s is computed once (3 aligned word loads, 2 funnel shifts,
+// 4 x (PRMT + DP2A)) and serves both destination rows that blend it.  The raw words of the next source row are
+// prefetched while the current one is processed.
+// grid = (ceil(ceil(w/4) * nstr / 128), n_img), block = 128; items are numbered column-group fastest.
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ PyrP P, int l, const uint8_t* __restrict__ in_l,
-                                                const uint8_t* __restrict__ in_r, uint8_t* __restrict__ pyr,
-                                                const uint32_t* __restrict__ coef) {
-  extern __shared__ __align__(16) uint8_t smem[];
+constexpr int kResizePrefetchRows = 8;  // source rows between the L2 prefetch and the register load
+__global__ void __launch_bounds__(128) k_resize(const __grid_constant__ PyrP P, int l, int rs,
+                                                const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
+                                                uint8_t* __restrict__ pyr, const uint32_t* __restrict__ coef) {
   const LevelP& D = P.lv[l];
   const LevelP& S = P.lv[l - 1];
   const int img = blockIdx.y;
-  const int y0 = blockIdx.x * VSLAM_RESIZE_ROWS;
-  const int rows = min(VSLAM_RESIZE_ROWS, D.h - y0);
+  const int ncg = (D.w + 3) >> 2;
+  const int item = blockIdx.x * 128 + threadIdx.x;
+  const int strip = item / ncg, cg = item - strip * ncg;
+  const int y0 = strip * rs;
+  if (y0 >= D.h) return;
+  const int rows = min(rs, D.h - y0);
   int spitch;
   const uint8_t* src = level_ptr(P, l - 1, img, in_l, in_r, pyr, spitch);
-  uint8_t* dst = pyr + (long long)img * P.pyr_img_stride + D.pyr_off;
-  const uint32_t* yc = coef + D.ycoef_off;
+  uint8_t* dst = pyr + (long long)img * P.pyr_img_stride + D.pyr_off + (size_t)y0 * D.pitch + 4 * cg;
+  const uint32_t* yc = coef + D.ycoef_off + y0;
   const uint32_t* xc = coef + D.xcoef_off;
-  const int sy0 = (int)(yc[y0] & 0xffffu);
-  const int sy1 = min((int)(yc[y0 + rows - 1] & 0xffffu) + 1, S.h - 1);
-  const int nrows = sy1 - sy0 + 1;
-  const int vpr = spitch >> 4;
-  for (int r = threadIdx.x >> 5; r < nrows; r += 8) {
-    const uint4* srow = reinterpret_cast<const uint4*>(src + (size_t)(sy0 + r) * spitch);
-    uint4* drow = reinterpret_cast<uint4*>(smem + r * spitch);
-    for (int c = threadIdx.x & 31; c < vpr; c += 32) drow[c] = srow[c];
+
+  // ---- per-item column setup.  The (at most 8) source bytes the four pixels need start at ox[0]: three aligned
+  //      words + two funnel shifts bring them to bytes 0..7 of (v0, v1); a per-pixel PRMT selector picks
+  //      (p[ox], p[ox+1]) and DP2A forms alpha0*p0 + alpha1*p1.  Word offsets are clamped to the row: a clamped word
+  //      only ever supplies bytes beyond the source row, whose weight is 0.  Items whose window is wider than 8 bytes
+  //      (scale factors near 2) use byte loads.
+  int ox[4];
+  unsigned a01[4], sel[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned c = xc[min(4 * cg + k, D.w - 1)];
+    ox[k] = (int)(c & 0xffffu);
+    const unsigned a1 = c >> 16;
+    a01[k] = (256u - a1) | (a1 << 16);
   }
-  __syncthreads();
-  // Each thread owns 4 destination columns and walks down the strip's rows.  The kernel is bound by shared-memory
-  // wavefronts, not by issue slots, so the taps are fetched as aligned words: the (at most 8) source bytes the four
-  // pixels need start at ox[0]; three LDS.32 + two funnel shifts bring them to bytes 0..7 of (v0, v1), a per-thread
-  // PRMT selector picks each pixel's (p[ox], p[ox+1]) pair and DP2A forms alpha0*p0 + alpha1*p1 in one instruction
-  // (16 byte loads per row pair -> 6 word loads).  Threads whose window is wider than 8 bytes (scale factors near 2)
-  // use byte loads.
-  const int ngroups = D.pitch >> 2;
-  for (int g = threadIdx.x; g < ngroups; g += 256) {
-    int ox[4];
-    unsigned a01[4];  // alpha0 | alpha1 << 16
+  const bool wide = ox[3] + 1 - ox[0] > 7;
+  const unsigned sh = 8u * (unsigned)(ox[0] & 3);
+  int wo[3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = xc[min(4 * g + k, D.w - 1)];
-      ox[k] = (int)(c & 0xffffu);
-      const unsigned a1 = c >> 16;
-      a01[k] = (256u - a1) | (a1 << 16);
+  for (int j = 0; j < 3; ++j) wo[j] = min((ox[0] & ~3) + 4 * j, spitch - 4);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned e = (unsigned)(ox[k] - ox[0]) & 7u;   // byte offset of p[ox[k]] inside (v0, v1)
+    sel[k] = e | (((e + 1u) & 7u) << 4) | 0x4400u;       // bytes 2,3 of the result are don't-care (DP2A.LO ignores them)
+  }
+  const int shm1 = S.h - 1, swm1 = S.w - 1;
+
+  auto load_raw = [&](int sy, unsigned (&u)[3]) {
+    const uint8_t* rp = src + (size_t)min(sy, shm1) * spitch;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) u[j] = *reinterpret_cast<const uint32_t*>(rp + wo[j]);
+  };
+  auto hcalc = [&](int sy, const unsigned (&u)[3], unsigned (&h)[4]) {
+    if (!wide) {
+      const unsigned v0 = __funnelshift_r(u[0], u[1], sh), v1 = __funnelshift_r(u[1], u[2], sh);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(a01[k], __byte_perm(v0, v1, sel[k]), 0u);
+    } else {
+      const uint8_t* rp = src + (size_t)sy * spitch;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        h[k] = (a01[k] & 0xffffu) * rp[ox[k]] + (a01[k] >> 16) * rp[min(ox[k] + 1, swm1)];
     }
-    const bool wide = ox[3] + 1 - ox[0] > 7;
-    const int wbase = ox[0] & ~3;
-    const unsigned sh = 8u * (unsigned)(ox[0] & 3);
-    unsigned sel[4];
+  };
+
+  unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0}, nx[3];
+  int rowB = (int)(yc[0] & 0xffffu) - 1;  // hB = h(rowB); the first destination row computes rows o and o+1
+  load_raw(rowB + 1, nx);
+  unsigned yy = yc[0];
+  for (int r = 0; r < rows; ++r) {
+    const int o = (int)(yy & 0xffffu), o1 = min(o + 1, shm1);
+    const unsigned b1 = yy >> 16, b0 = 256u - b1;
+    yy = yc[min(r + 1, rows - 1)];
+    while (rowB < o1) {
+      unsigned cur[3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned e = (unsigned)(ox[k] - ox[0]) & 7u;  // byte offset of p[ox[k]] inside (v0, v1)
-      sel[k] = e | (((e + 1u) & 7u) << 4) | 0x4400u;      // bytes 2,3 of the result are don't-care (DP2A.LO ignores them)
+      for (int j = 0; j < 3; ++j) cur[j] = nx[j];
+      ++rowB;
+      load_raw(rowB + 1, nx);
+      prefetch_l2(src + (size_t)min(rowB + kResizePrefetchRows, shm1) * spitch + wo[1]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hA[k] = hB[k];
+      hcalc(rowB, cur, hB);
     }
-    for (int r = 0; r < rows; ++r) {
-      const unsigned yy = yc[y0 + r];
-      const int o = (int)(yy & 0xffffu);
-      const unsigned b1 = yy >> 16, b0 = 256u - b1;
-      const uint8_t* r0 = smem + (o - sy0) * spitch;
-      const uint8_t* r1 = smem + (min(o + 1, S.h - 1) - sy0) * spitch;
-      unsigned h0[4], h1[4];
-      if (!wide) {
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(r0 + wbase);
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(r1 + wbase);
-        const unsigned u0 = q0[0], u1 = q0[1], u2 = q0[2], t0 = q1[0], t1 = q1[1], t2 = q1[2];
-        const unsigned v00 = __funnelshift_r(u0, u1, sh), v01 = __funnelshift_r(u1, u2, sh);
-        const unsigned v10 = __funnelshift_r(t0, t1, sh), v11 = __funnelshift_r(t1, t2, sh);
+    const bool same = o1 == o;  // bottom replicate: both taps are the last source row (beta1 == 0)
+    unsigned v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          h0[k] = __dp2a_lo(a01[k], __byte_perm(v00, v01, sel[k]), 0u);
-          h1[k] = __dp2a_lo(a01[k], __byte_perm(v10, v11, sel[k]), 0u);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned a0 = a01[k] & 0xffffu, a1 = a01[k] >> 16;
-          h0[k] = a0 * r0[ox[k]] + a1 * r0[ox[k] + 1];
-          h1[k] = a0 * r1[ox[k]] + a1 * r1[ox[k] + 1];
-        }
-      }
-      unsigned word = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const unsigned v = b0 * h0[k] + b1 * h1[k];
-        word |= ((v + 32768u) >> 16) << (8 * k);
-      }
-      *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * D.pitch + 4 * g) = word;
-    }
+    for (int k = 0; k < 4; ++k) v[k] = b0 * (same ? hB[k] : hA[k]) + (b1 * hB[k] + 32768u);  // < 2^24: byte 2 = result
+    const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+    *reinterpret_cast<uint32_t*>(dst + (size_t)r * D.pitch) = word;
   }
 }
 
@@ -801,6 +817,7 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
   return d;
 }
 
+constexpr int kBlurPrefetchRows = 6;  // source rows between the L2 prefetch and the register load
 __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
@@ -844,20 +861,36 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
   const unsigned sh = 8u * (unsigned)((e - 3) & 3);
   const uint8_t* ps = src + ((e - 3) & ~3);
   const int ps2 = sh ? 4 : 0;
-  const int hm1 = L.h - 1;
+  int hm1 = L.h - 1, dpitch = L.pitch;
+  unsigned pfmax = (unsigned)hm1 * (unsigned)spitch;  // prefetches stay inside the level
+  // Loop invariants must live in registers: under register pressure ptxas otherwise re-derives them inside the row
+  // loop through indexed constant-bank loads (LDC c[0x0][R+..], long-scoreboard latency in front of every SHF / PRMT).
+  unsigned shv = sh;
+  asm volatile("" : "+r"(hm1), "+r"(dpitch), "+r"(shv), "+r"(spitch), "+r"(pfmax));
+  asm volatile("" : "+r"(sel[0]), "+r"(sel[1]), "+r"(sel[2]), "+r"(sel[3]));
+  asm volatile("" : "+l"(dst));
 
-  auto load_row = [&](int t, unsigned (&w)[4]) {
+  // Raw loads of source row t (4 window words + the 2 words holding S for right-edge lanes); fix_row applies the
+  // border selectors when the row is consumed, two rows later, so that no instruction waits on a load right after
+  // issuing it (prefetch distance 2 covers a DRAM miss at 3 warps per scheduler).
+  auto load_row = [&](int t, unsigned (&w)[6]) {
     // reflect-101 of yy = y0 - 3 + t (|yy| mirrors the top, (h-1) - |(h-1) - .| the bottom), clamped for the rows
     // past the mirror that feed no stored output
     const int gy = max(hm1 - abs(hm1 - abs(y0 - 3 + t)), 0);
     const unsigned ro = (unsigned)gy * (unsigned)spitch;
 #pragma unroll
     for (int k = 0; k < 4; ++k) w[k] = *reinterpret_cast<const uint32_t*>(pw[k] + ro);
-    unsigned S = 0;
-    if (redge) S = __funnelshift_r(*reinterpret_cast<const uint32_t*>(ps + ro),
-                                   *reinterpret_cast<const uint32_t*>(ps + ro + ps2), sh);
+    prefetch_l2(pw[1] + min(ro + (unsigned)(kBlurPrefetchRows * spitch), pfmax));
+    w[4] = w[5] = 0;
+    if (redge) {
+      w[4] = *reinterpret_cast<const uint32_t*>(ps + ro);
+      w[5] = *reinterpret_cast<const uint32_t*>(ps + ro + ps2);
+    }
+  };
+  auto fix_row = [&](const unsigned (&r)[6], unsigned (&w)[4]) {
+    const unsigned S = __funnelshift_r(r[4], r[5], shv);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = __byte_perm(w[k], S, sel[k]);
+    for (int k = 0; k < 4; ++k) w[k] = __byte_perm(r[k], S, sel[k]);
   };
 
   const f32x2_t K0 = pk2(0x1.1f5f62p-4f, 0x1.1f5f62p-4f), K1 = pk2(0x1.0c70fcp-3f, 0x1.0c70fcp-3f);
@@ -890,15 +923,20 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
   };
 
   f32x2_t win[7][4];  // row-pass results of the last 7 source rows; every index is a compile-time constant
-  unsigned cw[4];
-  load_row(0, cw);
+  unsigned r0[6], r1[6];  // raw words of source rows t and t+1
+  load_row(0, r0);
+  load_row(1, r1);
 #pragma unroll
   for (int t = 0; t < 6; ++t) {  // fill the window: source rows 0..5 of the item
-    unsigned nw[4];
-    load_row(t + 1, nw);
+    unsigned r2[6], cw[4];
+    load_row(t + 2, r2);
+    fix_row(r0, cw);
     row_pass(cw, win[t]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cw[k] = nw[k];
+    for (int k = 0; k < 6; ++k) {
+      r0[k] = r1[k];
+      r1[k] = r2[k];
+    }
   }
 #pragma unroll 1
   for (int blk = 0; blk < nblk; ++blk) {
@@ -906,10 +944,10 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
 #pragma unroll
     for (int ph = 0; ph < 7; ++ph) {
       const int t = tb + ph;          // source row of the item; window slot (6 + ph) % 7
-      constexpr int kSlot0 = 6;
-      unsigned nw[4];
-      load_row(t + 1, nw);            // software prefetch of the next source row
-      row_pass(cw, win[(kSlot0 + ph) % 7]);
+      unsigned r2[6], cw[4];
+      load_row(t + 2, r2);            // software prefetch, two rows ahead
+      fix_row(r0, cw);
+      row_pass(cw, win[(6 + ph) % 7]);
       // column pass of output row t - 6: source rows t-6 .. t live in slots (ph + j) % 7, j = 0..6
       unsigned b[8];
 #pragma unroll
@@ -923,9 +961,12 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
       uint2 o;
       o.x = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
       o.y = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
-      if (t - 6 < rs) *reinterpret_cast<uint2*>(dst + (unsigned)(t - 6) * (unsigned)L.pitch) = o;
+      if (t - 6 < rs) *reinterpret_cast<uint2*>(dst + (unsigned)(t - 6) * (unsigned)dpitch) = o;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) cw[k] = nw[k];
+      for (int k = 0; k < 6; ++k) {
+        r0[k] = r1[k];
+        r1[k] = r2[k];
+      }
     }
   }
 }

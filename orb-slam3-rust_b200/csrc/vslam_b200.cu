@@ -78,7 +78,8 @@ struct vslam_handle_s {
   float harris_scale4 = 0.f;
   std::vector<uint32_t> coef;
   uint32_t* d_coef = nullptr;
-  size_t resize_smem[VSLAM_MAX_LEVELS] = {0};
+  int resize_rows = VSLAM_RESIZE_ROWS;  // destination rows per k_resize lane item
+  int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
   size_t fast_smem = 0;
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   int harris_blocks = 1;
@@ -234,7 +235,7 @@ int build_params(vslam_handle h) {
     L.rec_off = (int)rec_off;
     rec_off += (long long)L.fast_nstrips * L.strip_cap;
     L.blur_ncg = (L.w + 7) / 8;
-    L.blur_nstr = (L.h + VSLAM_BLUR_ROWS - 1) / VSLAM_BLUR_ROWS;
+    L.blur_nstr = (L.h + h->blur_rows - 1) / h->blur_rows;
     L.blur_rs = (L.h + L.blur_nstr - 1) / L.blur_nstr;
     L.blur_item0 = tile0;
     tile0 += (L.blur_ncg * L.blur_nstr + 31) & ~31;
@@ -256,22 +257,13 @@ int build_params(vslam_handle h) {
     }
     P.lv[P.nlevels - 1].nfeat = std::max(c.n_features - sum, 0);
   }
-  // resize coefficient table + per-level shared-memory need
+  // resize coefficient table
   h->coef.assign(std::max<size_t>(ncoef, 1), 0);
   for (int l = 1; l < P.nlevels; ++l) {
     LevelP& L = P.lv[l];
     const LevelP& Sx = P.lv[l - 1];
     linear_exact_coeffs(Sx.w, L.w, h->coef.data() + L.xcoef_off);
     linear_exact_coeffs(Sx.h, L.h, h->coef.data() + L.ycoef_off);
-    const uint32_t* yc = h->coef.data() + L.ycoef_off;
-    int max_rows = 0;
-    for (int y0 = 0; y0 < L.h; y0 += VSLAM_RESIZE_ROWS) {
-      int rows = std::min(VSLAM_RESIZE_ROWS, L.h - y0);
-      int sy0 = (int)(yc[y0] & 0xffffu);
-      int sy1 = std::min((int)(yc[y0 + rows - 1] & 0xffffu) + 1, Sx.h - 1);
-      max_rows = std::max(max_rows, sy1 - sy0 + 1);
-    }
-    h->resize_smem[l] = (size_t)max_rows * Sx.pitch + 16;  // + spare bytes: the kernel reads p[ox + 1] unconditionally
   }
   h->fast_smem = vk::fast_smem_bytes(P.in_pitch);
   // selection scratch in shared memory: select1 sized for ~3% corner density on the largest level (typical < 2%),
@@ -409,10 +401,9 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   CU_TRY(h, cudaMemsetAsync(s.d_lay.hdr, 0, sizeof(ResHdr) * (size_t)frames, st));
   mark();  // 0
   for (int l = 1; l < P.nlevels; ++l) {
-    // (a variant without shared-memory staging, four __ldg taps per pixel, measured 1.7x slower: 9.9 vs 5.8 ms/step)
-    dim3 grid((P.lv[l].h + VSLAM_RESIZE_ROWS - 1) / VSLAM_RESIZE_ROWS, nimg);
-    size_t smem = l == 1 ? ((h->resize_smem[l] - 16) / (size_t)h->P.lv[0].pitch) * (size_t)pitch + 16 : h->resize_smem[l];
-    vk::k_resize<<<grid, 256, smem, st>>>(P, l, in_l, in_r, s.d_pyr, h->d_coef);
+    const int rs = h->resize_rows, nstr = (P.lv[l].h + rs - 1) / rs, ncg = (P.lv[l].w + 3) / 4;
+    dim3 grid((ncg * nstr + 127) / 128, nimg);
+    vk::k_resize<<<grid, 128, 0, st>>>(P, l, (P.lv[l].h + nstr - 1) / nstr, in_l, in_r, s.d_pyr, h->d_coef);
     h->launches++;
   }
   mark();  // 1
@@ -740,6 +731,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   h->max_batch = c.max_batch;
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
+  if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
+  if (const char* ev = getenv("VSLAM_BLUR_ROWS")) h->blur_rows = std::min(std::max(atoi(ev), 8), 4096);
   int rc = build_params(h);
   if (rc != VSLAM_OK) {
     g_create_error = h->err;
@@ -761,21 +754,19 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   cudaEventCreate(&h->ev_batch[0]);
   cudaEventCreate(&h->ev_batch[1]);
   // opt in to large dynamic shared memory where needed
-  size_t max_resize = 0;
-  for (int l = 1; l < h->P.nlevels; ++l) max_resize = std::max(max_resize, h->resize_smem[l]);
   const size_t max_sel1 = vk::select1_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency));
   const size_t max_sel = std::max(max_sel1, vk::select2_smem_bytes(h->sel2_cap));
   const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
-  if (h->fast_smem > lim || max_resize > lim || max_sel > lim) {
-    fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image too wide for the shared-memory tiles (%zu/%zu/%zu > %zu bytes)",
-         h->fast_smem, max_resize, max_sel, lim);
+  if (h->fast_smem > lim || max_sel > lim) {
+    fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image too wide for the shared-memory tiles (%zu/%zu > %zu bytes)",
+         h->fast_smem, max_sel, lim);
     return bail(VSLAM_ERR_INVALID_ARGUMENT);
   }
   // The opt-in limit is a per-function (not per-handle) attribute: only ever raise it, so that handles created for
   // smaller images do not shrink what an older handle's launches need.
   {
     static std::mutex mu;
-    static size_t cur_dev[64][5] = {{0}};
+    static size_t cur_dev[64][4] = {{0}};
     size_t* cur = cur_dev[c.device & 63];
     std::lock_guard<std::mutex> lock(mu);
     // row-bucketed fused matcher when its tables fit in shared memory; otherwise the chunked pair of kernels
@@ -783,11 +774,10 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
       const size_t need = vk::match_rows_smem_bytes(h->kp_cap, c.height);
       h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
     }
-    const size_t want[5] = {h->fast_smem, std::max<size_t>(max_resize, 1024), max_sel1,
-                            vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
-    const void* fn[5] = {(const void*)vk::k_fast, (const void*)vk::k_resize, (const void*)vk::k_select1,
-                         (const void*)vk::k_select2, (const void*)vk::k_match_rows};
-    for (int i = 0; i < 5; ++i)
+    const size_t want[4] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
+    const void* fn[4] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
+                         (const void*)vk::k_match_rows};
+    for (int i = 0; i < 4; ++i)
       if (want[i] > cur[i]) {
         e = cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want[i]);
         if (e != cudaSuccess) {
