@@ -263,9 +263,11 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   __syncthreads();
 
   // ---- scores on the emission region dilated by one pixel (clipped to FAST's own 3-px border).
-  // Phase A (every group of 4 pixels, byte-SIMD): a necessary condition for a FAST-9 corner — every 9-arc of the
-  //   16-circle contains one of the points {0, 8} and one of {4, 12}, so (|d0|>t or |d8|>t) and (|d4|>t or |d12|>t)
-  //   must hold.  Pairs of pixels that pass are queued per warp.
+  // Phase A (every group of 4 pixels, byte-SIMD): a necessary condition for a FAST-9 corner — a 9-arc of the
+  //   16-circle contains at least one point of every antipodal pair {k, k+8}, so (|d_k|>t or |d_{k+8}|>t) must hold
+  //   for each pair; the four pairs k = 0, 2, 4, 6 are tested (22 % of the pixel pairs of the synthetic scenes
+  //   survive, against 38 % with two pairs and 10 % that contain a corner).  Pairs of pixels that pass are queued
+  //   per warp.
   // Phase B (queued pairs only, 32 at a time so every lane is busy): the exact score with DPX min/max.
   // Pixels that fail phase A keep score 0 — exactly what the full computation would give them.
   const int sx0 = max(3, L.ex0 - 1), sx1 = min(L.w - 3, L.ex1 + 1);
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   while (true) {
     if (qn >= 32 || (it0 >= nitems && qn > 0)) {
       // ---- phase B: exact score of up to 32 queued pairs, one pair per lane
+      unsigned cflag = 0, ccode = 0;  // bit 0 / 1: pixel x / x+1 is a corner inside the emission region
       if (lane < qn) {
         const unsigned code = q[(qhead + lane) & 127];
         const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
@@ -332,19 +335,24 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
         if (x < sx0 || x >= sx1) out16 &= 0xff00u;                // pixels outside the scored columns stay 0
         if (x + 1 < sx0 || x + 1 >= sx1) out16 &= 0x00ffu;
         *reinterpret_cast<unsigned short*>(sc0 + ry * SP + x) = (unsigned short)out16;
-        // remember non-zero scores inside the emission region for the sparse NMS pass (a few per warp call; ptxas
-        // aggregates the same-address shared atomics of a warp)
         const int y = sy_lo + ry;
         if (y >= ys && y < ye) {
-          const unsigned ccode = ((unsigned)(y - ys) << 12) | (unsigned)x;
-          if ((out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1) {
-            const int pos = atomicAdd(&s_cn, 1);
-            if (pos < kCornerList) s_clist[pos] = (unsigned short)ccode;
-          }
-          if ((out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1) {
-            const int pos = atomicAdd(&s_cn, 1);
-            if (pos < kCornerList) s_clist[pos] = (unsigned short)(ccode + 1u);
-          }
+          ccode = ((unsigned)(y - ys) << 12) | (unsigned)x;
+          cflag = (((out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1) ? 1u : 0u) |
+                  (((out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1) ? 2u : 0u);
+        }
+      }
+      // remember non-zero scores inside the emission region for the sparse NMS pass: one shared atomic per warp call
+      // (ballot + prefix popcount), not one per corner
+      {
+        const unsigned m0 = __ballot_sync(VSLAM_FULL, cflag & 1u), m1 = __ballot_sync(VSLAM_FULL, cflag & 2u);
+        if (m0 | m1) {
+          int base_pos = 0;
+          if (lane == 0) base_pos = atomicAdd(&s_cn, __popc(m0) + __popc(m1));
+          base_pos = __shfl_sync(VSLAM_FULL, base_pos, 0);
+          const int pos0 = base_pos + __popc(m0 & lt), pos1 = base_pos + __popc(m0) + __popc(m1 & lt);
+          if ((cflag & 1u) && pos0 < kCornerList) s_clist[pos0] = (unsigned short)ccode;
+          if ((cflag & 2u) && pos1 < kCornerList) s_clist[pos1] = (unsigned short)(ccode + 1u);
         }
       }
       const int done = min(qn, 32);
@@ -363,13 +371,24 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
     const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
     const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + SP3);
     const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - SP3);
+    const uint32_t* ru = reinterpret_cast<const uint32_t*>(base + 2 * SP);
+    const uint32_t* rd = reinterpret_cast<const uint32_t*>(base - 2 * SP);
+    const unsigned ua = ru[-1], ub = ru[0], uc = ru[1], da = rd[-1], db = rd[0], dc = rd[1];
     const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
+    const unsigned p2 = shifted4<2>(ua, ub, uc), p14 = shifted4<-2>(ua, ub, uc);
+    const unsigned p6 = shifted4<2>(da, db, dc), p10 = shifted4<-2>(da, db, dc);
     const unsigned a0 = __vabsdiffu4(p0, cw), a8 = __vabsdiffu4(p8, cw);
     const unsigned a4 = __vabsdiffu4(p4, cw), a12 = __vabsdiffu4(p12, cw);
-    // per byte v > t (t <= 127): bit 7 of ((v & 0x7f) + 127 - t) | v
-    const unsigned f08 = ((a0 & 0x7f7f7f7fu) + tadd) | a0 | ((a8 & 0x7f7f7f7fu) + tadd) | a8;
-    const unsigned f412 = ((a4 & 0x7f7f7f7fu) + tadd) | a4 | ((a12 & 0x7f7f7f7fu) + tadd) | a12;
-    const unsigned pass = (it0 + lane < nitems) ? (f08 & f412) : 0u;
+    const unsigned a2 = __vabsdiffu4(p2, cw), a10 = __vabsdiffu4(p10, cw);
+    const unsigned a6 = __vabsdiffu4(p6, cw), a14 = __vabsdiffu4(p14, cw);
+    // per byte "v > t" (t <= 127) as bit 7 of (v + 127 - t) | v.  The add is not masked per byte: a carry out of a
+    // byte with v >= 129 + t can only SET the flag of its neighbour (a false positive of a necessary test, i.e. one
+    // superfluous exact evaluation), and that byte's own flag is still set through "| v" (v >= 128).
+    const unsigned f08 = (a0 + tadd) | a0 | (a8 + tadd) | a8;
+    const unsigned f412 = (a4 + tadd) | a4 | (a12 + tadd) | a12;
+    const unsigned f210 = (a2 + tadd) | a2 | (a10 + tadd) | a10;
+    const unsigned f614 = (a6 + tadd) | a6 | (a14 + tadd) | a14;
+    const unsigned pass = (it0 + lane < nitems) ? (f08 & f412 & f210 & f614) : 0u;
     const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
     const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
     const unsigned code = ((unsigned)ry << 11) | ((unsigned)g << 1);
