@@ -211,23 +211,67 @@ __device__ __forceinline__ unsigned shifted4(unsigned a, unsigned b, unsigned c)
 __device__ __forceinline__ unsigned pair_lo(unsigned s) { return __byte_perm(s, 0u, 0x4140); }
 __device__ __forceinline__ unsigned pair_hi(unsigned s) { return __byte_perm(s, 0u, 0x4342); }
 
+// ---- shared-memory access by 32-bit shared-window address (plain LDS / STS with immediate offsets; generic
+//      pointers to shared arrays make ptxas re-derive the window base inside every loop)
+template <int OFF>
+__device__ __forceinline__ unsigned lds32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ unsigned lds16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds8(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts16(unsigned a, unsigned v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v));
+}
+
+constexpr int kFastThreads = 192;                   // 6 warps: one per 128-pixel column group of a 752-wide level
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastSeg = 7;                         // score rows per phase-A segment == depth of the register window
+constexpr int kFastQ = 512;                         // per-warp candidate ring (entries) >= 7 rows x 64 pairs + 31
+constexpr int kFastCL = 512;                        // per-warp pre-NMS corner list (entries)
+static_assert((VSLAM_FAST_ROWS + 2) % kFastSeg == 0, "score rows of a strip must be whole segments");
+static_assert(VSLAM_FAST_ROWS + 2 <= 32, "score row index is a 5-bit field of the queue entries");
+static_assert(kFastQ >= kFastSeg * 64 + 31, "candidate ring too small");
+
 // Shared-memory footprint of k_fast for a level of the given pitch.
 __host__ __device__ inline int fast_sp(int pitch) { return pitch + 32; }
 __host__ __device__ inline int fast_bw(int pitch) { return (pitch + 31) >> 5; }
 __host__ inline size_t fast_smem_bytes(int pitch) {
   size_t sp = fast_sp(pitch), bw = fast_bw(pitch);
-  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + 2 * VSLAM_FAST_ROWS * bw * 4 + 64;
+  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + 2 * VSLAM_FAST_ROWS * bw * 4 +
+         kFastWarps * (kFastQ + kFastCL) * 2 + 64;
 }
 
-// grid = (total_fast_strips, n_img), block = 256.
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
-                                              const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
-                                              int* __restrict__ strip_cnt, uint32_t* __restrict__ strip_rec) {
+// grid = (total_fast_strips, n_img), block = kFastThreads.  One block = one strip of VSLAM_FAST_ROWS emission rows of
+// one level of one image.
+//   staging   the strip's pixel rows (+-4) are copied global -> shared by the bulk-copy engine (cp.async.bulk, one
+//             instruction per row, completion on an mbarrier) while the threads clear the score tile
+//   phase A   every lane owns one group of 4 pixels and walks DOWN the strip with a 7-row window of raw words in
+//             registers (3 LDS per step): byte-SIMD necessary condition on 4 antipodal pairs of the circle; the pixel
+//             pairs that pass are appended to the warp's candidate ring (ballot compaction)
+//   phase B   whenever the ring holds >= 32 pairs (and once at the end) 32 lanes score 32 pairs exactly (DPX);
+//             non-zero scores go to the score tile and to the warp's pre-NMS corner list
+//   NMS       sparse, over the corner lists (full scan if a list overflowed), into a bitmask
+//   emission  popcount scan of the bitmask -> raster-ordered records (== cv::FAST's output order), no atomics, no sort
+__global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+                                                       const uint8_t* __restrict__ in_r,
+                                                       const uint8_t* __restrict__ pyr, int* __restrict__ strip_cnt,
+                                                       uint32_t* __restrict__ strip_rec) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int strip = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   int l = 0;
-  for (int k = 0; k < P.nlevels; ++k)
-    if (strip >= P.lv[k].fast_strip0 && strip < P.lv[k].fast_strip0 + P.lv[k].fast_nstrips) l = k;
+  for (int k = 1; k < P.nlevels; ++k)
+    if (strip >= P.lv[k].fast_strip0 && P.lv[k].fast_nstrips > 0) l = k;
   const LevelP& L = P.lv[l];
   const int s_local = strip - L.fast_strip0;
   const int ys = L.ey0 + s_local * VSLAM_FAST_ROWS;
@@ -236,203 +280,235 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
   int pitch;
   const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
   const int SP = fast_sp(pitch), BW = fast_bw(pitch);
-  uint8_t* pix = smem;                                   // (rows+8) x SP, image row ys-4+r at pix + r*SP + 16
-  uint8_t* sc = pix + (VSLAM_FAST_ROWS + 8) * SP;        // (rows+2) x SP, score row of image row ys-1+r
-  uint32_t* bits = reinterpret_cast<uint32_t*>(sc + (VSLAM_FAST_ROWS + 2) * SP);  // rows x BW corner bitmask
-  uint32_t* woff = bits + VSLAM_FAST_ROWS * BW;          // rows x BW exclusive corner offsets
-  __shared__ int s_total;
-  __shared__ int s_cn;  // number of pre-NMS corners pushed to the sparse-NMS list
-  if (tid == 0) s_cn = 0;  // ordered before the first push by the __syncthreads() that ends the staging
+  // layout (byte offsets into the dynamic shared memory)
+  const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*SP + 16
+  const int o_bits = o_sc + (VSLAM_FAST_ROWS + 2) * SP;      // score tile: image row ys-1+r at o_sc + r*SP + 16
+  const int o_woff = o_bits + VSLAM_FAST_ROWS * BW * 4;      // corner bitmask, then its exclusive popcount scan
+  const int o_q = o_woff + VSLAM_FAST_ROWS * BW * 4;         // per-warp candidate rings
+  const int o_cl = o_q + kFastWarps * kFastQ * 2;            // per-warp corner lists
+  const int o_misc = (o_cl + kFastWarps * kFastCL * 2 + 15) & ~15;  // mbarrier (8 B), list counts, total
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+  uint8_t* sc = smem + o_sc;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem + o_bits);
+  uint32_t* woff = reinterpret_cast<uint32_t*>(smem + o_woff);
+  int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 8);   // [kFastWarps] corner-list lengths
+  int* s_total = s_ccnt + kFastWarps;
+  const unsigned mbar = sbase + (unsigned)o_misc;
 
-  // ---- stage the pixel tile (128-bit loads), clear margins / score tile / bitmask
-  const int vpr = pitch >> 4;
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int r = warp; r < rows + 8; r += 8) {
-    const int gy = min(max(ys - 4 + r, 0), L.h - 1);
-    const uint4* srow = reinterpret_cast<const uint4*>(img_base + (size_t)gy * pitch);
-    uint4* drow = reinterpret_cast<uint4*>(pix + r * SP + 16);
-    for (int c = lane; c < vpr; c += 32) drow[c] = srow[c];
+  // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < (rows + 8) * 2; i += 256) {
-    int r = i >> 1;
-    *reinterpret_cast<uint4*>(pix + r * SP + ((i & 1) ? 16 + pitch : 0)) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)((rows + 8) * pitch))
+                   : "memory");
+    __syncwarp();
+    for (int r = lane; r < rows + 8; r += 32) {
+      const uint8_t* g = img_base + (size_t)(ys - 4 + r) * pitch;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       sbase + (unsigned)(r * SP + 16)),
+                   "l"(g), "r"((unsigned)pitch), "r"(mbar)
+                   : "memory");
+    }
   }
-  for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += 256)
+  for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * VSLAM_FAST_ROWS * BW; i += 256) bits[i] = 0;
+  for (int i = tid; i < 2 * VSLAM_FAST_ROWS * BW; i += kFastThreads) bits[i] = 0;
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mbar)
+          : "memory");
+  }
   __syncthreads();
 
-  // ---- scores on the emission region dilated by one pixel (clipped to FAST's own 3-px border).
-  // Phase A (every group of 4 pixels, byte-SIMD): a necessary condition for a FAST-9 corner — a 9-arc of the
-  //   16-circle contains at least one point of every antipodal pair {k, k+8}, so (|d_k|>t or |d_{k+8}|>t) must hold
-  //   for each pair; the four pairs k = 0, 2, 4, 6 are tested (22 % of the pixel pairs of the synthetic scenes
-  //   survive, against 38 % with two pairs and 10 % that contain a corner).  Pairs of pixels that pass are queued
-  //   per warp.
-  // Phase B (queued pairs only, 32 at a time so every lane is busy): the exact score with DPX min/max.
-  // Pixels that fail phase A keep score 0 — exactly what the full computation would give them.
+  // ---- scores on the emission region dilated by one pixel (always inside FAST's own 3-px border because ex0 >= 4).
+  // Phase A: a 9-arc of the 16-circle contains at least one point of every antipodal pair {k, k+8}, so
+  //   (|d_k| > t or |d_{k+8}| > t) must hold for each pair; the four pairs k = 0, 2, 4, 6 are tested (22 % of the pixel
+  //   pairs of the synthetic scenes survive, 10 % contain a corner).  Pixels that fail keep score 0 — exactly what the
+  //   full computation would give them.
   const int sx0 = max(3, L.ex0 - 1), sx1 = min(L.w - 3, L.ex1 + 1);
   const int sy_lo = max(3, ys - 1), sy_hi = min(L.h - 3, ye + 1);  // [sy_lo, sy_hi)
   const int gx0 = sx0 >> 2, ngx = ((sx1 - 1) >> 2) - gx0 + 1;
-  const int nsr = sy_hi - sy_lo;
+  const int nsr = sy_hi - sy_lo;                                   // <= VSLAM_FAST_ROWS + 2
   const unsigned t = (unsigned)P.fast_threshold;
   const unsigned t2 = t * 0x00010001u;
   const unsigned tadd = (127u - t) * 0x01010101u;  // fast_threshold <= 127 (checked by vslam_create)
   const unsigned lt = (1u << lane) - 1u;
-  constexpr int kCornerList = 2048;  // pre-NMS corners of a strip kept for the sparse NMS pass (else: full scan)
-  __shared__ unsigned short s_clist[kCornerList];  // (emission row << 12) | x   (row < 16, x < 4096)
-  __shared__ unsigned short s_queue[8][128];  // per-warp ring of queued pairs: (score row << 11) | (group << 1) | half
-  unsigned short* q = s_queue[warp];
-  int qn = 0, qhead = 0;  // warp-uniform
-  const int nitems = nsr * ngx;
-  const unsigned inv_ngx = (unsigned)((0x100000000ull + (unsigned)ngx - 1u) / (unsigned)ngx);  // exact for it < 65536
-  const uint8_t* const pix0 = pix + (sy_lo - (ys - 4)) * SP + 16;  // centre pixel of score row 0, group 0
-  uint8_t* const sc0 = sc + (sy_lo - (ys - 1)) * SP + 16;
-  const int SP3 = 3 * SP;
-  int it0 = warp * 32;
-#pragma unroll 1
-  while (true) {
-    if (qn >= 32 || (it0 >= nitems && qn > 0)) {
-      // ---- phase B: exact score of up to 32 queued pairs, one pair per lane
-      unsigned cflag = 0, ccode = 0;  // bit 0 / 1: pixel x / x+1 is a corner inside the emission region
-      if (lane < qn) {
-        const unsigned code = q[(qhead + lane) & 127];
-        const int half = code & 1, g = (code >> 1) & 0x3ff, ry = code >> 11;
-        const uint8_t* base = pix0 + ry * SP + 4 * g;
-        unsigned w[7][3];
+  const unsigned pix0 = sbase + (unsigned)((sy_lo - (ys - 4)) * SP + 16);  // centre pixel of score row 0, x = 0
+  const unsigned sc0 = sbase + (unsigned)(o_sc + (sy_lo - (ys - 1)) * SP + 16);
+  const unsigned qb = sbase + (unsigned)(o_q + warp * kFastQ * 2);
+  const unsigned clb = sbase + (unsigned)(o_cl + warp * kFastCL * 2);
+  int qn = 0, qhead = 0, cn = 0;  // warp-uniform: ring fill / head, corner-list length
+  const int ncg = (ngx + 31) >> 5;
+
+  // exact scores of up to 32 queued pairs, one pair per lane
+  auto phase_b = [&]() {
+    unsigned flag = 0, ccode = 0;
+    if (lane < qn) {
+      const unsigned code = lds16(qb + 2u * (unsigned)((qhead + lane) & (kFastQ - 1)));
+      const unsigned half = code & 1u, g4 = (code << 1) & 0xffcu, ry = code >> 11;  // g4 = 4 * group
+      const unsigned rowo = ry * (unsigned)SP + g4;
+      const unsigned a0 = pix0 + rowo - 3u * (unsigned)SP;
+      unsigned w[7][3];
 #pragma unroll
-        for (int dy = -3; dy <= 3; ++dy) {
-          const uint32_t* qq = reinterpret_cast<const uint32_t*>(base + dy * SP);
-          w[dy + 3][0] = qq[-1];
-          w[dy + 3][1] = qq[0];
-          w[dy + 3][2] = qq[1];
-        }
+      for (int j = 0; j < 7; ++j) {
+        const unsigned a = a0 + (unsigned)j * (unsigned)SP;
+        w[j][0] = lds32<-4>(a);
+        w[j][1] = lds32<0>(a);
+        w[j][2] = lds32<4>(a);
+      }
 #define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
-        unsigned sv[16];
-        sv[0] = shifted4<0>(VS_ROW(3));
-        sv[1] = shifted4<1>(VS_ROW(3));
-        sv[2] = shifted4<2>(VS_ROW(2));
-        sv[3] = shifted4<3>(VS_ROW(1));
-        sv[4] = shifted4<3>(VS_ROW(0));
-        sv[5] = shifted4<3>(VS_ROW(-1));
-        sv[6] = shifted4<2>(VS_ROW(-2));
-        sv[7] = shifted4<1>(VS_ROW(-3));
-        sv[8] = shifted4<0>(VS_ROW(-3));
-        sv[9] = shifted4<-1>(VS_ROW(-3));
-        sv[10] = shifted4<-2>(VS_ROW(-2));
-        sv[11] = shifted4<-3>(VS_ROW(-1));
-        sv[12] = shifted4<-3>(VS_ROW(0));
-        sv[13] = shifted4<-3>(VS_ROW(1));
-        sv[14] = shifted4<-2>(VS_ROW(2));
-        sv[15] = shifted4<-1>(VS_ROW(3));
+      unsigned sv[16];
+      sv[0] = shifted4<0>(VS_ROW(3));
+      sv[1] = shifted4<1>(VS_ROW(3));
+      sv[2] = shifted4<2>(VS_ROW(2));
+      sv[3] = shifted4<3>(VS_ROW(1));
+      sv[4] = shifted4<3>(VS_ROW(0));
+      sv[5] = shifted4<3>(VS_ROW(-1));
+      sv[6] = shifted4<2>(VS_ROW(-2));
+      sv[7] = shifted4<1>(VS_ROW(-3));
+      sv[8] = shifted4<0>(VS_ROW(-3));
+      sv[9] = shifted4<-1>(VS_ROW(-3));
+      sv[10] = shifted4<-2>(VS_ROW(-2));
+      sv[11] = shifted4<-3>(VS_ROW(-1));
+      sv[12] = shifted4<-3>(VS_ROW(0));
+      sv[13] = shifted4<-3>(VS_ROW(1));
+      sv[14] = shifted4<-2>(VS_ROW(2));
+      sv[15] = shifted4<-1>(VS_ROW(3));
 #undef VS_ROW
-        const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
-        unsigned p[16];
+      const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
+      unsigned p[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
-        const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
-        const int x = 4 * g + 2 * half;
-        unsigned out16 = __byte_perm(xs, 0u, 0x4420);            // (lane0, lane1) low bytes -> one u16
-        if (x < sx0 || x >= sx1) out16 &= 0xff00u;                // pixels outside the scored columns stay 0
-        if (x + 1 < sx0 || x + 1 >= sx1) out16 &= 0x00ffu;
-        *reinterpret_cast<unsigned short*>(sc0 + ry * SP + x) = (unsigned short)out16;
-        const int y = sy_lo + ry;
-        if (y >= ys && y < ye) {
-          ccode = ((unsigned)(y - ys) << 12) | (unsigned)x;
-          cflag = (((out16 & 0x00ffu) && x >= L.ex0 && x < L.ex1) ? 1u : 0u) |
-                  (((out16 & 0xff00u) && x + 1 >= L.ex0 && x + 1 < L.ex1) ? 2u : 0u);
-        }
-      }
-      // remember non-zero scores inside the emission region for the sparse NMS pass: one shared atomic per warp call
-      // (ballot + prefix popcount), not one per corner
-      {
-        const unsigned m0 = __ballot_sync(VSLAM_FULL, cflag & 1u), m1 = __ballot_sync(VSLAM_FULL, cflag & 2u);
-        if (m0 | m1) {
-          int base_pos = 0;
-          if (lane == 0) base_pos = atomicAdd(&s_cn, __popc(m0) + __popc(m1));
-          base_pos = __shfl_sync(VSLAM_FULL, base_pos, 0);
-          const int pos0 = base_pos + __popc(m0 & lt), pos1 = base_pos + __popc(m0) + __popc(m1 & lt);
-          if ((cflag & 1u) && pos0 < kCornerList) s_clist[pos0] = (unsigned short)ccode;
-          if ((cflag & 2u) && pos1 < kCornerList) s_clist[pos1] = (unsigned short)(ccode + 1u);
-        }
-      }
-      const int done = min(qn, 32);
-      qhead = (qhead + done) & 127;
-      qn -= done;
-      __syncwarp();
-      continue;
+      for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
+      const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
+      const unsigned out16 = __byte_perm(xs, 0u, 0x4420);                     // (lane0, lane1) low bytes -> one u16
+      const unsigned xo = g4 + 2u * half;
+      sts16(sc0 + ry * (unsigned)SP + xo, out16);
+      // corner-list entry: (score row << 11) | x; rows / columns outside the emission region are dropped by the NMS
+      ccode = (ry << 11) | xo;
+      flag = ((out16 & 0x00ffu) ? 1u : 0u) | ((out16 & 0xff00u) ? 2u : 0u);
     }
-    if (it0 >= nitems) break;
-    // ---- phase A: necessary condition on a group of 4 pixels (byte SIMD), queue the pairs that pass
-    const int it = min(it0 + lane, nitems - 1);
-    const int ry = (int)__umulhi((unsigned)it, inv_ngx);
-    const int g = gx0 + (it - ry * ngx);
-    const uint8_t* base = pix0 + ry * SP + 4 * g;
-    const uint32_t* rc = reinterpret_cast<const uint32_t*>(base);
-    const unsigned wa = rc[-1], cw = rc[0], wc = rc[1];
-    const unsigned p0 = *reinterpret_cast<const uint32_t*>(base + SP3);
-    const unsigned p8 = *reinterpret_cast<const uint32_t*>(base - SP3);
-    const uint32_t* ru = reinterpret_cast<const uint32_t*>(base + 2 * SP);
-    const uint32_t* rd = reinterpret_cast<const uint32_t*>(base - 2 * SP);
-    const unsigned ua = ru[-1], ub = ru[0], uc = ru[1], da = rd[-1], db = rd[0], dc = rd[1];
-    const unsigned p4 = shifted4<3>(wa, cw, wc), p12 = shifted4<-3>(wa, cw, wc);
-    const unsigned p2 = shifted4<2>(ua, ub, uc), p14 = shifted4<-2>(ua, ub, uc);
-    const unsigned p6 = shifted4<2>(da, db, dc), p10 = shifted4<-2>(da, db, dc);
-    const unsigned a0 = __vabsdiffu4(p0, cw), a8 = __vabsdiffu4(p8, cw);
-    const unsigned a4 = __vabsdiffu4(p4, cw), a12 = __vabsdiffu4(p12, cw);
-    const unsigned a2 = __vabsdiffu4(p2, cw), a10 = __vabsdiffu4(p10, cw);
-    const unsigned a6 = __vabsdiffu4(p6, cw), a14 = __vabsdiffu4(p14, cw);
-    // per byte "v > t" (t <= 127) as bit 7 of (v + 127 - t) | v.  The add is not masked per byte: a carry out of a
-    // byte with v >= 129 + t can only SET the flag of its neighbour (a false positive of a necessary test, i.e. one
-    // superfluous exact evaluation), and that byte's own flag is still set through "| v" (v >= 128).
-    const unsigned f08 = (a0 + tadd) | a0 | (a8 + tadd) | a8;
-    const unsigned f412 = (a4 + tadd) | a4 | (a12 + tadd) | a12;
-    const unsigned f210 = (a2 + tadd) | a2 | (a10 + tadd) | a10;
-    const unsigned f614 = (a6 + tadd) | a6 | (a14 + tadd) | a14;
-    const unsigned pass = (it0 + lane < nitems) ? (f08 & f412 & f210 & f614) : 0u;
-    const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
-    const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
-    const unsigned code = ((unsigned)ry << 11) | ((unsigned)g << 1);
-    const int tail = qhead + qn;
-    if (mlo & (1u << lane)) q[(tail + __popc(mlo & lt)) & 127] = (unsigned short)code;
-    if (mhi & (1u << lane)) q[(tail + __popc(mlo) + __popc(mhi & lt)) & 127] = (unsigned short)(code | 1u);
-    qn += __popc(mlo) + __popc(mhi);
-    it0 += 256;
+    const unsigned m0 = __ballot_sync(VSLAM_FULL, flag & 1u), m1 = __ballot_sync(VSLAM_FULL, flag & 2u);
+    const int n0 = __popc(m0), pos0 = cn + __popc(m0 & lt), pos1 = cn + n0 + __popc(m1 & lt);
+    if ((flag & 1u) && pos0 < kFastCL) sts16(clb + 2u * (unsigned)pos0, ccode);
+    if ((flag & 2u) && pos1 < kFastCL) sts16(clb + 2u * (unsigned)pos1, ccode + 1u);
+    cn += n0 + __popc(m1);
+    const int done = min(qn, 32);
+    qhead = (qhead + done) & (kFastQ - 1);
+    qn -= done;
     __syncwarp();
+  };
+
+  for (int cgi = warp; cgi < ncg; cgi += kFastWarps) {
+    const int gi = cgi * 32 + lane;
+    const bool has = gi < ngx;
+    const int g = gx0 + min(gi, ngx - 1);
+    // per-byte mask of the scored columns [sx0, sx1) of this group (only the first / last group is partial)
+    unsigned colmask = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (has && 4 * g + b >= sx0 && 4 * g + b < sx1) colmask |= 0x80u << (8 * b);
+    const unsigned codeg = (unsigned)g << 1;
+    unsigned arow = pix0 + 4u * (unsigned)g - 3u * (unsigned)SP;  // word b of pixel row (sy_lo - 3)
+    unsigned W[7][3];  // raw words (x-4, x, x+4) of the pixel rows y-3 .. y+3; every index is a compile-time constant
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      W[j][0] = lds32<-4>(arow);
+      W[j][1] = lds32<0>(arow);
+      W[j][2] = lds32<4>(arow);
+      arow += (unsigned)SP;
+    }
+#pragma unroll 1
+    for (int r0 = 0; r0 < nsr; r0 += kFastSeg) {
+#pragma unroll
+      for (int ph = 0; ph < kFastSeg; ++ph) {
+        // window slot of pixel row y-3+j is (ph + j) % 7
+#define WR(j, c) W[((ph) + (j)) % 7][c]
+        WR(6, 0) = lds32<-4>(arow);
+        WR(6, 1) = lds32<0>(arow);
+        WR(6, 2) = lds32<4>(arow);
+        arow += (unsigned)SP;
+        const unsigned cw = WR(3, 1);
+        const unsigned a0 = __vabsdiffu4(WR(6, 1), cw), a8 = __vabsdiffu4(WR(0, 1), cw);
+        const unsigned a4 = __vabsdiffu4(shifted4<3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
+        const unsigned a12 = __vabsdiffu4(shifted4<-3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
+        const unsigned a2 = __vabsdiffu4(shifted4<2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
+        const unsigned a14 = __vabsdiffu4(shifted4<-2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
+        const unsigned a6 = __vabsdiffu4(shifted4<2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
+        const unsigned a10 = __vabsdiffu4(shifted4<-2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
+#undef WR
+        // per byte "v > t" (t <= 127) as bit 7 of (v + 127 - t) | v.  The add is not masked per byte: a carry out of
+        // a byte with v >= 129 + t can only SET the flag of its neighbour (a false positive of a necessary test, i.e.
+        // one superfluous exact evaluation), and that byte's own flag is still set through "| v" (v >= 128).
+        const unsigned f08 = (a0 + tadd) | a0 | (a8 + tadd) | a8;
+        const unsigned f412 = (a4 + tadd) | a4 | (a12 + tadd) | a12;
+        const unsigned f210 = (a2 + tadd) | a2 | (a10 + tadd) | a10;
+        const unsigned f614 = (a6 + tadd) | a6 | (a14 + tadd) | a14;
+        const int ry = r0 + ph;
+        const unsigned pass = (ry < nsr) ? (f08 & f412 & f210 & f614 & colmask) : 0u;
+        const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
+        const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
+        const unsigned code = ((unsigned)ry << 11) | codeg;
+        const int tail = qhead + qn, nlo = __popc(mlo);
+        if (mlo & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + __popc(mlo & lt)) & (kFastQ - 1)), code);
+        if (mhi & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + nlo + __popc(mhi & lt)) & (kFastQ - 1)), code | 1u);
+        qn += nlo + __popc(mhi);
+      }
+      __syncwarp();
+      while (qn >= 32) phase_b();
+    }
   }
+  while (qn > 0) phase_b();
+  if (lane == 0) s_ccnt[warp] = cn;
   __syncthreads();
 
   // ---- non-maximum suppression (strictly greater than the 8 neighbours) + runByImageBorder
-  const int ncorn = s_cn;
-  if (ncorn <= kCornerList) {
-    for (int i = tid; i < ncorn; i += 256) {
-      const unsigned code = s_clist[i];
-      const int ry = (int)(code >> 12), x = (int)(code & 0xfffu);
-      const uint8_t* c = sc + (ry + 1) * SP + 16 + x;
-      const int v = c[0];
-      const bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
-                        v > c[SP] && v > c[SP + 1];
-      if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+  bool sparse = L.w <= 2048;  // x is an 11-bit field of the corner-list entries
+#pragma unroll
+  for (int w = 0; w < kFastWarps; ++w) sparse = sparse && s_ccnt[w] <= kFastCL;
+  if (sparse) {
+    const int ry_lo = ys - sy_lo, ry_hi = ye - sy_lo;  // score rows that are emission rows: [ry_lo, ry_hi)
+    for (int w = 0; w < kFastWarps; ++w) {
+      const int n = s_ccnt[w];
+      for (int i = tid; i < n; i += kFastThreads) {
+        const unsigned code = lds16(sbase + (unsigned)(o_cl + (w * kFastCL + i) * 2));
+        const int ry = (int)(code >> 11), x = (int)(code & 0x7ffu);
+        if (ry < ry_lo || ry >= ry_hi || x < L.ex0 || x >= L.ex1) continue;
+        const int er = ry - ry_lo;  // emission row
+        const uint8_t* c = sc + (er + 1) * SP + 16 + x;
+        const int v = c[0];
+        const bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
+                          v > c[SP] && v > c[SP + 1];
+        if (keep) atomicOr(&bits[er * BW + (x >> 5)], 1u << (x & 31));
+      }
     }
   } else {
-  const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
-  const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
-  for (int it = tid; it < rows * negx; it += 256) {
-    const int ry = (int)__umulhi((unsigned)it, inv_negx);
-    const int g = egx0 + (it - ry * negx);
-    const uint8_t* srow = sc + (ry + 1) * SP + 16;
-    unsigned word = *reinterpret_cast<const uint32_t*>(srow + 4 * g);
-    if (word == 0) continue;
+    const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
+    const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
+    for (int it = tid; it < rows * negx; it += kFastThreads) {
+      const int ry = (int)__umulhi((unsigned)it, inv_negx);
+      const int g = egx0 + (it - ry * negx);
+      const uint8_t* srow = sc + (ry + 1) * SP + 16;
+      unsigned word = *reinterpret_cast<const uint32_t*>(srow + 4 * g);
+      if (word == 0) continue;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int v = (word >> (8 * k)) & 0xff;
-      int x = 4 * g + k;
-      if (v == 0 || x < L.ex0 || x >= L.ex1) continue;
-      const uint8_t* c = srow + x;
-      bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
-                  v > c[SP] && v > c[SP + 1];
-      if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+      for (int k = 0; k < 4; ++k) {
+        int v = (word >> (8 * k)) & 0xff;
+        int x = 4 * g + k;
+        if (v == 0 || x < L.ex0 || x >= L.ex1) continue;
+        const uint8_t* c = srow + x;
+        bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
+                    v > c[SP] && v > c[SP + 1];
+        if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+      }
     }
-  }
   }
   __syncthreads();
 
@@ -455,11 +531,11 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
       woff[i] = run;
       run += __popc(bits[i]);
     }
-    if (tid == 31) s_total = incl;
+    if (tid == 31) *s_total = incl;
   }
   __syncthreads();
   uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
-  for (int wi = tid; wi < nwords; wi += 256) {
+  for (int wi = tid; wi < nwords; wi += kFastThreads) {
     unsigned bw = bits[wi];
     if (!bw) continue;
     int off = woff[wi];
@@ -473,7 +549,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ PyrP P, co
       out[off++] = (score << 24) | ((unsigned)(ys + ry) << 12) | (unsigned)x;
     }
   }
-  if (tid == 0) strip_cnt[(long long)img * P.total_fast_strips + strip] = s_total;
+  if (tid == 0) strip_cnt[(long long)img * P.total_fast_strips + strip] = *s_total;
 }
 
 // ----------------------------------------------------------------------------------------------------------

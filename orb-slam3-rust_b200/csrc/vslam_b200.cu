@@ -421,7 +421,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   if (P.total_fast_strips > 0) {
     dim3 grid(P.total_fast_strips, nimg);
-    vk::k_fast<<<grid, 256, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)), st>>>(P, in_l, in_r, s.d_pyr,
+    vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)), st>>>(P, in_l, in_r, s.d_pyr,
                                                                                       s.d_strip_cnt, s.d_strip_rec);
     h->launches++;
   }
@@ -937,7 +937,7 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
     Pr.lv[0].pitch = h->last_pitch;
     Pr.in_frame_stride = h->last_frame_stride;
     dim3 grid(Pr.total_fast_strips, h->last_frames * h->last_eyes);
-    vk::k_fast<<<grid, 256, vk::fast_smem_bytes(std::max(h->last_pitch, h->P.in_pitch)), s.stream>>>(
+    vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(h->last_pitch, h->P.in_pitch)), s.stream>>>(
         Pr, h->last_in_l, h->last_in_r, s.d_pyr, s.d_strip_cnt, s.d_strip_rec);
     h->launches++;
     CU_TRY(h, cudaStreamSynchronize(s.stream));
