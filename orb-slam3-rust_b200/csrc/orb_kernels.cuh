@@ -293,10 +293,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
   uint32_t* woff = reinterpret_cast<uint32_t*>(smem + o_woff);
   int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 8);   // [kFastWarps] corner-list lengths
   int* s_total = s_ccnt + kFastWarps;
+  int* s_next = s_total + 1;                                 // dynamic work-item counter of phase A
   const unsigned mbar = sbase + (unsigned)o_misc;
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
   if (tid == 0) {
+    *s_next = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -406,7 +408,15 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
     __syncwarp();
   };
 
-  for (int cgi = warp; cgi < ncg; cgi += kFastWarps) {
+  // Work items = (32-group column block, 7-row segment), handed out dynamically (one shared atomic per item) so that
+  // the warps of a block finish together whatever the level width; every item refills its register window (6 rows).
+  const int nseg = (nsr + kFastSeg - 1) / kFastSeg, nitems = ncg * nseg;
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(s_next, 1);
+    item = __shfl_sync(VSLAM_FULL, item, 0);
+    if (item >= nitems) break;
+    const int seg = item / ncg, cgi = item - seg * ncg, r0 = seg * kFastSeg;
     const int gi = cgi * 32 + lane;
     const bool has = gi < ngx;
     const int g = gx0 + min(gi, ngx - 1);
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
     for (int b = 0; b < 4; ++b)
       if (has && 4 * g + b >= sx0 && 4 * g + b < sx1) colmask |= 0x80u << (8 * b);
     const unsigned codeg = (unsigned)g << 1;
-    unsigned arow = pix0 + 4u * (unsigned)g - 3u * (unsigned)SP;  // word b of pixel row (sy_lo - 3)
+    unsigned arow = pix0 + 4u * (unsigned)g + (unsigned)((r0 - 3) * SP);  // word b of pixel row (sy_lo + r0 - 3)
     unsigned W[7][3];  // raw words (x-4, x, x+4) of the pixel rows y-3 .. y+3; every index is a compile-time constant
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -425,45 +435,42 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
       W[j][2] = lds32<4>(arow);
       arow += (unsigned)SP;
     }
-#pragma unroll 1
-    for (int r0 = 0; r0 < nsr; r0 += kFastSeg) {
 #pragma unroll
-      for (int ph = 0; ph < kFastSeg; ++ph) {
-        // window slot of pixel row y-3+j is (ph + j) % 7
+    for (int ph = 0; ph < kFastSeg; ++ph) {
+      // window slot of pixel row y-3+j is (ph + j) % 7
 #define WR(j, c) W[((ph) + (j)) % 7][c]
-        WR(6, 0) = lds32<-4>(arow);
-        WR(6, 1) = lds32<0>(arow);
-        WR(6, 2) = lds32<4>(arow);
-        arow += (unsigned)SP;
-        const unsigned cw = WR(3, 1);
-        const unsigned a0 = __vabsdiffu4(WR(6, 1), cw), a8 = __vabsdiffu4(WR(0, 1), cw);
-        const unsigned a4 = __vabsdiffu4(shifted4<3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
-        const unsigned a12 = __vabsdiffu4(shifted4<-3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
-        const unsigned a2 = __vabsdiffu4(shifted4<2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
-        const unsigned a14 = __vabsdiffu4(shifted4<-2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
-        const unsigned a6 = __vabsdiffu4(shifted4<2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
-        const unsigned a10 = __vabsdiffu4(shifted4<-2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
+      WR(6, 0) = lds32<-4>(arow);
+      WR(6, 1) = lds32<0>(arow);
+      WR(6, 2) = lds32<4>(arow);
+      arow += (unsigned)SP;
+      const unsigned cw = WR(3, 1);
+      const unsigned a0 = __vabsdiffu4(WR(6, 1), cw), a8 = __vabsdiffu4(WR(0, 1), cw);
+      const unsigned a4 = __vabsdiffu4(shifted4<3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
+      const unsigned a12 = __vabsdiffu4(shifted4<-3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
+      const unsigned a2 = __vabsdiffu4(shifted4<2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
+      const unsigned a14 = __vabsdiffu4(shifted4<-2>(WR(5, 0), WR(5, 1), WR(5, 2)), cw);
+      const unsigned a6 = __vabsdiffu4(shifted4<2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
+      const unsigned a10 = __vabsdiffu4(shifted4<-2>(WR(1, 0), WR(1, 1), WR(1, 2)), cw);
 #undef WR
-        // per byte "v > t" (t <= 127) as bit 7 of (v + 127 - t) | v.  The add is not masked per byte: a carry out of
-        // a byte with v >= 129 + t can only SET the flag of its neighbour (a false positive of a necessary test, i.e.
-        // one superfluous exact evaluation), and that byte's own flag is still set through "| v" (v >= 128).
-        const unsigned f08 = (a0 + tadd) | a0 | (a8 + tadd) | a8;
-        const unsigned f412 = (a4 + tadd) | a4 | (a12 + tadd) | a12;
-        const unsigned f210 = (a2 + tadd) | a2 | (a10 + tadd) | a10;
-        const unsigned f614 = (a6 + tadd) | a6 | (a14 + tadd) | a14;
-        const int ry = r0 + ph;
-        const unsigned pass = (ry < nsr) ? (f08 & f412 & f210 & f614 & colmask) : 0u;
-        const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
-        const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
-        const unsigned code = ((unsigned)ry << 11) | codeg;
-        const int tail = qhead + qn, nlo = __popc(mlo);
-        if (mlo & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + __popc(mlo & lt)) & (kFastQ - 1)), code);
-        if (mhi & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + nlo + __popc(mhi & lt)) & (kFastQ - 1)), code | 1u);
-        qn += nlo + __popc(mhi);
-      }
-      __syncwarp();
-      while (qn >= 32) phase_b();
+      // per byte "v > t" (t <= 127) as bit 7 of (v + 127 - t) | v.  The add is not masked per byte: a carry out of
+      // a byte with v >= 129 + t can only SET the flag of its neighbour (a false positive of a necessary test, i.e.
+      // one superfluous exact evaluation), and that byte's own flag is still set through "| v" (v >= 128).
+      const unsigned f08 = (a0 + tadd) | a0 | (a8 + tadd) | a8;
+      const unsigned f412 = (a4 + tadd) | a4 | (a12 + tadd) | a12;
+      const unsigned f210 = (a2 + tadd) | a2 | (a10 + tadd) | a10;
+      const unsigned f614 = (a6 + tadd) | a6 | (a14 + tadd) | a14;
+      const int ry = r0 + ph;
+      const unsigned pass = (ry < nsr) ? (f08 & f412 & f210 & f614 & colmask) : 0u;
+      const unsigned mlo = __ballot_sync(VSLAM_FULL, (pass & 0x00008080u) != 0u);
+      const unsigned mhi = __ballot_sync(VSLAM_FULL, (pass & 0x80800000u) != 0u);
+      const unsigned code = ((unsigned)ry << 11) | codeg;
+      const int tail = qhead + qn, nlo = __popc(mlo);
+      if (mlo & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + __popc(mlo & lt)) & (kFastQ - 1)), code);
+      if (mhi & (1u << lane)) sts16(qb + 2u * (unsigned)((tail + nlo + __popc(mhi & lt)) & (kFastQ - 1)), code | 1u);
+      qn += nlo + __popc(mhi);
     }
+    __syncwarp();
+    while (qn >= 32) phase_b();
   }
   while (qn > 0) phase_b();
   if (lane == 0) s_ccnt[warp] = cn;

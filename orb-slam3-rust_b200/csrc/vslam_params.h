@@ -4,7 +4,9 @@
 #include <stdint.h>
 
 #define VSLAM_MAX_LEVELS 12
+#ifndef VSLAM_FAST_ROWS
 #define VSLAM_FAST_ROWS 26      // emission rows per FAST strip (+ 2 dilation rows = 4 phase-A segments of 7)
+#endif
 #define VSLAM_RESIZE_ROWS 32    // destination rows of one resize lane item (4 columns wide)
 #define VSLAM_BLUR_ROWS 64      // max output rows of one blur lane item (8 columns wide)
 #define VSLAM_DESC_BYTES 32

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvslam_b200.so")
+LIB_PATH = os.environ.get("VSLAM_B200_LIB") or os.path.join(_HERE, "libvslam_b200.so")  # env: A/B builds of the same ABI
 
 ABI_VERSION = 1
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_CAPACITY, ERR_KEYPOINT_OVERFLOW, ERR_OUT_OF_MEMORY = range(6)
