@@ -247,7 +247,7 @@ __host__ __device__ inline int fast_sp(int pitch) { return pitch + 32; }
 __host__ __device__ inline int fast_bw(int pitch) { return (pitch + 31) >> 5; }
 __host__ inline size_t fast_smem_bytes(int pitch) {
   size_t sp = fast_sp(pitch), bw = fast_bw(pitch);
-  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + 2 * VSLAM_FAST_ROWS * bw * 4 +
+  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + VSLAM_FAST_ROWS * bw * 4 +
          kFastWarps * (kFastQ + kFastCL) * 2 + 64;
 }
 
@@ -283,17 +283,14 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
   // layout (byte offsets into the dynamic shared memory)
   const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*SP + 16
   const int o_bits = o_sc + (VSLAM_FAST_ROWS + 2) * SP;      // score tile: image row ys-1+r at o_sc + r*SP + 16
-  const int o_woff = o_bits + VSLAM_FAST_ROWS * BW * 4;      // corner bitmask, then its exclusive popcount scan
-  const int o_q = o_woff + VSLAM_FAST_ROWS * BW * 4;         // per-warp candidate rings
+  const int o_q = o_bits + VSLAM_FAST_ROWS * BW * 4;         // corner bitmask; then the per-warp candidate rings
   const int o_cl = o_q + kFastWarps * kFastQ * 2;            // per-warp corner lists
   const int o_misc = (o_cl + kFastWarps * kFastCL * 2 + 15) & ~15;  // mbarrier (8 B), list counts, total
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   uint8_t* sc = smem + o_sc;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + o_bits);
-  uint32_t* woff = reinterpret_cast<uint32_t*>(smem + o_woff);
   int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 8);   // [kFastWarps] corner-list lengths
-  int* s_total = s_ccnt + kFastWarps;
-  int* s_next = s_total + 1;                                 // dynamic work-item counter of phase A
+  int* s_next = s_ccnt + kFastWarps;                               // dynamic work-item counter of phase A
   const unsigned mbar = sbase + (unsigned)o_misc;
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
   }
   for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * VSLAM_FAST_ROWS * BW; i += kFastThreads) bits[i] = 0;
+  for (int i = tid; i < VSLAM_FAST_ROWS * BW; i += kFastThreads) bits[i] = 0;
   {
     unsigned done = 0;
     while (!done)
@@ -519,44 +516,43 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ P
   }
   __syncthreads();
 
-  // ---- raster-ordered emission: exclusive scan of the bitmask popcounts by warp 0, then every thread
-  //      expands its words.  Order inside the strip == (y, x) == cv::FAST's output order.
+  // ---- raster-ordered emission.  Order inside the strip == (y, x) == cv::FAST's output order.  The bitmask words are
+  //      cut into 32 chunks; EVERY warp scans the chunk popcounts (redundantly: no single-warp phase, no extra
+  //      barrier), then lane j of warp w expands the words of chunk j that fall to warp w, carrying the running
+  //      offset through the chunk.
   const int nwords = rows * BW;
-  if (tid < 32) {
+  {
     const int per = (nwords + 31) >> 5;
-    const int b = tid * per, e = min(b + per, nwords);
+    const int b = lane * per, e = min(b + per, nwords);
     int sum = 0;
     for (int i = b; i < e; ++i) sum += __popc(bits[i]);
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int o = __shfl_up_sync(VSLAM_FULL, incl, d);
-      if (tid >= d) incl += o;
+      if (lane >= d) incl += o;
     }
     int run = incl - sum;
+    uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
     for (int i = b; i < e; ++i) {
-      woff[i] = run;
-      run += __popc(bits[i]);
+      unsigned bw = bits[i];
+      const int cnt = __popc(bw);
+      if (bw && (i - b) % kFastWarps == warp) {
+        int off = run;
+        const int ry = i / BW;
+        const int xb = (i - ry * BW) << 5;
+        while (bw) {
+          const int bpos = __ffs(bw) - 1;
+          bw &= bw - 1;
+          const int x = xb + bpos;
+          const unsigned score = (unsigned)sc[(ry + 1) * SP + 16 + x] + (unsigned)P.fast_threshold - 1u;  // S-1 <= 254
+          out[off++] = (score << 24) | ((unsigned)(ys + ry) << 12) | (unsigned)x;
+        }
+      }
+      run += cnt;
     }
-    if (tid == 31) *s_total = incl;
+    if (tid == 31) strip_cnt[(long long)img * P.total_fast_strips + strip] = incl;
   }
-  __syncthreads();
-  uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
-  for (int wi = tid; wi < nwords; wi += kFastThreads) {
-    unsigned bw = bits[wi];
-    if (!bw) continue;
-    int off = woff[wi];
-    const int ry = wi / BW;
-    const int xb = (wi - ry * BW) << 5;
-    while (bw) {
-      int b = __ffs(bw) - 1;
-      bw &= bw - 1;
-      int x = xb + b;
-      unsigned score = (unsigned)sc[(ry + 1) * SP + 16 + x] + (unsigned)P.fast_threshold - 1u;  // S - 1 <= 254
-      out[off++] = (score << 24) | ((unsigned)(ys + ry) << 12) | (unsigned)x;
-    }
-  }
-  if (tid == 0) strip_cnt[(long long)img * P.total_fast_strips + strip] = *s_total;
 }
 
 // ----------------------------------------------------------------------------------------------------------
