@@ -21,6 +21,13 @@
 #include "select_serial.h"
 #include "vslam_params.h"
 
+#ifndef VSLAM_BLUR_MINB
+#define VSLAM_BLUR_MINB 3
+#endif
+#ifndef VSLAM_RESIZE_MINB
+#define VSLAM_RESIZE_MINB 7
+#endif
+
 namespace vk {
 
 #define VSLAM_FULL 0xffffffffu
@@ -78,7 +85,7 @@ __device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int im
 // grid = (ceil(ceil(w/4) * nstr / 128), n_img), block = 128; items are numbered column-group fastest.
 // ----------------------------------------------------------------------------------------------------------
 constexpr int kResizePrefetchRows = 8;  // source rows between the L2 prefetch and the register load
-__global__ void __launch_bounds__(128) k_resize(const __grid_constant__ PyrP P, int l, int rs,
+__global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_constant__ PyrP P, int l, int rs,
                                                 const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
                                                 uint8_t* __restrict__ pyr, const uint32_t* __restrict__ coef) {
   const LevelP& D = P.lv[l];
@@ -915,8 +922,8 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
   return d;
 }
 
-constexpr int kBlurPrefetchRows = 6;  // source rows between the L2 prefetch and the register load
-__global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+constexpr int kBlurRing = 8;  // source rows in flight per lane (cp.async ring in shared memory)
+__global__ void __launch_bounds__(128, VSLAM_BLUR_MINB) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                               const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
   const int img = blockIdx.y;
@@ -960,35 +967,54 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
   const uint8_t* ps = src + ((e - 3) & ~3);
   const int ps2 = sh ? 4 : 0;
   int hm1 = L.h - 1, dpitch = L.pitch;
-  unsigned pfmax = (unsigned)hm1 * (unsigned)spitch;  // prefetches stay inside the level
   // Loop invariants must live in registers: under register pressure ptxas otherwise re-derives them inside the row
   // loop through indexed constant-bank loads (LDC c[0x0][R+..], long-scoreboard latency in front of every SHF / PRMT).
   unsigned shv = sh;
-  asm volatile("" : "+r"(hm1), "+r"(dpitch), "+r"(shv), "+r"(spitch), "+r"(pfmax));
+  asm volatile("" : "+r"(hm1), "+r"(dpitch), "+r"(shv), "+r"(spitch));
   asm volatile("" : "+r"(sel[0]), "+r"(sel[1]), "+r"(sel[2]), "+r"(sel[3]));
   asm volatile("" : "+l"(dst));
 
-  // Raw loads of source row t (4 window words + the 2 words holding S for right-edge lanes); fix_row applies the
-  // border selectors when the row is consumed, two rows later, so that no instruction waits on a load right after
-  // issuing it (prefetch distance 2 covers a DRAM miss at 3 warps per scheduler).
-  auto load_row = [&](int t, unsigned (&w)[6]) {
+  // Source rows reach the lane through a private ring in shared memory filled by cp.async (LDGSTS: global -> shared
+  // without a register, kBlurRing rows in flight per lane — enough for a DRAM miss, which two rows of register
+  // prefetch were not).  Per row: 4 window words (16 B, read back as one conflict-free LDS.128) + for right-edge lanes
+  // the 2 words that hold S.  issue_row(t) enqueues source row t into slot t % kBlurRing as one commit group;
+  // take_row() waits for the oldest group and applies the border selectors.
+  __shared__ __align__(16) uint4 s_ring[kBlurRing][128];
+  __shared__ __align__(8) uint2 s_ringS[kBlurRing][128];
+  const unsigned ring0 = (unsigned)__cvta_generic_to_shared(&s_ring[0][threadIdx.x]);
+  const unsigned ringS0 = (unsigned)__cvta_generic_to_shared(&s_ringS[0][threadIdx.x]);
+  auto issue_row = [&](int t, int slot) {
     // reflect-101 of yy = y0 - 3 + t (|yy| mirrors the top, (h-1) - |(h-1) - .| the bottom), clamped for the rows
     // past the mirror that feed no stored output
     const int gy = max(hm1 - abs(hm1 - abs(y0 - 3 + t)), 0);
     const unsigned ro = (unsigned)gy * (unsigned)spitch;
+    const unsigned d = ring0 + (unsigned)slot * (unsigned)(128 * sizeof(uint4));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = *reinterpret_cast<const uint32_t*>(pw[k] + ro);
-    prefetch_l2(pw[1] + min(ro + (unsigned)(kBlurPrefetchRows * spitch), pfmax));
-    w[4] = w[5] = 0;
+    for (int k = 0; k < 4; ++k)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * k), "l"(pw[k] + ro) : "memory");
     if (redge) {
-      w[4] = *reinterpret_cast<const uint32_t*>(ps + ro);
-      w[5] = *reinterpret_cast<const uint32_t*>(ps + ro + ps2);
+      const unsigned ds = ringS0 + (unsigned)slot * (unsigned)(128 * sizeof(uint2));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds), "l"(ps + ro) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds + 4u), "l"(ps + ro + ps2) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto fix_row = [&](const unsigned (&r)[6], unsigned (&w)[4]) {
-    const unsigned S = __funnelshift_r(r[4], r[5], shv);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = __byte_perm(r[k], S, sel[k]);
+  auto take_row = [&](int slot, unsigned (&w)[4]) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kBlurRing - 1) : "memory");
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(ring0 + (unsigned)slot * (unsigned)(128 * sizeof(uint4))));
+    unsigned sA = 0, sB = 0;
+    if (redge)
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                   : "=r"(sA), "=r"(sB)
+                   : "r"(ringS0 + (unsigned)slot * (unsigned)(128 * sizeof(uint2))));
+    const unsigned S = __funnelshift_r(sA, sB, shv);
+    w[0] = __byte_perm(r.x, S, sel[0]);
+    w[1] = __byte_perm(r.y, S, sel[1]);
+    w[2] = __byte_perm(r.z, S, sel[2]);
+    w[3] = __byte_perm(r.w, S, sel[3]);
   };
 
   const f32x2_t K0 = pk2(0x1.1f5f62p-4f, 0x1.1f5f62p-4f), K1 = pk2(0x1.0c70fcp-3f, 0x1.0c70fcp-3f);
@@ -1021,31 +1047,28 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
   };
 
   f32x2_t win[7][4];  // row-pass results of the last 7 source rows; every index is a compile-time constant
-  unsigned r0[6], r1[6];  // raw words of source rows t and t+1
-  load_row(0, r0);
-  load_row(1, r1);
+  static_assert(kBlurRing == 8, "slot arithmetic below assumes a ring of 8 rows");
+#pragma unroll
+  for (int t = 0; t < kBlurRing; ++t) issue_row(t, t);
 #pragma unroll
   for (int t = 0; t < 6; ++t) {  // fill the window: source rows 0..5 of the item
-    unsigned r2[6], cw[4];
-    load_row(t + 2, r2);
-    fix_row(r0, cw);
+    unsigned cw[4];
+    take_row(t, cw);
     row_pass(cw, win[t]);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      r0[k] = r1[k];
-      r1[k] = r2[k];
-    }
+    issue_row(t + kBlurRing, t);  // the slot is free once its words sit in registers (row_pass consumed them)
   }
+  int slot = 6;  // ring slot of source row t (t & 7), carried because 7 rows per trip do not divide the ring
 #pragma unroll 1
   for (int blk = 0; blk < nblk; ++blk) {
     const int tb = 6 + 7 * blk;
 #pragma unroll
     for (int ph = 0; ph < 7; ++ph) {
       const int t = tb + ph;          // source row of the item; window slot (6 + ph) % 7
-      unsigned r2[6], cw[4];
-      load_row(t + 2, r2);            // software prefetch, two rows ahead
-      fix_row(r0, cw);
+      unsigned cw[4];
+      take_row(slot, cw);
       row_pass(cw, win[(6 + ph) % 7]);
+      issue_row(t + kBlurRing, slot);
+      slot = (slot + 1) & (kBlurRing - 1);
       // column pass of output row t - 6: source rows t-6 .. t live in slots (ph + j) % 7, j = 0..6
       unsigned b[8];
 #pragma unroll
@@ -1060,13 +1083,9 @@ __global__ void __launch_bounds__(128) k_blur(const __grid_constant__ PyrP P, co
       o.x = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
       o.y = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
       if (t - 6 < rs) *reinterpret_cast<uint2*>(dst + (unsigned)(t - 6) * (unsigned)dpitch) = o;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        r0[k] = r1[k];
-        r1[k] = r2[k];
-      }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain the look-ahead rows before the block's memory is reused
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -110,6 +110,33 @@ def test_stage_pyramid_fast_blur(sp752, oracle, pairs):
             assert np.array_equal(c, ref), f"fast corners level {lvl} (raster order, scores)"
 
 
+@pytest.mark.parametrize("w,h,nfeat,fast_t", [(641, 479, 800, 20), (333, 255, 300, 7), (1001, 403, 1500, 35),
+                                              (260, 258, 200, 20)])
+def test_stage_parity_odd_sizes(oracle, camera_dict, w, h, nfeat, fast_t):
+    """Widths / heights that are not multiples of 4, 8 or 16 and other FAST thresholds: exercises the border selectors
+    of k_blur, the clamped word offsets of k_resize, the partial column groups / strips of k_fast."""
+    from vslam_b200 import STAGE_BLURRED, STAGE_PYRAMID, CameraModel, StereoProcessor, synth
+
+    l, r = synth.make_stereo_pair(11, w, h)
+    l, r = l.numpy(), r.numpy()
+    with StereoProcessor(CameraModel(**camera_dict), nfeat, w, h, max_batch=1, fast_threshold=fast_t) as sp:
+        fr = sp.process(l, r)
+        for eye, img in enumerate((l, r)):
+            st = oracle.detect_stages(img, nfeat, fast_threshold=fast_t)
+            for lvl in range(8):
+                assert np.array_equal(sp.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
+                assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, eye, lvl), st["blurred"][lvl]), f"blur {lvl}"
+                c = sp.debug_fast_corners(eye, lvl)
+                o = st["fast"][lvl]
+                ref = np.stack([o["x"], o["y"], o["resp"].astype(np.int32)], 1)
+                assert np.array_equal(c, ref), f"fast corners level {lvl}"
+        kl, dl = oracle.detect_and_compute(l, nfeat, fast_threshold=fast_t)
+        kr, dr = oracle.detect_and_compute(r, nfeat, fast_threshold=fast_t)
+        assert_struct_equal(fr.left_features.keypoints, kl, "left keypoints")
+        assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
+        assert np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
+
+
 # ------------------------------------------------------------------ batch pipeline (chunks, slots, strides)
 def test_batch_multi_chunk_equals_per_frame(sp752, oracle, pairs, camera_dict):
     seeds = list(range(20, 31))  # 11 frames, max_batch 4 -> chunks 4/4/3 over 3 slots
