@@ -84,7 +84,7 @@ __device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int im
 // prefetched while the current one is processed.
 // grid = (ceil(ceil(w/4) * nstr / 128), n_img), block = 128; items are numbered column-group fastest.
 // ----------------------------------------------------------------------------------------------------------
-constexpr int kResizePrefetchRows = 8;  // source rows between the L2 prefetch and the register load
+constexpr int kResizeRing = 8;  // source rows in flight per lane (cp.async ring in shared memory)
 __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_constant__ PyrP P, int l, int rs,
                                                 const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
                                                 uint8_t* __restrict__ pyr, const uint32_t* __restrict__ coef) {
@@ -129,14 +129,35 @@ __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_
   }
   const int shm1 = S.h - 1, swm1 = S.w - 1;
 
-  auto load_raw = [&](int sy, unsigned (&u)[3]) {
-    const uint8_t* rp = src + (size_t)min(sy, shm1) * spitch;
+  // Source rows reach the lane through a private ring in shared memory filled by cp.async (global -> shared without a
+  // register): kResizeRing consecutive source rows are in flight per lane, starting at the first row the item needs.
+  // Row s of the item lives in slot s % kResizeRing as one 16-byte record (3 words used), read back with one LDS.128.
+  __shared__ __align__(16) uint4 s_ring[kResizeRing][128];
+  const unsigned ring0 = (unsigned)__cvta_generic_to_shared(&s_ring[0][threadIdx.x]);
+  const int srow0 = (int)(yc[0] & 0xffffu);       // first source row of the item
+  const uint8_t* gp[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) u[j] = *reinterpret_cast<const uint32_t*>(rp + wo[j]);
+  for (int j = 0; j < 3; ++j) gp[j] = src + (size_t)srow0 * spitch + wo[j];
+  int issued = 0;                                  // source rows enqueued so far (relative to srow0)
+  auto issue_next = [&]() {
+    const unsigned d = ring0 + (unsigned)(issued & (kResizeRing - 1)) * (unsigned)(128 * sizeof(uint4));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * j), "l"(gp[j]) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (srow0 + issued < shm1) {  // rows past the last one re-read the last row (never consumed with weight > 0)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gp[j] += spitch;
+    }
+    ++issued;
   };
-  auto hcalc = [&](int sy, const unsigned (&u)[3], unsigned (&h)[4]) {
+  auto hcalc = [&](int sy, unsigned (&h)[4]) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kResizeRing - 1) : "memory");
     if (!wide) {
-      const unsigned v0 = __funnelshift_r(u[0], u[1], sh), v1 = __funnelshift_r(u[1], u[2], sh);
+      uint4 u;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                   : "r"(ring0 + (unsigned)((sy - srow0) & (kResizeRing - 1)) * (unsigned)(128 * sizeof(uint4))));
+      const unsigned v0 = __funnelshift_r(u.x, u.y, sh), v1 = __funnelshift_r(u.y, u.z, sh);
 #pragma unroll
       for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(a01[k], __byte_perm(v0, v1, sel[k]), 0u);
     } else {
@@ -147,32 +168,33 @@ __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_
     }
   };
 
-  unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0}, nx[3];
-  int rowB = (int)(yc[0] & 0xffffu) - 1;  // hB = h(rowB); the first destination row computes rows o and o+1
-  load_raw(rowB + 1, nx);
+#pragma unroll
+  for (int i = 0; i < kResizeRing; ++i) issue_next();
+  unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+  int rowB = srow0 - 1;  // hB = h(rowB); the first destination row computes rows o and o+1
   unsigned yy = yc[0];
   for (int r = 0; r < rows; ++r) {
     const int o = (int)(yy & 0xffffu), o1 = min(o + 1, shm1);
-    const unsigned b1 = yy >> 16, b0 = 256u - b1;
+    unsigned b1 = yy >> 16, b0 = 256u - b1;
     yy = yc[min(r + 1, rows - 1)];
     while (rowB < o1) {
-      unsigned cur[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) cur[j] = nx[j];
       ++rowB;
-      load_raw(rowB + 1, nx);
-      prefetch_l2(src + (size_t)min(rowB + kResizePrefetchRows, shm1) * spitch + wo[1]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) hA[k] = hB[k];
-      hcalc(rowB, cur, hB);
+      hcalc(rowB, hB);   // waits for the oldest row in flight and interpolates it horizontally
+      issue_next();      // its slot is free again: enqueue the row kResizeRing ahead
     }
-    const bool same = o1 == o;  // bottom replicate: both taps are the last source row (beta1 == 0)
+    if (o1 == o) {  // bottom replicate: both taps are the last source row (beta1 == 0): take it from hB
+      b1 = b0;
+      b0 = 0;
+    }
     unsigned v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = b0 * (same ? hB[k] : hA[k]) + (b1 * hB[k] + 32768u);  // < 2^24: byte 2 = result
+    for (int k = 0; k < 4; ++k) v[k] = b0 * hA[k] + (b1 * hB[k] + 32768u);  // < 2^24: byte 2 = result
     const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
     *reinterpret_cast<uint32_t*>(dst + (size_t)r * D.pitch) = word;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ----------------------------------------------------------------------------------------------------------
