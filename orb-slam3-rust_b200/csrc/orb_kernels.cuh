@@ -65,7 +65,7 @@ struct __align__(8) LvlKp {
 __device__ __forceinline__ const uint8_t* level_ptr(const PyrP& P, int l, int img, const uint8_t* in_l,
                                                     const uint8_t* in_r, const uint8_t* pyr, int& pitch) {
   if (l == 0) {
-    int f = img / P.eyes, e = img - f * P.eyes;
+    const int f = P.eyes == 2 ? img >> 1 : img, e = P.eyes == 2 ? (img & 1) : 0;  // eyes is 1 or 2
     pitch = P.in_pitch;
     return (e ? in_r : in_l) + (long long)f * P.in_frame_stride;
   }
@@ -1165,16 +1165,21 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   __shared__ uint32_t s_patch[8][kPatchWords];
   const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 8 + warp;
-  const int frame = img / P.eyes, eye = img - frame * P.eyes;
+  const int frame = P.eyes == 2 ? img >> 1 : img, eye = P.eyes == 2 ? (img & 1) : 0;  // eyes is 1 or 2
   const int* cnt = lvl_cnt + (long long)img * P.nlevels;
   int total = 0, l = -1, jl = 0;
-  for (int k = 0; k < P.nlevels; ++k) {
-    int c = cnt[k];
-    if (l < 0 && j < total + c) {
-      l = k;
-      jl = j - total;
+  {
+    int c[VSLAM_MAX_LEVELS];  // all loads first (independent), then the prefix walk
+#pragma unroll
+    for (int k = 0; k < VSLAM_MAX_LEVELS; ++k) c[k] = k < P.nlevels ? cnt[k] : 0;
+#pragma unroll
+    for (int k = 0; k < VSLAM_MAX_LEVELS; ++k) {
+      if (l < 0 && j < total + c[k]) {
+        l = k;
+        jl = j - total;
+      }
+      total += c[k];
     }
-    total += c;
   }
   ResHdr* hdr = F.hdr + frame;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1196,40 +1201,37 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   const uint8_t* blurred = blur + (long long)img * P.blur_img_stride + L.blur_off;
   const int xb0 = (cx - kBriefR) & ~3, xa0 = (cx - kAngleR) & ~3;
   {
-    // three rows per step: lanes 0-9 / 10-19 / 20-29 load the 10 words of a BRIEF row, lanes 0-8 / 9-17 / 18-26 the
-    // 9 words of an orientation row; every load is issued before the first store.
+    // three rows per step: lanes 0-9 / 10-19 / 20-29 copy the 10 words of a BRIEF row, lanes 0-8 / 9-17 / 18-26 the
+    // 9 words of an orientation row, with cp.async (global -> shared without a register round trip; all 24 copies of
+    // a lane are in flight at once).  Only the last step of each patch has rows past the end (row 37 / 38, 31 / 32).
     const int rb = lane / 10, wb = lane - 10 * rb;
     const int ra = lane / 9, wa = lane - 9 * ra;
     const uint8_t* pb = blurred + (size_t)(cy - kBriefR + rb) * L.pitch + xb0 + 4 * wb;
     const uint8_t* pa = unblurred + (size_t)(cy - kAngleR + ra) * upitch + xa0 + 4 * wa;
     constexpr int NB = (kBriefRows + 2) / 3, NA = (kAngleRows + 2) / 3;  // 13, 11 steps of three rows
-    const bool lb = lane < 30, la = lane < 27;
+    static_assert(3 * (NB - 1) == kBriefRows - 1 && 3 * (NA - 1) == kAngleRows - 1, "last step holds exactly one row");
     const size_t stepb = (size_t)3 * L.pitch, stepa = (size_t)3 * upitch;
-    unsigned* qb = sb + rb * kBriefRowWords + wb;
-    unsigned* qa = sa + ra * kAngleRowWords + wa;
-    // groups of six loads in flight (small arrays stay in registers)
+    const unsigned qb = (unsigned)__cvta_generic_to_shared(sb + rb * kBriefRowWords + wb);
+    const unsigned qa = (unsigned)__cvta_generic_to_shared(sa + ra * kAngleRowWords + wa);
+    if (lane < 30) {
 #pragma unroll
-    for (int k0 = 0; k0 < NB; k0 += 6) {
-      unsigned v[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        v[k] = (k0 + k < NB && lb && rb + 3 * (k0 + k) < kBriefRows)
-                   ? *reinterpret_cast<const uint32_t*>(pb + (size_t)(k0 + k) * stepb) : 0u;
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        if (k0 + k < NB && lb && rb + 3 * (k0 + k) < kBriefRows) qb[3 * (k0 + k) * kBriefRowWords] = v[k];
+      for (int k = 0; k < NB; ++k) {
+        if (k < NB - 1 || rb == 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(qb + (unsigned)(k * 3 * kBriefRowWords * 4)), "l"(pb)
+                       : "memory");
+        pb += stepb;
+      }
     }
+    if (lane < 27) {
 #pragma unroll
-    for (int k0 = 0; k0 < NA; k0 += 6) {
-      unsigned v[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        v[k] = (k0 + k < NA && la && ra + 3 * (k0 + k) < kAngleRows)
-                   ? *reinterpret_cast<const uint32_t*>(pa + (size_t)(k0 + k) * stepa) : 0u;
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        if (k0 + k < NA && la && ra + 3 * (k0 + k) < kAngleRows) qa[3 * (k0 + k) * kAngleRowWords] = v[k];
+      for (int k = 0; k < NA; ++k) {
+        if (k < NA - 1 || ra == 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(qa + (unsigned)(k * 3 * kAngleRowWords * 4)), "l"(pa)
+                       : "memory");
+        pa += stepa;
+      }
     }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
   }
   __syncwarp();
 
@@ -1272,19 +1274,23 @@ __global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, c
   const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
   float a, b;
   sincos_f64_to_f32(rad, a, b);
-  const uint8_t* center = reinterpret_cast<const uint8_t*>(sb) + kBriefR * (kBriefRowWords * 4) + (cx - xb0);
-
-  // cvRound of a value in (-32, 32): adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits
-  auto rnd = [](float v) -> int { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; };
+  // cvRound of a value in (-32, 32): adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits, i.e. the
+  // float's bit pattern is 0x4B400000 + round(v).  The bias is not subtracted per coordinate: with row stride 44 the
+  // sample address is center + 44 * iy + ix = (center - 45 * 0x4B400000) + 44 * raw_y + raw_x in wrap-around 32-bit
+  // arithmetic (shared-window addresses are 32 bits wide).
+  constexpr unsigned kRowB = kBriefRowWords * 4;
+  const unsigned center = (unsigned)__cvta_generic_to_shared(sb) + kBriefR * kRowB + (unsigned)(cx - xb0) -
+                          (kRowB + 1u) * 0x4B400000u;
+  auto raw = [](float v) -> unsigned { return __float_as_uint(__fadd_rn(v, 12582912.0f)); };
   unsigned byte = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 t = g_brief_pattern_t[q][lane];  // test 8*lane + q: (x0,y0,x1,y1)
-    const int ix0 = rnd(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
-    const int iy0 = rnd(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
-    const int ix1 = rnd(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
-    const int iy1 = rnd(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
-    const int t0 = center[iy0 * (kBriefRowWords * 4) + ix0], t1 = center[iy1 * (kBriefRowWords * 4) + ix1];
+    const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
+    const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
+    const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
+    const unsigned iy1 = raw(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
+    const unsigned t0 = lds8(center + iy0 * kRowB + ix0), t1 = lds8(center + iy1 * kRowB + ix1);
     byte |= (unsigned)(t0 < t1) << q;
   }
   unsigned char* descbase = eye ? F.desc[1] : F.desc[0];
