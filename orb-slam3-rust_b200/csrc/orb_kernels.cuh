@@ -262,11 +262,20 @@ __device__ __forceinline__ void sts16(unsigned a, unsigned v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v));
 }
 
-constexpr int kFastThreads = 192;                   // 6 warps: one per 128-pixel column group of a 752-wide level
+#ifndef VSLAM_FAST_THREADS
+#define VSLAM_FAST_THREADS 192  // 6 warps: one per 128-pixel column group of a 752-wide level
+#endif
+#ifndef VSLAM_FAST_MINB
+#define VSLAM_FAST_MINB 4
+#endif
+#ifndef VSLAM_FAST_CL
+#define VSLAM_FAST_CL 512
+#endif
+constexpr int kFastThreads = VSLAM_FAST_THREADS;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastSeg = 7;                         // score rows per phase-A segment == depth of the register window
 constexpr int kFastQ = 512;                         // per-warp candidate ring (entries) >= 7 rows x 64 pairs + 31
-constexpr int kFastCL = 512;                        // per-warp pre-NMS corner list (entries)
+constexpr int kFastCL = VSLAM_FAST_CL;              // per-warp pre-NMS corner list (entries)
 static_assert((VSLAM_FAST_ROWS + 2) % kFastSeg == 0, "score rows of a strip must be whole segments");
 static_assert(VSLAM_FAST_ROWS + 2 <= 32, "score row index is a 5-bit field of the queue entries");
 static_assert(kFastQ >= kFastSeg * 64 + 31, "candidate ring too small");
@@ -291,7 +300,7 @@ __host__ inline size_t fast_smem_bytes(int pitch) {
 //             non-zero scores go to the score tile and to the warp's pre-NMS corner list
 //   NMS       sparse, over the corner lists (full scan if a list overflowed), into a bitmask
 //   emission  popcount scan of the bitmask -> raster-ordered records (== cv::FAST's output order), no atomics, no sort
-__global__ void __launch_bounds__(kFastThreads) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+__global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                        const uint8_t* __restrict__ in_r,
                                                        const uint8_t* __restrict__ pyr, int* __restrict__ strip_cnt,
                                                        uint32_t* __restrict__ strip_rec) {
