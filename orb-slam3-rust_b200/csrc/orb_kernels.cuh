@@ -954,11 +954,9 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
 }
 
 constexpr int kBlurRing = 8;  // source rows in flight per lane (cp.async ring in shared memory)
-__global__ void __launch_bounds__(128, VSLAM_BLUR_MINB) k_blur(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
-                                              const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
-                                              uint8_t* __restrict__ blur) {
-  const int img = blockIdx.y;
-  const int item = blockIdx.x * 128 + threadIdx.x;
+__device__ __forceinline__ void blur_item(const PyrP& P, const int img, const int item, const uint8_t* __restrict__ in_l,
+                                          const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
+                                          uint8_t* __restrict__ blur) {
   int l = 0;
   for (int k = 1; k < P.nlevels; ++k)
     if (item >= P.lv[k].blur_item0) l = k;  // warp-uniform
@@ -1117,6 +1115,23 @@ __global__ void __launch_bounds__(128, VSLAM_BLUR_MINB) k_blur(const __grid_cons
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain the look-ahead rows before the block's memory is reused
+}
+
+// Persistent launch: grid = (blocks, 1) with a fixed number of blocks per SM chosen by the host; every block walks
+// the (image, 128-item group) space with a grid stride.  A blur that cannot fill the SMs on its own leaves registers
+// and shared memory for the FAST blocks of the same chunk: the two kernels are bound by different pipes (FMA vs ALU)
+// and are launched together on two streams.
+__global__ void __launch_bounds__(128, VSLAM_BLUR_MINB) k_blur(const __grid_constant__ PyrP P, int nimg,
+                                                               const uint8_t* __restrict__ in_l,
+                                                               const uint8_t* __restrict__ in_r,
+                                                               const uint8_t* __restrict__ pyr,
+                                                               uint8_t* __restrict__ blur) {
+  const int groups = (P.total_blur_items + 127) >> 7;  // 128-item groups per image
+  const int total = nimg * groups;
+  for (int gi = blockIdx.x; gi < total; gi += gridDim.x) {
+    const int img = gi / groups, grp = gi - img * groups;
+    blur_item(P, img, grp * 128 + (int)threadIdx.x, in_l, in_r, pyr, blur);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------

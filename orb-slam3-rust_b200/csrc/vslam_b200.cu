@@ -80,6 +80,8 @@ struct vslam_handle_s {
   uint32_t* d_coef = nullptr;
   int resize_rows = VSLAM_RESIZE_ROWS;  // destination rows per k_resize lane item
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
+  int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
+  int sm_count = 148;
   size_t fast_smem = 0;
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   int harris_blocks = 1;
@@ -270,13 +272,16 @@ int build_params(vslam_handle h) {
   // select2 for 2N_l plus ties; anything larger is replayed in global memory.
   {
     long long epx0 = (long long)(P.lv[0].ex1 - P.lv[0].ex0) * (P.lv[0].ey1 - P.lv[0].ey0);
-    // Two budgets for k_select1's records in shared memory.  Large chunks: 4096 records (32 KB) — the kernel is
-    // latency-bound (one warp per problem), so what matters is that its blocks leave shared memory free for the dense
-    // kernels of the other pipeline slots to co-reside (measured +6 % frames/s against a 72 KB budget even though the
-    // largest problems then replay in global memory).  Small chunks (single pairs): ~3 % corner density of level 0, so
-    // that every problem replays in shared memory (single-pair latency 0.29 ms instead of 0.40 ms).
+    // Two budgets for k_select1's records in shared memory.  Large chunks: 512 records (4 KB).  The kernel is
+    // latency-bound (one warp per problem, SM issue slots 3 % busy) and hidden behind the dense kernels of the other
+    // pipeline slots, so what matters is its FOOTPRINT: with a 32 KB budget its 1024 blocks held ~220 KB of shared
+    // memory per SM for ~270 us per chunk and kept k_fast / k_brief / k_blur blocks of the other slots from becoming
+    // resident (measured: 73.9k -> 77.7k frames/s going from 4096 to 512 records; anything from 256 to 1536 is
+    // equivalent).  Problems larger than the budget replay in global memory (L1/L2-resident), same result.
+    // Small chunks (single pairs): ~3 % corner density of level 0, so that every problem replays in shared memory
+    // (single-pair latency 0.29 ms instead of 0.40 ms).
     h->sel1_cap_latency = (int)std::min<long long>(std::max<long long>(epx0 / 32, 1024), 24000) & ~7;
-    h->sel1_cap = std::min(h->sel1_cap_latency, 4096);
+    h->sel1_cap = std::min(h->sel1_cap_latency, 512);
     if (const char* ev = getenv("VSLAM_SEL1_CAP")) h->sel1_cap = std::max(256, atoi(ev)) & ~7;  // tuning knob
     int max2n = 0;
     for (int l = 0; l < P.nlevels; ++l) max2n = std::max(max2n, 2 * P.lv[l].nfeat);
@@ -377,6 +382,12 @@ void free_slot(Slot& s) {
   s = Slot();
 }
 
+// Blocks of the persistent k_blur launch: blur_blocks_per_sm per SM (0 = as many as the work needs, i.e. not persistent).
+static int blur_grid(vslam_handle h, int nimg) {
+  const int full = nimg * ((h->P.total_blur_items + 127) / 128);
+  return h->blur_blocks_per_sm > 0 ? std::min(full, h->blur_blocks_per_sm * h->sm_count) : full;
+}
+
 // Enqueue every kernel of one chunk on the slot's stream.  in_l / in_r: device pointers of the first frame's
 // left / right level-0 image; frames `frame_stride` bytes apart, rows `pitch` bytes apart.
 int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* in_l, const uint8_t* in_r,
@@ -414,8 +425,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   if (fork) {
     CU_TRY(h, cudaEventRecord(s.ev_pyr, st));
     CU_TRY(h, cudaStreamWaitEvent(sb, s.ev_pyr, 0));
-    dim3 grid((P.total_blur_items + 127) / 128, nimg);
-    vk::k_blur<<<grid, 128, 0, sb>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
+    vk::k_blur<<<blur_grid(h, nimg), 128, 0, sb>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
     CU_TRY(h, cudaEventRecord(s.ev_blur, sb));
   }
@@ -438,8 +448,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 3
   if (!fork) {
-    dim3 grid((P.total_blur_items + 127) / 128, nimg);
-    vk::k_blur<<<grid, 128, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur);
+    vk::k_blur<<<blur_grid(h, nimg), 128, 0, st>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
   } else {
     CU_TRY(h, cudaStreamWaitEvent(st, s.ev_blur, 0));
@@ -729,9 +738,11 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   vslam_handle h = new vslam_handle_s();
   h->cfg = c;
   h->max_batch = c.max_batch;
+  h->sm_count = prop.multiProcessorCount;
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
+  if (const char* ev = getenv("VSLAM_BLUR_BPS")) h->blur_blocks_per_sm = std::max(atoi(ev), 0);
   if (const char* ev = getenv("VSLAM_BLUR_ROWS")) h->blur_rows = std::min(std::max(atoi(ev), 8), 4096);
   int rc = build_params(h);
   if (rc != VSLAM_OK) {
