@@ -343,7 +343,9 @@ def main():
     alg = [LEVEL_PIXELS, LEVEL_PIXELS, 2 * NFEAT * 81 + NFEAT * 749, 2 * LEVEL_PIXELS, NFEAT * (512 + 60), NFEAT * 40]
     total_ms = float(stage[6])
     shares = {names[i]: round(float(stage[i]) / total_ms, 4) for i in range(6)}
-    dom = int(np.argmax(stage[:6]))
+    # dominant kernel = the dense kernel with the largest device time (the selection chain, index 2, is three
+    # latency-bound launches that hide behind the dense kernels of the other pipeline slots)
+    dom = max((0, 1, 3, 4, 5), key=lambda i: float(stage[i]))
     per_launch_ms = float(stage[dom]) / nchunks
     images_per_launch = 2 * min(args.batch, n)
     achieved = alg[dom] * images_per_launch / (per_launch_ms * 1e-3) / 1e9
@@ -367,8 +369,9 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "note": ("k_fast is bound by the integer ALU pipe (ncu: ALU 70 %, issue 78 %, DRAM 3 %), not by HBM; the HBM "
-                 "fraction is reported because SURVEY.md 8(d) defines the roofline in algorithmic bytes"),
+        "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r01q_summary.md: ALU pipe "
+                 "63 %, issue 59 %, DRAM 5 %), not by HBM; the HBM fraction is reported because SURVEY.md 8(d) defines "
+                 "the roofline in algorithmic bytes"),
         "algorithmic_bytes_per_launch": alg[dom] * images_per_launch, "launch_ms": round(per_launch_ms, 4),
         "stage_ms_per_step": {names[i]: round(float(stage[i]), 3) for i in range(6)}, "stage_share": shares,
         "extraction_dense": {"stages": "pyramid+FAST+blur", "algorithmic_bytes_per_stereo_frame": 8 * LEVEL_PIXELS,

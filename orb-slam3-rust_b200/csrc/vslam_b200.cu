@@ -83,6 +83,7 @@ struct vslam_handle_s {
   int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
   int sm_count = 148;
   size_t fast_smem = 0;
+  size_t fast_smem_pad = 0;  // tuning knob VSLAM_FAST_SMEM_PAD: extra bytes per k_fast block (caps its blocks per SM)
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   int harris_blocks = 1;
   size_t match_rows_smem = 0;  // 0: fall back to k_match + k_match_finalize
@@ -267,7 +268,8 @@ int build_params(vslam_handle h) {
     linear_exact_coeffs(Sx.w, L.w, h->coef.data() + L.xcoef_off);
     linear_exact_coeffs(Sx.h, L.h, h->coef.data() + L.ycoef_off);
   }
-  h->fast_smem = vk::fast_smem_bytes(P.in_pitch);
+  if (const char* ev = getenv("VSLAM_FAST_SMEM_PAD")) h->fast_smem_pad = (size_t)std::max(atoi(ev), 0);
+  h->fast_smem = vk::fast_smem_bytes(P.in_pitch) + h->fast_smem_pad;
   // selection scratch in shared memory: select1 sized for ~3% corner density on the largest level (typical < 2%),
   // select2 for 2N_l plus ties; anything larger is replayed in global memory.
   {
@@ -431,7 +433,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   if (P.total_fast_strips > 0) {
     dim3 grid(P.total_fast_strips, nimg);
-    vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)), st>>>(P, in_l, in_r, s.d_pyr,
+    vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)) + h->fast_smem_pad, st>>>(P, in_l, in_r, s.d_pyr,
                                                                                       s.d_strip_cnt, s.d_strip_rec);
     h->launches++;
   }
