@@ -286,7 +286,7 @@ __host__ __device__ inline int fast_bw(int pitch) { return (pitch + 31) >> 5; }
 __host__ inline size_t fast_smem_bytes(int pitch) {
   size_t sp = fast_sp(pitch), bw = fast_bw(pitch);
   return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + VSLAM_FAST_ROWS * bw * 4 +
-         kFastWarps * (kFastQ + kFastCL) * 2 + 64;
+         kFastWarps * (kFastQ + kFastCL) * 2 + 64 + (kFastWarps + 2 + VSLAM_FAST_ROWS) * 4;
 }
 
 // grid = (total_fast_strips, n_img), block = kFastThreads.  One block = one strip of VSLAM_FAST_ROWS emission rows of
@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   uint8_t* sc = smem + o_sc;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + o_bits);
   int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 8);   // [kFastWarps] corner-list lengths
-  int* s_next = s_ccnt + kFastWarps;                               // dynamic work-item counter of phase A
+  int* s_next = s_ccnt + kFastWarps;
+  int* s_rowcnt = s_next + 1;                                // [VSLAM_FAST_ROWS] NMS survivors per emission row                               // dynamic work-item counter of phase A
   const unsigned mbar = sbase + (unsigned)o_misc;
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < VSLAM_FAST_ROWS * BW; i += kFastThreads) bits[i] = 0;
+  if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
   {
     unsigned done = 0;
     while (!done)
@@ -528,7 +530,10 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
         const int v = c[0];
         const bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
                           v > c[SP] && v > c[SP + 1];
-        if (keep) atomicOr(&bits[er * BW + (x >> 5)], 1u << (x & 31));
+        if (keep) {
+          atomicOr(&bits[er * BW + (x >> 5)], 1u << (x & 31));
+          atomicAdd(&s_rowcnt[er], 1);
+        }
       }
     }
   } else {
@@ -548,46 +553,52 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
         const uint8_t* c = srow + x;
         bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
                     v > c[SP] && v > c[SP + 1];
-        if (keep) atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+        if (keep) {
+          atomicOr(&bits[ry * BW + (x >> 5)], 1u << (x & 31));
+          atomicAdd(&s_rowcnt[ry], 1);
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- raster-ordered emission.  Order inside the strip == (y, x) == cv::FAST's output order.  The bitmask words are
-  //      cut into 32 chunks; EVERY warp scans the chunk popcounts (redundantly: no single-warp phase, no extra
-  //      barrier), then lane j of warp w expands the words of chunk j that fall to warp w, carrying the running
-  //      offset through the chunk.
-  const int nwords = rows * BW;
+  // ---- raster-ordered emission.  Order inside the strip == (y, x) == cv::FAST's output order.  The NMS pass counted
+  //      the survivors of every emission row (s_rowcnt); every warp scans those <= 32 counts (5 shuffles, redundantly:
+  //      no single-warp phase, no extra barrier) and then emits the rows r = warp, warp + nwarps, ...: lane j takes
+  //      word j of the row, a warp prefix sum of the popcounts gives its offset.  (POPC issues once per 8 clk per
+  //      scheduler on B200: one per word here, not one per word per warp.)
   {
-    const int per = (nwords + 31) >> 5;
-    const int b = lane * per, e = min(b + per, nwords);
-    int sum = 0;
-    for (int i = b; i < e; ++i) sum += __popc(bits[i]);
-    int incl = sum;
+    const int rc = lane < rows ? s_rowcnt[lane] : 0;
+    int incl = rc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+      const int o = __shfl_up_sync(VSLAM_FULL, incl, d);
       if (lane >= d) incl += o;
     }
-    int run = incl - sum;
+    const int excl = incl - rc;  // lane r: records of the rows above row r
     uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
-    for (int i = b; i < e; ++i) {
-      unsigned bw = bits[i];
-      const int cnt = __popc(bw);
-      if (bw && (i - b) % kFastWarps == warp) {
-        int off = run;
-        const int ry = i / BW;
-        const int xb = (i - ry * BW) << 5;
+    for (int er = warp; er < rows; er += kFastWarps) {
+      int run = __shfl_sync(VSLAM_FULL, excl, er);
+      for (int j0 = 0; j0 < BW; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned bw = j < BW ? bits[er * BW + j] : 0u;
+        const int c = __popc(bw);
+        int pin = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(VSLAM_FULL, pin, d);
+          if (lane >= d) pin += o;
+        }
+        int off = run + pin - c;
+        const uint8_t* srow = sc + (er + 1) * SP + 16 + (j << 5);
         while (bw) {
           const int bpos = __ffs(bw) - 1;
           bw &= bw - 1;
-          const int x = xb + bpos;
-          const unsigned score = (unsigned)sc[(ry + 1) * SP + 16 + x] + (unsigned)P.fast_threshold - 1u;  // S-1 <= 254
-          out[off++] = (score << 24) | ((unsigned)(ys + ry) << 12) | (unsigned)x;
+          const unsigned score = (unsigned)srow[bpos] + (unsigned)P.fast_threshold - 1u;  // S - 1 <= 254
+          out[off++] = (score << 24) | ((unsigned)(ys + er) << 12) | (unsigned)((j << 5) + bpos);
         }
+        run += __shfl_sync(VSLAM_FULL, pin, 31);
       }
-      run += cnt;
     }
     if (tid == 31) strip_cnt[(long long)img * P.total_fast_strips + strip] = incl;
   }
@@ -846,7 +857,10 @@ __global__ void __launch_bounds__(128) k_select1(const __grid_constant__ PyrP P,
 }
 
 // Harris response of every select1 survivor: grid = (blocks, nlevels, n_img), block = 128, thread per survivor.
-__global__ void __launch_bounds__(128) k_harris(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+#ifndef VSLAM_HARRIS_MINB
+#define VSLAM_HARRIS_MINB 1
+#endif
+__global__ void __launch_bounds__(128, VSLAM_HARRIS_MINB) k_harris(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                 const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                                 const uint32_t* __restrict__ sel1, const int* __restrict__ sel1_cnt,
                                                 vrec_t* __restrict__ cand, float harris_scale4) {

@@ -288,6 +288,7 @@ int build_params(vslam_handle h) {
     int max2n = 0;
     for (int l = 0; l < P.nlevels; ++l) max2n = std::max(max2n, 2 * P.lv[l].nfeat);
     h->sel2_cap = std::min((max2n + max2n / 4 + 64 + 7) & ~7, 16000);
+    if (const char* ev = getenv("VSLAM_SEL2_CAP")) h->sel2_cap = std::max(64, atoi(ev)) & ~7;  // tuning knob
     h->harris_blocks = std::max(1, (max2n + 127) / 128);
   }
   // HarrisResponses scale: scale = 1/((1<<2)*7*255.f); scale^4 = ((s*s)*s)*s   (f32, one rounding per op)
