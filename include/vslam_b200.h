@@ -19,6 +19,8 @@
  *   vslam_fuse_search                   <- descriptor search of fuse_points_into_keyframes
  *                                          src/local_mapping/search_in_neighbors.rs:303-340 (+ keyframe.rs:408-446)
  *   vslam_distinctive_descriptors       <- Map::compute_distinctive_descriptors       src/atlas/map/map.rs:917-937
+ *   vslam_vocab_upload / vslam_bow_quantize <- OrbVocabulary::{load_from_text, transform_descriptor,
+ *                                          get_parent_at_level}                       src/vocabulary/mod.rs:109-206, 230-275
  *
  * All pixel/descriptor arithmetic runs in hand-written CUDA kernels for sm_100a.  There is NO CPU fallback:
  * every call fails with VSLAM_ERR_CUDA when no usable device is present.
@@ -207,6 +209,19 @@ int vslam_fuse_search(vslam_handle h, const vslam_keypoint* kps, const uint8_t* 
  * desc; out_idx[m] = position (within the group) of the descriptor whose maximum distance to the others is smallest
  * (first minimum), 0 for a single descriptor, -1 for none. */
 int vslam_distinctive_descriptors(vslam_handle h, const uint8_t* desc, const int32_t* offsets, int M, int32_t* out_idx);
+
+/* BoW quantisation against a vocabulary tree (the per-descriptor part of OrbVocabulary::transform, mod.rs:290-318).
+ * vslam_vocab_upload keeps the flattened tree on the device: node 0 is the root; node_desc[n_nodes][32];
+ * children of node i are child_ids[child_begin[i] .. child_begin[i+1]) in the order of VocabNode::children;
+ * parent[i] (0xFFFFFFFF for the root, exactly VocabNode::parent); word_id[i] = Some(w) -> w, None -> -1.
+ * vslam_bow_quantize: for each of the n descriptors (desc[n][32]) descend from the root to the closest child (first
+ * minimum Hamming distance) until a node without children: out_word = word_id.unwrap_or(0), out_leaf = that node,
+ * out_node = get_parent_at_level(leaf, levels_up).  The TF-IDF accumulation / L1 normalisation of BowVector stays on the
+ * host: the reference sums f64 weights in HashMap iteration order, which no device order can reproduce. */
+int vslam_vocab_upload(vslam_handle h, int n_nodes, const uint8_t* node_desc, const int32_t* child_begin,
+                       const int32_t* child_ids, const uint32_t* parent, const int32_t* word_id);
+int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up, uint32_t* out_word,
+                       uint32_t* out_leaf, uint32_t* out_node);
 
 /* ---- introspection for parity tests and profiling ---------------------------------------------------------- */
 enum {

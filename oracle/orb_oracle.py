@@ -284,3 +284,46 @@ def distinctive_descriptors(desc, offsets):
     out = np.full(max(M, 1), -1, dtype=np.int32)
     lib().orc_distinctive_descriptors(_p(desc), _p(offsets), M, _p(out))
     return out[:M]
+
+
+def make_vocabulary_arrays(parent_file_order, is_leaf, node_desc):
+    """Restates the tree construction of OrbVocabulary::load_from_text (vocabulary/mod.rs:109-206) for nodes given in
+    file order (node i+1 = line i): returns the flattened arrays of include/vslam_b200.h
+    (node_desc[n_nodes,32], child_begin, child_ids, parent, word_id) with node 0 = root."""
+    parent_file_order = np.asarray(parent_file_order, dtype=np.int64)
+    n_nodes = len(parent_file_order) + 1
+    desc = np.zeros((n_nodes, 32), dtype=np.uint8)
+    desc[1:] = np.asarray(node_desc, dtype=np.uint8).reshape(-1, 32)
+    parent = np.full(n_nodes, 0xFFFFFFFF, dtype=np.uint32)
+    word = np.full(n_nodes, -1, dtype=np.int32)
+    children = [[] for _ in range(n_nodes)]
+    wc = 0
+    for i, p in enumerate(parent_file_order):
+        nid = i + 1
+        parent[nid] = np.uint32(p)
+        if is_leaf[i]:
+            word[nid] = wc
+            wc += 1
+        if p < nid:  # "if (parent_id as usize) < nodes.len()" at the time the node is appended
+            children[int(p)].append(nid)
+    child_begin = np.zeros(n_nodes + 1, dtype=np.int32)
+    child_begin[1:] = np.cumsum([len(c) for c in children])
+    child_ids = np.array([c for cs in children for c in cs], dtype=np.int32)
+    return desc, child_begin, child_ids, parent, word
+
+
+def bow_quantize(desc, vocab, levels_up):
+    """vocab = (node_desc, child_begin, child_ids, parent, word_id) -> (word, leaf, node_at_level) uint32 arrays."""
+    nd, cb, ci, pa, wi = vocab
+    desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    nd = np.ascontiguousarray(nd, dtype=np.uint8)
+    cb = np.ascontiguousarray(cb, dtype=np.int32)
+    ci = np.ascontiguousarray(ci if len(ci) else np.zeros(1), dtype=np.int32)
+    pa = np.ascontiguousarray(pa, dtype=np.uint32)
+    wi = np.ascontiguousarray(wi, dtype=np.int32)
+    n = len(desc)
+    w = np.zeros(max(n, 1), dtype=np.uint32)
+    lf = np.zeros(max(n, 1), dtype=np.uint32)
+    nl = np.zeros(max(n, 1), dtype=np.uint32)
+    lib().orc_bow_quantize(_p(desc), n, _p(nd), _p(cb), _p(ci), _p(pa), _p(wi), int(levels_up), _p(w), _p(lf), _p(nl))
+    return w[:n], lf[:n], nl[:n]

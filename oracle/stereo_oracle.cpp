@@ -11,6 +11,7 @@
 //   fusion search         /root/reference/src/local_mapping/search_in_neighbors.rs:303-340 with the linear-scan
 //                         KeyFrame::get_features_in_area of src/atlas/map/keyframe.rs:408-446      
 //   distinctive descriptor /root/reference/src/atlas/map/map.rs:917-937 (min over i of max_j Hamming)   (row f2)
+//   BoW quantisation       /root/reference/src/vocabulary/mod.rs:230-251, 263-275 (tree descent)         (row f2)
 //
 // PARITY UNPINNED for this file: the reference cannot be built here (no Rust toolchain) and holds no test
 // for these functions; the only related known-answer vectors are the popcount twins at
@@ -332,6 +333,42 @@ void orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int M,
       }
     }
     out_idx[m] = best_idx;
+  }
+}
+
+// vocabulary/mod.rs:230-251 transform_descriptor + :263-275 get_parent_at_level, per descriptor row as transform()
+// (:290-318) calls them.  Tree flattened as in include/vslam_b200.h: node 0 = root, CSR children in VocabNode::children
+// order, parent (0xFFFFFFFF = root), word_id (-1 = None -> unwrap_or(0)).
+void orc_bow_quantize(const uint8_t* desc, int n, const uint8_t* node_desc, const int* child_begin, const int* child_ids,
+                      const uint32_t* parent, const int* word_id, int levels_up, uint32_t* out_word, uint32_t* out_leaf,
+                      uint32_t* out_node) {
+  for (int i = 0; i < n; ++i) {
+    const uint8_t* d = desc + (size_t)i * 32;
+    size_t node_id = 0;  // start at root
+    int guard = 0;
+    while (child_begin[node_id + 1] != child_begin[node_id] && guard++ < 64) {  // !children.is_empty()
+      const int b = child_begin[node_id], e = child_begin[node_id + 1];
+      int best_child = child_ids[b];
+      uint32_t best_dist = orc_descriptor_distance(d, 32, node_desc + (size_t)best_child * 32, 32);
+      for (int c = b + 1; c < e; ++c) {
+        const int child = child_ids[c];
+        const uint32_t dist = orc_descriptor_distance(d, 32, node_desc + (size_t)child * 32, 32);
+        if (dist < best_dist) {
+          best_dist = dist;
+          best_child = child;
+        }
+      }
+      node_id = (size_t)best_child;
+    }
+    out_word[i] = word_id[node_id] < 0 ? 0u : (uint32_t)word_id[node_id];
+    out_leaf[i] = (uint32_t)node_id;
+    uint32_t up = (uint32_t)node_id;
+    for (int k = 0; k < levels_up; ++k) {
+      const uint32_t pa = parent[up];
+      if (pa == 0xFFFFFFFFu) break;  // reached root
+      up = pa;
+    }
+    out_node[i] = up;
   }
 }
 

@@ -348,4 +348,66 @@ int vslam_distinctive_descriptors(vslam_handle h, const uint8_t* desc, const int
   return VSLAM_OK;
 }
 
+int vslam_vocab_upload(vslam_handle h, int n_nodes, const uint8_t* node_desc, const int32_t* child_begin,
+                       const int32_t* child_ids, const uint32_t* parent, const int32_t* word_id) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n_nodes < 1 || !node_desc || !child_begin || !parent || !word_id)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "vocabulary: null argument or no root node");
+  const int nch = child_begin[n_nodes];
+  if (child_begin[0] != 0 || nch < 0 || (nch > 0 && !child_ids)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad child_begin");
+  for (int i = 0; i < n_nodes; ++i)
+    if (child_begin[i + 1] < child_begin[i]) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "child_begin must be non-decreasing");
+  for (int c = 0; c < nch; ++c)
+    if (child_ids[c] < 0 || child_ids[c] >= n_nodes) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "child id %d out of range", child_ids[c]);
+  for (int i = 0; i < n_nodes; ++i)
+    if (parent[i] != 0xffffffffu && parent[i] >= (uint32_t)n_nodes)
+      return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "parent of node %d out of range", i);
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  CU_TRY(h, cudaStreamSynchronize(st));
+  cudaFree(h->voc_desc); cudaFree(h->voc_child_begin); cudaFree(h->voc_child_ids); cudaFree(h->voc_parent); cudaFree(h->voc_word);
+  h->voc_desc = nullptr; h->voc_child_begin = h->voc_child_ids = h->voc_word = nullptr; h->voc_parent = nullptr;
+  h->voc_nodes = 0;
+  const size_t nn = (size_t)n_nodes;
+  CU_TRY(h, cudaMalloc(&h->voc_desc, nn * 32));
+  CU_TRY(h, cudaMalloc(&h->voc_child_begin, (nn + 1) * 4));
+  CU_TRY(h, cudaMalloc(&h->voc_child_ids, (size_t)std::max(nch, 1) * 4));
+  CU_TRY(h, cudaMalloc(&h->voc_parent, nn * 4));
+  CU_TRY(h, cudaMalloc(&h->voc_word, nn * 4));
+  CU_TRY(h, cudaMemcpy(h->voc_desc, node_desc, nn * 32, cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->voc_child_begin, child_begin, (nn + 1) * 4, cudaMemcpyHostToDevice));
+  if (nch > 0) CU_TRY(h, cudaMemcpy(h->voc_child_ids, child_ids, (size_t)nch * 4, cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->voc_parent, parent, nn * 4, cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->voc_word, word_id, nn * 4, cudaMemcpyHostToDevice));
+  h->voc_nodes = n_nodes;
+  return VSLAM_OK;
+}
+
+int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up, uint32_t* out_word,
+                       uint32_t* out_leaf, uint32_t* out_node) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (h->voc_nodes <= 0) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "no vocabulary uploaded (vslam_vocab_upload)");
+  if (n < 0 || levels_up < 0 || (n > 0 && (!desc || !out_word || !out_leaf || !out_node)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bow_quantize: bad argument");
+  if (n == 0) return VSLAM_OK;
+  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nn = (size_t)n;
+  int rc = arena_begin(h, pad256(nn * 32) + 3 * pad256(nn * 4));
+  if (rc) return rc;
+  unsigned* dd = arena_take<unsigned>(h, nn * 8);
+  unsigned* dw = arena_take<unsigned>(h, nn);
+  unsigned* dl = arena_take<unsigned>(h, nn);
+  unsigned* dn = arena_take<unsigned>(h, nn);
+  CU_TRY(h, cudaMemcpyAsync(dd, desc, nn * 32, cudaMemcpyHostToDevice, st));
+  vk::k_bow_quantize<<<(unsigned)((nn * 8 + 255) / 256), 256, 0, st>>>(dd, n, h->voc_desc, h->voc_child_begin, h->voc_child_ids,
+                                                                     h->voc_parent, h->voc_word, levels_up, dw, dl, dn);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(out_word, dw, nn * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out_leaf, dl, nn * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out_node, dn, nn * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return VSLAM_OK;
+}
+
 }  // extern "C"

@@ -5,6 +5,7 @@
 //   k_nearest/k_cross   BFMatcher(NORM_HAMMING, crossCheck=true) src/tracking/tracker.rs:1001-1010
 //   k_fuse_search       fusion search of local mapping          src/local_mapping/search_in_neighbors.rs:303-340
 //   k_distinctive       Map::compute_distinctive_descriptors    src/atlas/map/map.rs:917-937
+//   k_bow_quantize      OrbVocabulary::transform_descriptor     src/vocabulary/mod.rs:230-251, 263-275
 //
 // Rust cast semantics reproduced explicitly: f64 -> usize / i32 `as` saturates (NaN -> 0); i32 -> usize `as`
 // sign-extends, so a negative max cell clamps to the LAST column/row (SURVEY.md §8.C trap 6).
@@ -401,6 +402,61 @@ __global__ void __launch_bounds__(256) k_distinctive(const unsigned* __restrict_
     }
   }
   if (lane == 0) out_idx[m] = best_idx;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// BoW quantisation: OrbVocabulary::transform_descriptor + get_parent_at_level,
+// /root/reference/src/vocabulary/mod.rs:230-251, 263-275 (called per descriptor row by transform(), :290-318).
+// 8 lanes per descriptor (one 32-bit word each, coalesced 32-byte node descriptors), 4 descriptors per warp.  At each
+// node the children are scanned in list order; the closest child wins, first one on ties (strict `<`).  A node
+// without children is a leaf; word = word_id or 0 (`unwrap_or(0)`).  The walk is capped at kBowMaxDepth levels (the
+// reference would not terminate on a cyclic child list).
+// ----------------------------------------------------------------------------------------------------------
+constexpr int kBowMaxDepth = 64;
+__global__ void __launch_bounds__(256) k_bow_quantize(const unsigned* __restrict__ desc, int n,
+                                                      const unsigned* __restrict__ node_desc,
+                                                      const int* __restrict__ child_begin,
+                                                      const int* __restrict__ child_ids,
+                                                      const unsigned* __restrict__ parent,
+                                                      const int* __restrict__ word_id, int levels_up,
+                                                      unsigned* __restrict__ out_word, unsigned* __restrict__ out_leaf,
+                                                      unsigned* __restrict__ out_node) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = t >> 3, sub = t & 7, lane = threadIdx.x & 31;
+  if (g >= n) return;  // whole 8-lane groups leave together
+  const unsigned gmask = 0xffu << (lane & 24);
+  const unsigned mine = desc[(size_t)g * 8 + sub];
+  int node = 0;
+  for (int depth = 0; depth < kBowMaxDepth; ++depth) {
+    const int b = child_begin[node], e = child_begin[node + 1];
+    if (b == e) break;
+    unsigned best_dist = 0xffffffffu;
+    int best_child = node;
+    for (int c = b; c < e; ++c) {
+      const int child = child_ids[c];
+      unsigned d = (unsigned)__popc(mine ^ node_desc[(size_t)child * 8 + sub]);
+      d += __shfl_xor_sync(gmask, d, 1);
+      d += __shfl_xor_sync(gmask, d, 2);
+      d += __shfl_xor_sync(gmask, d, 4);
+      if (c == b || d < best_dist) {
+        best_dist = d;
+        best_child = child;
+      }
+    }
+    node = best_child;
+  }
+  if (sub == 0) {
+    const int w = word_id[node];
+    out_word[g] = w < 0 ? 0u : (unsigned)w;
+    out_leaf[g] = (unsigned)node;
+    unsigned up = (unsigned)node;
+    for (int i = 0; i < levels_up; ++i) {
+      const unsigned pa = parent[up];
+      if (pa == 0xffffffffu) break;
+      up = pa;
+    }
+    out_node[g] = up;
+  }
 }
 
 }  // namespace vk

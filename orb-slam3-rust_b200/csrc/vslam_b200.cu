@@ -85,6 +85,11 @@ struct vslam_handle_s {
   size_t fast_smem = 0;
   size_t fast_smem_pad = 0;  // tuning knob VSLAM_FAST_SMEM_PAD: extra bytes per k_fast block (caps its blocks per SM)
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
+  // vocabulary tree of vslam_vocab_upload (device)
+  unsigned* voc_desc = nullptr;
+  int *voc_child_begin = nullptr, *voc_child_ids = nullptr, *voc_word = nullptr;
+  unsigned* voc_parent = nullptr;
+  int voc_nodes = 0;
   int harris_blocks = 1;
   size_t match_rows_smem = 0;  // 0: fall back to k_match + k_match_finalize
   size_t in_img_bytes = 0;
@@ -821,6 +826,7 @@ void vslam_destroy(vslam_handle h) {
   for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
   cudaFree(h->d_coef);
   cudaFree(h->arena_base);
+  cudaFree(h->voc_desc); cudaFree(h->voc_child_begin); cudaFree(h->voc_child_ids); cudaFree(h->voc_parent); cudaFree(h->voc_word);
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; ++i)

@@ -61,4 +61,13 @@ extern "C" {
                                       out_idx: *mut i32, out_dist: *mut i32) -> c_int;
     pub fn vslam_bf_match_crosscheck(h: vslam_handle, query: *const u8, n_query: c_int, train: *const u8, n_train: c_int,
                                      matches: *mut vslam_dmatch, n_matches: *mut c_int) -> c_int;
+    pub fn vslam_fuse_search(h: vslam_handle, kps: *const vslam_keypoint, desc: *const u8, n: c_int, uvr: *const f64,
+                             mp_desc: *const u8, m: c_int, desc_threshold: u32, out_idx: *mut i32, out_dist: *mut i32) -> c_int;
+    pub fn vslam_distinctive_descriptors(h: vslam_handle, desc: *const u8, offsets: *const i32, m: c_int,
+                                         out_idx: *mut i32) -> c_int;
+    // OrbVocabulary (src/vocabulary/mod.rs): tree flattened once after load_from_text, quantisation per keyframe
+    pub fn vslam_vocab_upload(h: vslam_handle, n_nodes: c_int, node_desc: *const u8, child_begin: *const i32,
+                              child_ids: *const i32, parent: *const u32, word_id: *const i32) -> c_int;
+    pub fn vslam_bow_quantize(h: vslam_handle, desc: *const u8, n: c_int, levels_up: c_int, out_word: *mut u32,
+                              out_leaf: *mut u32, out_node: *mut u32) -> c_int;
 }

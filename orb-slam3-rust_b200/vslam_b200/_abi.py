@@ -62,7 +62,8 @@ SYMBOLS = [
     "vslam_triangulate", "vslam_descriptor_distance", "vslam_grid_build", "vslam_grid_query",
     "vslam_search_by_projection", "vslam_bf_match_crosscheck", "vslam_level_info", "vslam_debug_level_image",
     "vslam_debug_fast_corners", "vslam_kernel_launches", "vslam_set_profiling", "vslam_last_stage_ms",
-    "vslam_last_batch_ms", "vslam_fuse_search", "vslam_distinctive_descriptors",
+    "vslam_last_batch_ms", "vslam_fuse_search", "vslam_distinctive_descriptors", "vslam_vocab_upload",
+    "vslam_bow_quantize",
 ]
 
 _lib = None
@@ -98,6 +99,8 @@ def lib():
         L.vslam_bf_match_crosscheck.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(i32)]
         L.vslam_fuse_search.argtypes = [vp, vp, vp, i32, vp, vp, i32, C.c_uint32, vp, vp]
         L.vslam_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
+        L.vslam_vocab_upload.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.vslam_bow_quantize.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.vslam_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i32)]
         L.vslam_debug_level_image.argtypes = [vp, i32, i32, i32, vp, sz]
         L.vslam_debug_fast_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]

@@ -347,6 +347,32 @@ class StereoProcessor:
             self._raise(rc)
         return out[:M]
 
+    def vocab_upload(self, node_desc, child_begin, child_ids, parent, word_id):
+        """Keeps a flattened OrbVocabulary tree (vocabulary/mod.rs:109-206) on the device; node 0 is the root."""
+        nd = np.ascontiguousarray(node_desc, dtype=np.uint8).reshape(-1, 32)
+        cb = np.ascontiguousarray(child_begin, dtype=np.int32)
+        ci = np.ascontiguousarray(child_ids if len(child_ids) else np.zeros(1), dtype=np.int32)
+        pa = np.ascontiguousarray(parent, dtype=np.uint32)
+        wi = np.ascontiguousarray(word_id, dtype=np.int32)
+        if not (len(cb) == len(nd) + 1 and len(pa) == len(nd) and len(wi) == len(nd)):
+            raise ValueError("vocabulary arrays disagree on the node count")
+        rc = self._lib.vslam_vocab_upload(self._h, len(nd), _ptr(nd), _ptr(cb), _ptr(ci), _ptr(pa), _ptr(wi))
+        if rc != _abi.OK:
+            self._raise(rc)
+
+    def bow_quantize(self, desc, levels_up):
+        """OrbVocabulary::transform_descriptor + get_parent_at_level (vocabulary/mod.rs:230-275) for every row of desc:
+        returns (word_id, leaf_node, node_at_level) as uint32 arrays."""
+        d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        n = len(d)
+        w = np.zeros(max(n, 1), dtype=np.uint32)
+        lf = np.zeros(max(n, 1), dtype=np.uint32)
+        nl = np.zeros(max(n, 1), dtype=np.uint32)
+        rc = self._lib.vslam_bow_quantize(self._h, _ptr(d), n, int(levels_up), _ptr(w), _ptr(lf), _ptr(nl))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return w[:n], lf[:n], nl[:n]
+
     # -- introspection (parity tests / profiling)
     def level_info(self, level):
         w, h, s, n = C.c_int(), C.c_int(), C.c_float(), C.c_int()

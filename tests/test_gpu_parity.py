@@ -460,3 +460,49 @@ def test_distinctive_descriptors(sp752, oracle, pairs):
     desc = np.concatenate(groups)
     off = np.array(offsets, np.int32)
     assert np.array_equal(sp752.distinctive_descriptors(desc, off), oracle.distinctive_descriptors(desc, off))
+
+
+def _random_vocabulary(oracle, k, depth, seed):
+    """DBoW2-shaped k-ary tree of the given depth, nodes in breadth-first file order (as ORBvoc.txt lists them)."""
+    rng = np.random.default_rng(seed)
+    parents, leaf = [], []
+    level = [0]
+    nid = 0
+    for lv in range(depth):
+        nxt = []
+        for p in level:
+            for _ in range(k):
+                nid += 1
+                parents.append(p)
+                leaf.append(1 if lv == depth - 1 else 0)
+                nxt.append(nid)
+        level = nxt
+    nd = rng.integers(0, 256, (len(parents), 32), dtype=np.uint8)
+    nd[5] = nd[4]  # a tie between two siblings: the first must win
+    return oracle.make_vocabulary_arrays(parents, leaf, nd)
+
+
+def test_bow_quantize(sp752, oracle, pairs):
+    from vslam_b200 import VslamError
+
+    l, r = pairs(0)
+    desc = sp752.process(l, r).left_features.descriptors
+    with pytest.raises(VslamError):
+        # a fresh processor has no vocabulary
+        from vslam_b200 import CameraModel, StereoProcessor, synth
+        with StereoProcessor(CameraModel(**synth.EUROC_CAMERA), 200, 320, 240, max_batch=1) as sp:
+            sp.bow_quantize(desc[:4], 4)
+    for k, depth, seed in ((10, 4, 1), (3, 6, 2), (7, 1, 3)):
+        voc = _random_vocabulary(oracle, k, depth, seed)
+        sp752.vocab_upload(*voc)
+        q = np.concatenate([desc, voc[0][1:200], np.zeros((1, 32), np.uint8)])  # real descriptors + exact node copies
+        for lu in (0, 2, depth - 1, depth + 3):
+            got = sp752.bow_quantize(q, lu)
+            ref = oracle.bow_quantize(q, voc, lu)
+            for a, b, name in zip(got, ref, ("word", "leaf", "node_at_level")):
+                assert np.array_equal(a, b), f"{name} k={k} L={depth} levels_up={lu}"
+    assert all(len(x) == 0 for x in sp752.bow_quantize(np.zeros((0, 32), np.uint8), 2))
+    # root-only vocabulary: every descriptor maps to word 0 at the root
+    sp752.vocab_upload(*oracle.make_vocabulary_arrays([], [], np.zeros((0, 32), np.uint8)))
+    w, lf, up = sp752.bow_quantize(desc[:9], 3)
+    assert not w.any() and not lf.any() and not up.any()

@@ -122,3 +122,66 @@ def test_distinctive_descriptor_minmax_first_wins(oracle):
     assert list(out) == [2, 0, -1, 0]
     # all equal maxima -> first index
     assert list(oracle.distinctive_descriptors(np.stack([a, b]), np.array([0, 2], np.int32))) == [0]
+
+
+def _py_bow(desc, vocab, levels_up):
+    """Independent pure-Python restatement of vocabulary/mod.rs:230-251, 263-275 (small cases only)."""
+    nd, cb, ci, pa, wi = vocab
+    out = []
+    for d in desc:
+        node = 0
+        while cb[node + 1] != cb[node]:
+            ch = ci[cb[node]:cb[node + 1]]
+            dist = [int(np.unpackbits(d ^ nd[c]).sum()) for c in ch]
+            node = int(ch[int(np.argmin(dist))])  # argmin returns the first minimum == strict `<` scan
+        up = node
+        for _ in range(levels_up):
+            if pa[up] == 0xFFFFFFFF:
+                break
+            up = int(pa[up])
+        out.append((max(int(wi[node]), 0), node, up))
+    return np.array(out, dtype=np.uint32).T
+
+
+def test_bow_quantize_tree_descent_quirks(oracle):
+    # k = 3, L = 2 tree written in DBoW2 file order; node 4 and 5 have IDENTICAL descriptors (tie -> first child wins)
+    rng = np.random.default_rng(3)
+    parents = [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3]
+    leaf = [0, 0, 0] + [1] * 9
+    nd = rng.integers(0, 256, (12, 32), dtype=np.uint8)
+    nd[4] = nd[3]  # file line 4 -> node 5, line 3 -> node 4
+    voc = oracle.make_vocabulary_arrays(parents, leaf, nd)
+    assert list(voc[1][:5]) == [0, 3, 6, 9, 12] and voc[3][0] == 0xFFFFFFFF and list(voc[4][:5]) == [-1, -1, -1, -1, 0]
+    q = np.stack([nd[3] ^ nd[0] ^ nd[0], nd[7], nd[11]])  # exact copies of node 4(=5), node 8, node 12
+    q[0] = nd[3]
+    # force the first level towards node 1 / 2 / 3 by querying the children's own parents' descriptors is not needed:
+    # compare with the independent restatement instead
+    d = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    for lu in (0, 1, 2, 5):
+        got = np.stack(oracle.bow_quantize(np.concatenate([q, d]), voc, lu))
+        assert np.array_equal(got, _py_bow(np.concatenate([q, d]), voc, lu)), f"levels_up={lu}"
+    # a descriptor equal to nodes 4 and 5, once under parent 1: leaf must be 4 (first), never 5
+    w, lf, up = oracle.bow_quantize(np.stack([nd[3]]), (voc[0], np.array([0, 2, 2, 2] + [2] * 10, np.int32),
+                                                         np.array([4, 5], np.int32), voc[3], voc[4]), 1)
+    assert (int(w[0]), int(lf[0])) == (0, 4)
+    # levels_up beyond the root stops at the root (parent == u32::MAX)
+    assert int(oracle.bow_quantize(np.stack([nd[3]]), voc, 9)[2][0]) == 0
+
+
+def test_bow_quantize_degenerate_trees(oracle):
+    rng = np.random.default_rng(4)
+    d = rng.integers(0, 256, (3, 32), dtype=np.uint8)
+    # root only: the root is a leaf without a word id -> word 0, leaf 0
+    voc = oracle.make_vocabulary_arrays([], [], np.zeros((0, 32), np.uint8))
+    w, lf, up = oracle.bow_quantize(d, voc, 4)
+    assert list(w) == [0, 0, 0] and list(lf) == [0, 0, 0] and list(up) == [0, 0, 0]
+    # a node whose parent id is not smaller than its own id is never linked (load_from_text: `parent_id < nodes.len()`)
+    voc = oracle.make_vocabulary_arrays([0, 5, 0], [1, 1, 1], rng.integers(0, 256, (3, 32), dtype=np.uint8))
+    assert list(voc[2]) == [1, 3]            # children of the root: nodes 1 and 3; node 2 dangles
+    assert list(voc[4]) == [-1, 0, 1, 2]     # ... but still consumed a word id
+    w, lf, _ = oracle.bow_quantize(d, voc, 0)
+    assert set(lf.tolist()) <= {1, 3} and all(int(x) in (0, 2) for x in w)
+    # an inner node flagged non-leaf without children is a leaf with word_id None -> word 0
+    voc = oracle.make_vocabulary_arrays([0], [0], rng.integers(0, 256, (1, 32), dtype=np.uint8))
+    w, lf, _ = oracle.bow_quantize(d, voc, 0)
+    assert list(w) == [0, 0, 0] and list(lf) == [1, 1, 1]
