@@ -709,14 +709,24 @@ __device__ int warp_retain_best(T* rec, int n, int n_points, IdxT* Ll, IdxT* Rl,
 __device__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y, float scale4) {
   // Ix = [1 2 1]^T (rows) applied to dx[r][j] = v[r][j+1] - v[r][j-1];  Iy = sm[r+1][j] - sm[r-1][j] with
   // sm[r][j] = v[r][j-1] + 2 v[r][j] + v[r][j+1].  Three rows of (dx, sm) are kept live while walking 9 rows.
-  const uint8_t* p0 = img + (size_t)(y - 4) * pitch + (x - 4);
+  // the 9 bytes x-4 .. x+4 of a row come from three aligned words (one L1 wavefront each instead of nine byte loads:
+  // the threads of a warp sit on different corners, so every load instruction touches 32 different lines)
+  const uint8_t* p0 = img + (size_t)(y - 4) * pitch + ((x - 4) & ~3);
+  const unsigned sh = 8u * (unsigned)((x - 4) & 3);
   int dx0[7], dx1[7], dx2[7], sm0[7], sm1[7], sm2[7];
   int a = 0, b = 0, c = 0;
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p0 + (size_t)r * pitch);
+    const unsigned w0 = q[0], w1 = q[1], w2 = q[2];
+    const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), top = w2 >> sh;
     int v[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) v[j] = p0[r * pitch + j];
+    for (int j = 0; j < 4; ++j) {
+      v[j] = (int)((lo >> (8 * j)) & 0xffu);
+      v[4 + j] = (int)((hi >> (8 * j)) & 0xffu);
+    }
+    v[8] = (int)(top & 0xffu);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       dx0[j] = dx1[j];
