@@ -111,14 +111,20 @@ def test_stage_pyramid_fast_blur(sp752, oracle, pairs):
 
 
 @pytest.mark.parametrize("w,h,nfeat,fast_t", [(641, 479, 800, 20), (333, 255, 300, 7), (1001, 403, 1500, 35),
-                                              (260, 258, 200, 20)])
+                                              (260, 258, 200, 20), (2304, 160, 700, 20)])
 def test_stage_parity_odd_sizes(oracle, camera_dict, w, h, nfeat, fast_t):
     """Widths / heights that are not multiples of 4, 8 or 16 and other FAST thresholds: exercises the border selectors
-    of k_blur, the clamped word offsets of k_resize, the partial column groups / strips of k_fast."""
+    of k_blur, the clamped word offsets of k_resize, the partial column groups / strips of k_fast; the 2304-wide case
+    takes k_fast's full-scan NMS path (x does not fit the 11-bit field of the sparse corner lists) and bitmask rows of
+    more than 32 words."""
     from vslam_b200 import STAGE_BLURRED, STAGE_PYRAMID, CameraModel, StereoProcessor, synth
 
-    l, r = synth.make_stereo_pair(11, w, h)
-    l, r = l.numpy(), r.numpy()
+    if w <= 1600:
+        l, r = synth.make_stereo_pair(11, w, h)
+        l, r = l.numpy(), r.numpy()
+    else:  # the generator's canvas margin does not scale to this width: tile a 768-wide pair
+        l, r = synth.make_stereo_pair(11, w // 3, h)
+        l, r = np.tile(l.numpy(), (1, 3)), np.tile(r.numpy(), (1, 3))
     with StereoProcessor(CameraModel(**camera_dict), nfeat, w, h, max_batch=1, fast_threshold=fast_t) as sp:
         fr = sp.process(l, r)
         for eye, img in enumerate((l, r)):
