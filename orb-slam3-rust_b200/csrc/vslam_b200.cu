@@ -82,6 +82,8 @@ struct vslam_handle_s {
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
   int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
   int sm_count = 148;
+  bool blur_after_fast = true;          // fork the blur after k_fast (it then fills the SMs under the latency-bound selection
+                                        // chain) instead of right after the pyramid; VSLAM_BLUR_AFTER_FAST=0 restores the latter
   size_t fast_smem = 0;
   size_t fast_smem_pad = 0;  // tuning knob VSLAM_FAST_SMEM_PAD: extra bytes per k_fast block (caps its blocks per SM)
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
@@ -430,18 +432,27 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   // latency-bound selection chain (k_select1/k_harris/k_select2 keep the SMs mostly idle).
   const bool fork = !prof;
   cudaStream_t sb = fork ? s.stream2 : st;
-  if (fork) {
+  auto launch_blur_forked = [&]() -> int {
     CU_TRY(h, cudaEventRecord(s.ev_pyr, st));
     CU_TRY(h, cudaStreamWaitEvent(sb, s.ev_pyr, 0));
     vk::k_blur<<<blur_grid(h, nimg), 128, 0, sb>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
     CU_TRY(h, cudaEventRecord(s.ev_blur, sb));
+    return VSLAM_OK;
+  };
+  if (fork && !h->blur_after_fast) {
+    int rcb = launch_blur_forked();
+    if (rcb != VSLAM_OK) return rcb;
   }
   if (P.total_fast_strips > 0) {
     dim3 grid(P.total_fast_strips, nimg);
     vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)) + h->fast_smem_pad, st>>>(P, in_l, in_r, s.d_pyr,
                                                                                       s.d_strip_cnt, s.d_strip_rec);
     h->launches++;
+  }
+  if (fork && h->blur_after_fast) {  // the blur starts when k_fast is done: it fills the SMs under the selection chain
+    int rcb = launch_blur_forked();
+    if (rcb != VSLAM_OK) return rcb;
   }
   mark();  // 2
   {
@@ -750,6 +761,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
+  if (const char* ev = getenv("VSLAM_BLUR_AFTER_FAST")) h->blur_after_fast = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BLUR_BPS")) h->blur_blocks_per_sm = std::max(atoi(ev), 0);
   if (const char* ev = getenv("VSLAM_BLUR_ROWS")) h->blur_rows = std::min(std::max(atoi(ev), 8), 4096);
   int rc = build_params(h);
