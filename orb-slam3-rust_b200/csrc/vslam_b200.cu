@@ -349,8 +349,18 @@ size_t carve_results(unsigned char* base, size_t nfr, int cap, FrameLayout* F) {
 int alloc_slot(vslam_handle h, Slot& s) {
   const PyrP& P = h->P;
   const size_t nimg = 2 * (size_t)h->max_batch, nfr = (size_t)h->max_batch;
-  CU_TRY(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  CU_TRY(h, cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+  {
+    // VSLAM_BLUR_PRIO (tuning knob): -1 = blur stream at the highest priority, 1 = lowest, 0 = default
+    int lo = 0, hi = 0, p1 = 0, p2 = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (const char* ev = getenv("VSLAM_BLUR_PRIO")) {
+      const int v = atoi(ev);
+      p2 = v < 0 ? hi : (v > 0 ? lo : 0);
+      p1 = v < 0 ? lo : (v > 0 ? hi : 0);
+    }
+    CU_TRY(h, cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, p1));
+    CU_TRY(h, cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, p2));
+  }
   CU_TRY(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   CU_TRY(h, cudaEventCreateWithFlags(&s.ev_pyr, cudaEventDisableTiming));
   CU_TRY(h, cudaEventCreateWithFlags(&s.ev_blur, cudaEventDisableTiming));
