@@ -31,6 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "orb-slam3-rust_b200"))
 METRIC = "stereo frames/s (ORB+stereo match, 752x480)"
 W, H, NFEAT = 752, 480, 1200
 LEVEL_PIXELS = 1_117_367  # sum of the 8 pyramid levels at 752x480
+CONFIG_NAME = "configs[1]"
 
 
 _REAL_STDOUT = None
@@ -67,7 +68,16 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-frames", type=int, default=4)
-    return ap.parse_args()
+    ap.add_argument("--workload", default="euroc", choices=["euroc", "720p"],
+                    help="euroc = BASELINE configs[1] (752x480, 1200 features; the headline, default); 720p = configs[2] "
+                         "(1280x720, 2000 features) for the resolution sweep")
+    a = ap.parse_args()
+    if a.workload == "720p":
+        global W, H, NFEAT, LEVEL_PIXELS, METRIC, CONFIG_NAME
+        W, H, NFEAT, LEVEL_PIXELS = 1280, 720, 2000, 2_853_088
+        METRIC = "stereo frames/s (ORB+stereo match, 1280x720)"
+        CONFIG_NAME = "configs[2]"
+    return a
 
 
 # --------------------------------------------------------------------------------------- CPU reference path
@@ -151,14 +161,14 @@ def run_reference(args, rank):
     ref.close()
     value = frames / wall
     cores = ref.cores
-    sample = (f"{n} stereo frames per step ({n // cores} per core, {nuniq} distinct synthetic 752x480 pairs), "
-              f"cv2.ORB_create(1200,1.2,8,31,0,2,HARRIS,31,20).detectAndCompute on L and R (the cv::ORB the reference "
+    sample = (f"{n} stereo frames per step ({n // cores} per core, {nuniq} distinct synthetic {W}x{H} pairs), "
+              f"cv2.ORB_create({NFEAT},1.2,8,31,0,2,HARRIS,31,20).detectAndCompute on L and R (the cv::ORB the reference "
               f"calls) + C++ restatement of match_features/triangulate; one process per core, cv2.setNumThreads(1)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch of synthetic 752x480 stereo frames, 1200 features, 8 levels, scale 1.2"},
+        "config": {"workload": f"{CONFIG_NAME}: batch of synthetic {W}x{H} stereo frames, {NFEAT} features, 8 levels, scale 1.2"},
         "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -362,7 +372,7 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = tj.get(names[dom].split("(")[0].split(" ")[0])
-        if ent and ent["images_per_launch"] == images_per_launch:
+        if ent and ent["images_per_launch"] == images_per_launch and (W, H) == (752, 480):
             traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
     except Exception:
         pass
@@ -427,10 +437,10 @@ def main():
             "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"configs[1]: batch of {n} synthetic 752x480 stereo frames per GPU, 1200 features, 8 levels, "
+            "config": {"workload": f"{CONFIG_NAME}: batch of {n} synthetic {W}x{H} stereo frames per GPU, {NFEAT} features, 8 levels, "
                                    "scale 1.2: ORB extract x2 + stereo match + triangulate",
                        "frames_per_gpu_per_step": n, "distinct_frames": nuniq, "chunk": args.batch,
-                       "cache": "inputs larger than L2 (1.44 GB per step vs 126 MB L2); no flush needed",
+                       "cache": f"inputs larger than L2 ({2 * n * img_bytes / 1e9:.2f} GB per step vs 126 MB L2); no flush needed",
                        "sharding": "independent frames per rank, no collective"},
             "ms_per_step_wall": round(wall_ms / args.steps, 3), "p50_ms_per_frame": round(dev_ms / args.steps / n, 5),
             "p50_ms_single_pair_latency": round(p50_single, 3),
