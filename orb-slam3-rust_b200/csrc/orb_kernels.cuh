@@ -977,7 +977,10 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
   return d;
 }
 
-constexpr int kBlurRing = 8;  // source rows in flight per lane (cp.async ring in shared memory)
+#ifndef VSLAM_BLUR_RING
+#define VSLAM_BLUR_RING 8
+#endif
+constexpr int kBlurRing = VSLAM_BLUR_RING;  // source rows in flight per lane (cp.async ring in shared memory), power of 2
 __device__ __forceinline__ void blur_item(const PyrP& P, const int img, const int item, const uint8_t* __restrict__ in_l,
                                           const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                           uint8_t* __restrict__ blur) {
@@ -1100,17 +1103,17 @@ __device__ __forceinline__ void blur_item(const PyrP& P, const int img, const in
   };
 
   f32x2_t win[7][4];  // row-pass results of the last 7 source rows; every index is a compile-time constant
-  static_assert(kBlurRing == 8, "slot arithmetic below assumes a ring of 8 rows");
+  static_assert((kBlurRing & (kBlurRing - 1)) == 0 && kBlurRing >= 2, "ring size must be a power of two");
 #pragma unroll
   for (int t = 0; t < kBlurRing; ++t) issue_row(t, t);
 #pragma unroll
   for (int t = 0; t < 6; ++t) {  // fill the window: source rows 0..5 of the item
     unsigned cw[4];
-    take_row(t, cw);
+    take_row(t & (kBlurRing - 1), cw);
     row_pass(cw, win[t]);
-    issue_row(t + kBlurRing, t);  // the slot is free once its words sit in registers (row_pass consumed them)
+    issue_row(t + kBlurRing, t & (kBlurRing - 1));  // the slot is free once its words sit in registers
   }
-  int slot = 6;  // ring slot of source row t (t & 7), carried because 7 rows per trip do not divide the ring
+  int slot = 6 & (kBlurRing - 1);  // ring slot of source row t, carried because 7 rows per trip do not divide the ring
 #pragma unroll 1
   for (int blk = 0; blk < nblk; ++blk) {
     const int tb = 6 + 7 * blk;
@@ -1159,7 +1162,7 @@ __global__ void __launch_bounds__(128, VSLAM_BLUR_MINB) k_blur(const __grid_cons
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// A6 — steered BRIEF + KeyPoint assembly.  grid = (ceil(kp_cap / 8), n_img), block = 256 (8 warps, one keypoint
+// A6 — steered BRIEF + KeyPoint assembly.  grid = (ceil(kp_cap / 4), n_img), block = 128 (4 warps, one keypoint
 // each); lane b computes descriptor byte b (16 rotated pattern points).  Output order: levels 0..n-1 concatenated.
 // ----------------------------------------------------------------------------------------------------------
 // (float)cos((double)x), (float)sin((double)x) for 0 <= x < 2*pi + eps, as OpenCV's steering computes them with the
@@ -1206,13 +1209,17 @@ constexpr int kAngleRows = 2 * kAngleR + 1;     // 31
 constexpr int kAngleRowWords = 9;               // 31 px + up to 3 alignment bytes = 9 words
 constexpr int kPatchWords = kBriefRows * kBriefRowWords + kAngleRows * kAngleRowWords;
 
-__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
+#ifndef VSLAM_BRIEF_WARPS
+#define VSLAM_BRIEF_WARPS 4
+#endif
+constexpr int kBriefWarps = VSLAM_BRIEF_WARPS;  // keypoints (warps) per block
+__global__ void __launch_bounds__(32 * kBriefWarps) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                                const uint8_t* __restrict__ blur, const LvlKp* __restrict__ lvl_kp,
                                                const int* __restrict__ lvl_cnt, const FrameLayout F) {
-  __shared__ uint32_t s_patch[8][kPatchWords];
+  __shared__ uint32_t s_patch[kBriefWarps][kPatchWords];
   const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * 8 + warp;
+  const int j = blockIdx.x * kBriefWarps + warp;
   const int frame = P.eyes == 2 ? img >> 1 : img, eye = P.eyes == 2 ? (img & 1) : 0;  // eyes is 1 or 2
   const int* cnt = lvl_cnt + (long long)img * P.nlevels;
   int total = 0, l = -1, jl = 0;

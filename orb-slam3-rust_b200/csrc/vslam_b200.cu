@@ -484,8 +484,8 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   }
   mark();  // 4
   {
-    dim3 grid((P.kp_cap + 7) / 8, nimg);
-    vk::k_brief<<<grid, 256, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    dim3 grid((P.kp_cap + vk::kBriefWarps - 1) / vk::kBriefWarps, nimg);
+    vk::k_brief<<<grid, 32 * vk::kBriefWarps, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
     h->launches++;
   }
   mark();  // 5
