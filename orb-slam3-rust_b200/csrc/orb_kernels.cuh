@@ -991,8 +991,8 @@ __device__ __forceinline__ void blur_item(const PyrP& P, const int img, const in
   const int li = item - L.blur_item0;
   const int strip = li / L.blur_ncg, cg = li - strip * L.blur_ncg;
   if (strip >= L.blur_nstr) return;  // padding lanes (no warp collectives below)
-  const int x = 8 * cg, y0 = strip * L.blur_rs;
-  const int rs = min(L.blur_rs, L.h - y0);  // output rows of this item
+  const int x = 8 * (cg + L.blur_cg0), y0 = L.blur_y0 + strip * L.blur_rs;
+  const int rs = min(L.blur_rs, L.blur_y1 - y0);  // output rows of this item
   const int nblk = (L.blur_rs + 6) / 7;     // main-loop trips of 7 output rows (warp-uniform)
   int spitch;
   const uint8_t* src = level_ptr(P, l, img, in_l, in_r, pyr, spitch);

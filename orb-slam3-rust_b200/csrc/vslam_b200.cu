@@ -82,6 +82,7 @@ struct vslam_handle_s {
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
   int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
   int sm_count = 148;
+  bool blur_full = false;               // VSLAM_BLUR_FULL=1: blur whole levels, not only the region BRIEF can sample
   bool blur_after_fast = true;          // fork the blur after k_fast (it then fills the SMs under the latency-bound selection
                                         // chain) instead of right after the pyramid; VSLAM_BLUR_AFTER_FAST=0 restores the latter
   size_t fast_smem = 0;
@@ -244,9 +245,20 @@ int build_params(vslam_handle h) {
     strip0 += L.fast_nstrips;
     L.rec_off = (int)rec_off;
     rec_off += (long long)L.fast_nstrips * L.strip_cap;
-    L.blur_ncg = (L.w + 7) / 8;
-    L.blur_nstr = (L.h + h->blur_rows - 1) / h->blur_rows;
-    L.blur_rs = (L.h + L.blur_nstr - 1) / L.blur_nstr;
+    {
+      // Keypoints lie >= eb px from every border (runByImageBorder) and the rotated BRIEF pattern reaches 18 px, so the
+      // blurred level is only ever sampled in [eb - 18, w - eb + 18) x [eb - 18, h - eb + 18): blur just that (whole
+      // 8-column groups).  VSLAM_BLUR_FULL=1 blurs the whole level (debug / stage comparisons of the border ring).
+      const int m = h->blur_full ? 0 : std::max(eb - 18, 0);
+      const int bx0 = std::min(m, L.w - 1), bx1 = std::max(L.w - m, bx0 + 1);
+      L.blur_y0 = std::min(m, L.h - 1);
+      L.blur_y1 = std::max(L.h - m, L.blur_y0 + 1);
+      L.blur_cg0 = bx0 / 8;
+      L.blur_ncg = (bx1 - 1) / 8 - L.blur_cg0 + 1;
+      const int bh = L.blur_y1 - L.blur_y0;
+      L.blur_nstr = (bh + h->blur_rows - 1) / h->blur_rows;
+      L.blur_rs = (bh + L.blur_nstr - 1) / L.blur_nstr;
+    }
     L.blur_item0 = tile0;
     tile0 += (L.blur_ncg * L.blur_nstr + 31) & ~31;
   }
@@ -771,6 +783,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
+  if (const char* ev = getenv("VSLAM_BLUR_FULL")) h->blur_full = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BLUR_AFTER_FAST")) h->blur_after_fast = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BLUR_BPS")) h->blur_blocks_per_sm = std::max(atoi(ev), 0);
   if (const char* ev = getenv("VSLAM_BLUR_ROWS")) h->blur_rows = std::min(std::max(atoi(ev), 8), 4096);

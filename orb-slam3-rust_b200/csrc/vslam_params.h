@@ -27,6 +27,8 @@ struct LevelP {
   int rec_off;            // record offset of this level inside the per-image strip-record slab
   int blur_item0, blur_ncg, blur_nstr, blur_rs;  // blur lane items: first item (multiple of 32), 8-column groups,
                                                  // row strips, rows per strip
+  int blur_cg0, blur_y0, blur_y1;                // first column group and row range [y0, y1) that are blurred: only what
+                                                 // BRIEF can sample (>= edge_threshold - 18 px from every border)
 };
 
 struct PyrP {

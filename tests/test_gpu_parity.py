@@ -103,7 +103,9 @@ def test_stage_pyramid_fast_blur(sp752, oracle, pairs):
         st = oracle.detect_stages(img, 1200)
         for lvl in range(8):
             assert np.array_equal(sp752.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
-            assert np.array_equal(sp752.debug_level_image(STAGE_BLURRED, eye, lvl), st["blurred"][lvl]), f"blur {lvl}"
+            # only the region BRIEF can sample is blurred: >= edge_threshold - 18 = 13 px from every border
+            assert np.array_equal(sp752.debug_level_image(STAGE_BLURRED, eye, lvl)[13:-13, 13:-13],
+                                  st["blurred"][lvl][13:-13, 13:-13]), f"blur {lvl}"
             c = sp752.debug_fast_corners(eye, lvl)
             o = st["fast"][lvl]
             ref = np.stack([o["x"], o["y"], o["resp"].astype(np.int32)], 1)
@@ -131,7 +133,8 @@ def test_stage_parity_odd_sizes(oracle, camera_dict, w, h, nfeat, fast_t):
             st = oracle.detect_stages(img, nfeat, fast_threshold=fast_t)
             for lvl in range(8):
                 assert np.array_equal(sp.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
-                assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, eye, lvl), st["blurred"][lvl]), f"blur {lvl}"
+                assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, eye, lvl)[13:-13, 13:-13],
+                                      st["blurred"][lvl][13:-13, 13:-13]), f"blur {lvl}"
                 c = sp.debug_fast_corners(eye, lvl)
                 o = st["fast"][lvl]
                 ref = np.stack([o["x"], o["y"], o["resp"].astype(np.int32)], 1)
@@ -512,3 +515,17 @@ def test_bow_quantize(sp752, oracle, pairs):
     sp752.vocab_upload(*oracle.make_vocabulary_arrays([], [], np.zeros((0, 32), np.uint8)))
     w, lf, up = sp752.bow_quantize(desc[:9], 3)
     assert not w.any() and not lf.any() and not up.any()
+
+
+def test_blur_full_level_option(oracle, camera_dict, monkeypatch):
+    """VSLAM_BLUR_FULL=1 blurs whole levels (reflect-101 borders included), bit-exact with the oracle everywhere."""
+    from vslam_b200 import STAGE_BLURRED, CameraModel, StereoProcessor, synth
+
+    monkeypatch.setenv("VSLAM_BLUR_FULL", "1")
+    l, r = synth.make_stereo_pair(21, 333, 255)
+    l, r = l.numpy(), r.numpy()
+    with StereoProcessor(CameraModel(**camera_dict), 300, 333, 255, max_batch=1) as sp:
+        sp.process(l, r)
+        st = oracle.detect_stages(l, 300)
+        for lvl in range(8):
+            assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, 0, lvl), st["blurred"][lvl]), f"blur {lvl}"
