@@ -225,7 +225,8 @@ int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up
 
 /* ---- introspection for parity tests and profiling ---------------------------------------------------------- */
 enum {
-  VSLAM_STAGE_PYRAMID = 0,  /* u8 level image */
+  VSLAM_STAGE_PYRAMID = 0,  /* u8 level image; levels >= 1: the outer edge_threshold - 21 px ring, which no stage
+                             * reads, is not computed (whole levels with VSLAM_PYR_FULL=1) */
   VSLAM_STAGE_BLURRED = 1   /* u8 blurred level image; only the part BRIEF can sample is computed: pixels at least
                              * edge_threshold - 18 px from every border (whole levels with VSLAM_BLUR_FULL=1) */
 };

@@ -91,12 +91,12 @@ __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_
   const LevelP& D = P.lv[l];
   const LevelP& S = P.lv[l - 1];
   const int img = blockIdx.y;
-  const int ncg = (D.w + 3) >> 2;
+  const int ncg = D.pyr_ncg;
   const int item = blockIdx.x * 128 + threadIdx.x;
-  const int strip = item / ncg, cg = item - strip * ncg;
-  const int y0 = strip * rs;
-  if (y0 >= D.h) return;
-  const int rows = min(rs, D.h - y0);
+  const int strip = item / ncg, cg = D.pyr_cg0 + (item - strip * ncg);
+  const int y0 = D.pyr_y0 + strip * rs;
+  if (y0 >= D.pyr_y1) return;
+  const int rows = min(rs, D.pyr_y1 - y0);
   int spitch;
   const uint8_t* src = level_ptr(P, l - 1, img, in_l, in_r, pyr, spitch);
   uint8_t* dst = pyr + (long long)img * P.pyr_img_stride + D.pyr_off + (size_t)y0 * D.pitch + 4 * cg;

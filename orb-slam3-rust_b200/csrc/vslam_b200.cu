@@ -82,6 +82,7 @@ struct vslam_handle_s {
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
   int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
   int sm_count = 148;
+  bool pyr_full = false;                // VSLAM_PYR_FULL=1: compute whole pyramid levels, not only what is read
   bool blur_full = false;               // VSLAM_BLUR_FULL=1: blur whole levels, not only the region BRIEF can sample
   bool blur_after_fast = true;          // fork the blur after k_fast (it then fills the SMs under the latency-bound selection
                                         // chain) instead of right after the pyramid; VSLAM_BLUR_AFTER_FAST=0 restores the latter
@@ -245,6 +246,16 @@ int build_params(vslam_handle h) {
     strip0 += L.fast_nstrips;
     L.rec_off = (int)rec_off;
     rec_off += (long long)L.fast_nstrips * L.strip_cap;
+    {
+      // Pyramid levels >= 1: nothing reads the outer eb - 21 px ring (FAST reaches eb - 4, Harris eb - 4, the IC disc
+      // eb - 15, the restricted blur eb - 21, the next level's needed ring maps inside this one), so k_resize skips it.
+      const int m = (h->blur_full || h->pyr_full) ? 0 : std::max(eb - 21, 0);
+      const int px0 = std::min(m, L.w - 1), px1 = std::max(L.w - m, px0 + 1);
+      L.pyr_y0 = std::min(m, L.h - 1);
+      L.pyr_y1 = std::max(L.h - m, L.pyr_y0 + 1);
+      L.pyr_cg0 = px0 / 4;
+      L.pyr_ncg = (px1 - 1) / 4 - L.pyr_cg0 + 1;
+    }
     {
       // Keypoints lie >= eb px from every border (runByImageBorder) and the rotated BRIEF pattern reaches 18 px, so the
       // blurred level is only ever sampled in [eb - 18, w - eb + 18) x [eb - 18, h - eb + 18): blur just that (whole
@@ -444,9 +455,10 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   CU_TRY(h, cudaMemsetAsync(s.d_lay.hdr, 0, sizeof(ResHdr) * (size_t)frames, st));
   mark();  // 0
   for (int l = 1; l < P.nlevels; ++l) {
-    const int rs = h->resize_rows, nstr = (P.lv[l].h + rs - 1) / rs, ncg = (P.lv[l].w + 3) / 4;
+    const int ph = P.lv[l].pyr_y1 - P.lv[l].pyr_y0;
+    const int rs = h->resize_rows, nstr = (ph + rs - 1) / rs, ncg = P.lv[l].pyr_ncg;
     dim3 grid((ncg * nstr + 127) / 128, nimg);
-    vk::k_resize<<<grid, 128, 0, st>>>(P, l, (P.lv[l].h + nstr - 1) / nstr, in_l, in_r, s.d_pyr, h->d_coef);
+    vk::k_resize<<<grid, 128, 0, st>>>(P, l, (ph + nstr - 1) / nstr, in_l, in_r, s.d_pyr, h->d_coef);
     h->launches++;
   }
   mark();  // 1
@@ -784,6 +796,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
   if (const char* ev = getenv("VSLAM_BLUR_FULL")) h->blur_full = atoi(ev) != 0;
+  if (const char* ev = getenv("VSLAM_PYR_FULL")) h->pyr_full = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BLUR_AFTER_FAST")) h->blur_after_fast = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BLUR_BPS")) h->blur_blocks_per_sm = std::max(atoi(ev), 0);
   if (const char* ev = getenv("VSLAM_BLUR_ROWS")) h->blur_rows = std::min(std::max(atoi(ev), 8), 4096);

@@ -27,6 +27,8 @@ struct LevelP {
   int rec_off;            // record offset of this level inside the per-image strip-record slab
   int blur_item0, blur_ncg, blur_nstr, blur_rs;  // blur lane items: first item (multiple of 32), 8-column groups,
                                                  // row strips, rows per strip
+  int pyr_cg0, pyr_ncg, pyr_y0, pyr_y1;          // 4-column groups and rows [y0, y1) of this level that k_resize computes: what
+                                                 // FAST, Harris, IC angle, the (restricted) blur and the next level read
   int blur_cg0, blur_y0, blur_y1;                // first column group and row range [y0, y1) that are blurred: only what
                                                  // BRIEF can sample (>= edge_threshold - 18 px from every border)
 };

@@ -102,7 +102,10 @@ def test_stage_pyramid_fast_blur(sp752, oracle, pairs):
     for eye, img in enumerate((l, r)):
         st = oracle.detect_stages(img, 1200)
         for lvl in range(8):
-            assert np.array_equal(sp752.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
+            # levels >= 1: the outer edge_threshold - 21 = 10 px ring is read by nothing and not computed
+            b = 10 if lvl else 0
+            g, o = sp752.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]
+            assert np.array_equal(g[b:g.shape[0] - b, b:g.shape[1] - b], o[b:o.shape[0] - b, b:o.shape[1] - b]), f"pyr {lvl}"
             # only the region BRIEF can sample is blurred: >= edge_threshold - 18 = 13 px from every border
             assert np.array_equal(sp752.debug_level_image(STAGE_BLURRED, eye, lvl)[13:-13, 13:-13],
                                   st["blurred"][lvl][13:-13, 13:-13]), f"blur {lvl}"
@@ -132,7 +135,9 @@ def test_stage_parity_odd_sizes(oracle, camera_dict, w, h, nfeat, fast_t):
         for eye, img in enumerate((l, r)):
             st = oracle.detect_stages(img, nfeat, fast_threshold=fast_t)
             for lvl in range(8):
-                assert np.array_equal(sp.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
+                b = 10 if lvl else 0  # levels >= 1: the outer 10 px ring is not computed (nothing reads it)
+                g, o = sp.debug_level_image(STAGE_PYRAMID, eye, lvl), st["pyramid"][lvl]
+                assert np.array_equal(g[b:g.shape[0] - b, b:g.shape[1] - b], o[b:o.shape[0] - b, b:o.shape[1] - b]), f"pyr {lvl}"
                 assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, eye, lvl)[13:-13, 13:-13],
                                       st["blurred"][lvl][13:-13, 13:-13]), f"blur {lvl}"
                 c = sp.debug_fast_corners(eye, lvl)
@@ -519,7 +524,7 @@ def test_bow_quantize(sp752, oracle, pairs):
 
 def test_blur_full_level_option(oracle, camera_dict, monkeypatch):
     """VSLAM_BLUR_FULL=1 blurs whole levels (reflect-101 borders included), bit-exact with the oracle everywhere."""
-    from vslam_b200 import STAGE_BLURRED, CameraModel, StereoProcessor, synth
+    from vslam_b200 import STAGE_BLURRED, STAGE_PYRAMID, CameraModel, StereoProcessor, synth
 
     monkeypatch.setenv("VSLAM_BLUR_FULL", "1")
     l, r = synth.make_stereo_pair(21, 333, 255)
@@ -529,3 +534,4 @@ def test_blur_full_level_option(oracle, camera_dict, monkeypatch):
         st = oracle.detect_stages(l, 300)
         for lvl in range(8):
             assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, 0, lvl), st["blurred"][lvl]), f"blur {lvl}"
+            assert np.array_equal(sp.debug_level_image(STAGE_PYRAMID, 0, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
