@@ -379,7 +379,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r01q_summary.md: ALU pipe "
+        "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r01s_summary.md: ALU pipe "
                  "63 %, issue 59 %, DRAM 5 %), not by HBM; the HBM fraction is reported because SURVEY.md 8(d) defines "
                  "the roofline in algorithmic bytes"),
         "algorithmic_bytes_per_launch": alg[dom] * images_per_launch, "launch_ms": round(per_launch_ms, 4),
