@@ -56,6 +56,44 @@ int main(int argc, char** argv) {
     auto q = frame.value().grid->get_features_in_area(376.0, 240.0, 15.0);
     if (q) in_area = q.value().size();
   }
+  // BoW: a small deterministic k = 5, L = 2 vocabulary (descriptor bytes from an LCG), OrbVocabulary::transform of the
+  // left descriptors with levels_up = 1; the checksum covers the (word id, weight-free) assignment order
+  uint64_t hb = 0;
+  size_t n_words = 0, n_groups = 0;
+  {
+    std::vector<vslam::VocabNode> nodes(1 + 5 + 25);
+    uint32_t lcg = 12345u, wc = 0;
+    for (size_t i = 1; i < nodes.size(); ++i) {
+      const uint32_t parent = i <= 5 ? 0u : (uint32_t)((i - 6) / 5 + 1);
+      nodes[i].parent = parent;
+      nodes[parent].children.push_back((uint32_t)i);
+      for (int b = 0; b < 32; ++b) {
+        lcg = lcg * 1664525u + 1013904223u;
+        nodes[i].descriptor.bytes[b] = (uint8_t)(lcg >> 24);
+      }
+      if (i > 5) {
+        nodes[i].word_id = (int32_t)wc++;
+        nodes[i].weight = 1.0 + 0.125 * (double)(i % 7);
+      }
+    }
+    vslam::OrbVocabulary voc(std::move(nodes));
+    auto up = voc.upload(sp.value());
+    auto tr = up ? voc.transform(sp.value(), f.left_features.descriptors, 1)
+                 : vslam::Result<std::pair<vslam::BowVector, vslam::FeatureVector>>(up.error());
+    if (!tr) {
+      std::fprintf(stderr, "OrbVocabulary failed (%d): %s\n", tr.error().status, tr.error().message.c_str());
+      return 1;
+    }
+    n_words = tr.value().first.size();
+    n_groups = tr.value().second.size();
+    hb = 1469598103934665603ull;
+    for (const auto& kv : tr.value().second)  // node id -> feature indices (ascending ids, ascending indices)
+      for (size_t idx : kv.second) {
+        const uint32_t rec[2] = {kv.first, (uint32_t)idx};
+        hb = fnv1a(rec, sizeof(rec), hb);
+      }
+  }
+  std::printf("bow_words=%zu bow_groups=%zu bow=%016llx ", n_words, n_groups, (unsigned long long)hb);
   std::printf("n_left=%zu n_right=%zu n_matches=%zu n_points=%zu kp=%016llx desc=%016llx matches=%016llx area=%zu ts=%llu\n",
               f.left_features.keypoints.size(), f.right_features.keypoints.size(), f.matches_lr.size(), valid,
               (unsigned long long)hk, (unsigned long long)hd, (unsigned long long)hm, in_area,

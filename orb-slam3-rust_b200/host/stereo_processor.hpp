@@ -12,6 +12,7 @@
 //   vslam::FeatureGrid                    <- FeatureGrid                 src/tracking/tracking_frame.rs:23-128
 //   vslam::Frame::from_stereo             <- Frame::from_stereo          tracking_frame.rs:194-215
 //   vslam::search_by_projection           <- Tracker's inline searches   src/tracking/tracker.rs:863-923, 1093-1158
+//   vslam::OrbVocabulary::transform       <- OrbVocabulary::transform    src/vocabulary/mod.rs:290-340 (tree descent on the GPU)
 //
 // Errors: the reference returns anyhow::Result<T>; here every fallible call returns vslam::Result<T> holding either
 // the value or (status, message) from vslam_last_error().  Nothing here computes on the CPU: without the CUDA
@@ -19,6 +20,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <optional>
 #include <string>
@@ -322,5 +324,67 @@ inline Result<std::vector<int32_t>> search_by_projection(StereoProcessor& p, con
   idx.resize(uv.size());
   return idx;
 }
+
+// OrbVocabulary (src/vocabulary/mod.rs:79-96): the tree as the reference's loader builds it (node 0 = root).  upload()
+// flattens it once for vslam_vocab_upload; transform() mirrors OrbVocabulary::transform (mod.rs:290-331): the descent of
+// every descriptor row runs on the GPU (vslam_bow_quantize), the BowVector / FeatureVector accumulation and the L1
+// normalisation stay here (the reference sums f64 weights in HashMap order; std::map order is used instead, which is
+// one of the orders the reference can take).
+struct VocabNode {  // mod.rs:40-58
+  uint32_t parent = 0xFFFFFFFFu;
+  std::vector<uint32_t> children;
+  Descriptor descriptor{};
+  double weight = 0.0;
+  int32_t word_id = -1;  // Option<u32>: None -> -1
+};
+using BowVector = std::map<uint32_t, double>;
+using FeatureVector = std::map<uint32_t, std::vector<size_t>>;
+
+class OrbVocabulary {
+ public:
+  explicit OrbVocabulary(std::vector<VocabNode> nodes) : nodes_(std::move(nodes)) {}
+
+  Result<bool> upload(StereoProcessor& p) const {
+    const size_t n = nodes_.size();
+    std::vector<uint8_t> desc(n * 32);
+    std::vector<int32_t> begin(n + 1, 0), ids, word(n);
+    std::vector<uint32_t> parent(n);
+    for (size_t i = 0; i < n; ++i) {
+      std::memcpy(desc.data() + 32 * i, &nodes_[i].descriptor, 32);
+      begin[i + 1] = begin[i] + (int32_t)nodes_[i].children.size();
+      for (uint32_t c : nodes_[i].children) ids.push_back((int32_t)c);
+      parent[i] = nodes_[i].parent;
+      word[i] = nodes_[i].word_id;
+    }
+    if (ids.empty()) ids.push_back(0);
+    int rc = vslam_vocab_upload(p.raw(), (int)n, desc.data(), begin.data(), ids.data(), parent.data(), word.data());
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+    return true;
+  }
+
+  // (BowVector, FeatureVector) of the descriptor rows; levels_up as in the reference (typically 4 for L = 6).
+  Result<std::pair<BowVector, FeatureVector>> transform(StereoProcessor& p, const std::vector<Descriptor>& descriptors,
+                                                       int levels_up) const {
+    const size_t n = descriptors.size();
+    std::vector<uint32_t> word(n + 1), leaf(n + 1), node(n + 1);
+    int rc = vslam_bow_quantize(p.raw(), reinterpret_cast<const uint8_t*>(descriptors.data()), (int)n, levels_up, word.data(),
+                                leaf.data(), node.data());
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+    BowVector bow;
+    FeatureVector feat;
+    for (size_t i = 0; i < n; ++i) {
+      bow[word[i]] += nodes_[leaf[i]].weight;  // mod.rs:308-310
+      feat[node[i]].push_back(i);              // mod.rs:313-314
+    }
+    double sum = 0.0;
+    for (const auto& kv : bow) sum += kv.second;
+    if (sum > 0.0)
+      for (auto& kv : bow) kv.second /= sum;  // mod.rs:318-324
+    return std::make_pair(std::move(bow), std::move(feat));
+  }
+
+ private:
+  std::vector<VocabNode> nodes_;
+};
 
 }  // namespace vslam

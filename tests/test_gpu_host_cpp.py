@@ -39,3 +39,21 @@ def test_cpp_host_mirror_end_to_end(tmp_path, oracle, pairs, camera_dict):
     assert int(got["desc"], 16) == fnv1a(dr.tobytes(), fnv1a(dl.tobytes()))
     assert int(got["matches"], 16) == fnv1a(m.tobytes())
     assert int(got["area"]) == len(oracle.grid_query(cs, items, 376.0, 240.0, 15.0))
+    # OrbVocabulary mirror: same tiny k = 5, L = 2 tree as host_demo.cpp builds (LCG descriptor bytes)
+    lcg, nd = 12345, np.zeros((30, 32), np.uint8)
+    for i in range(30):
+        for b in range(32):
+            lcg = (lcg * 1664525 + 1013904223) & 0xFFFFFFFF
+            nd[i, b] = lcg >> 24
+    parents = [0] * 5 + [(i - 6) // 5 + 1 for i in range(6, 31)]
+    voc = oracle.make_vocabulary_arrays(parents, [0] * 5 + [1] * 25, nd)
+    word, leaf, node = oracle.bow_quantize(dl, voc, 1)
+    groups = {}
+    for i, n in enumerate(node.tolist()):
+        groups.setdefault(n, []).append(i)
+    h = 1469598103934665603
+    for n in sorted(groups):
+        for i in groups[n]:
+            h = fnv1a(np.array([n, i], np.uint32).tobytes(), h)
+    assert int(got["bow_words"]) == len(set(word.tolist())) and int(got["bow_groups"]) == len(groups)
+    assert int(got["bow"], 16) == h
