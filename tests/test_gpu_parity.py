@@ -535,3 +535,21 @@ def test_blur_full_level_option(oracle, camera_dict, monkeypatch):
         for lvl in range(8):
             assert np.array_equal(sp.debug_level_image(STAGE_BLURRED, 0, lvl), st["blurred"][lvl]), f"blur {lvl}"
             assert np.array_equal(sp.debug_level_image(STAGE_PYRAMID, 0, lvl), st["pyramid"][lvl]), f"pyr {lvl}"
+
+
+@pytest.mark.parametrize("edge", [22, 25, 40])
+def test_other_edge_thresholds(oracle, camera_dict, edge):
+    """The border rings k_resize / k_blur skip are derived from edge_threshold (eb - 21 and eb - 18 px): the smallest
+    allowed value (22) leaves rings of 1 and 4 px, and everything the later stages read must still be exact."""
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    l, r = synth.make_stereo_pair(31, 480, 320)
+    l, r = l.numpy(), r.numpy()
+    with StereoProcessor(CameraModel(**camera_dict), 500, 480, 320, max_batch=1, edge_threshold=edge) as sp:
+        fr = sp.process(l, r)
+    kl, dl = oracle.detect_and_compute(l, 500, edge_threshold=edge)
+    kr, dr = oracle.detect_and_compute(r, 500, edge_threshold=edge)
+    assert_struct_equal(fr.left_features.keypoints, kl, "left keypoints")
+    assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
+    assert np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
+    assert_struct_equal(fr.matches_lr, oracle.match_features(kl, dl, kr, dr, camera_dict), "matches")
