@@ -553,3 +553,25 @@ def test_other_edge_thresholds(oracle, camera_dict, edge):
     assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
     assert np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
     assert_struct_equal(fr.matches_lr, oracle.match_features(kl, dl, kr, dr, camera_dict), "matches")
+
+
+@pytest.mark.parametrize("scale,levels", [(1.5, 5), (2.0, 4), (1.1, 8), (1.2, 3)])
+def test_other_pyramid_shapes(oracle, camera_dict, scale, levels):
+    """Other scale factors / level counts than the reference's 1.2 x 8: scale 2.0 takes k_resize's wide-window path
+    (source window of a 4-pixel group wider than 8 bytes), 1.1 the densest coefficient pattern."""
+    from vslam_b200 import STAGE_PYRAMID, CameraModel, StereoProcessor, synth
+
+    l, r = synth.make_stereo_pair(41, 640, 400)
+    l, r = l.numpy(), r.numpy()
+    with StereoProcessor(CameraModel(**camera_dict), 600, 640, 400, max_batch=1, n_levels=levels, scale_factor=scale) as sp:
+        fr = sp.process(l, r)
+        st = oracle.detect_stages(l, 600, nlevels=levels, scale_factor=scale)
+        for lvl in range(levels):
+            b = 10 if lvl else 0
+            g, o = sp.debug_level_image(STAGE_PYRAMID, 0, lvl), st["pyramid"][lvl]
+            assert np.array_equal(g[b:g.shape[0] - b, b:g.shape[1] - b], o[b:o.shape[0] - b, b:o.shape[1] - b]), f"pyr {lvl}"
+    kl, dl = oracle.detect_and_compute(l, 600, nlevels=levels, scale_factor=scale)
+    kr, dr = oracle.detect_and_compute(r, 600, nlevels=levels, scale_factor=scale)
+    assert_struct_equal(fr.left_features.keypoints, kl, "left keypoints")
+    assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
+    assert np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
