@@ -37,6 +37,8 @@ namespace vk {
 // 8b .. 8b+7, so g_brief_pattern_t[q][b] = test 8b + q = (x0, y0, x1, y1); one LDG.128 per q then touches 4 cache lines
 // instead of 32.  Filled by the host at handle creation (upload_tables in vslam_b200.cu) from brief_pattern.inc.
 __device__ float4 g_brief_pattern_t[8][32];
+// the same table as four int8 per test (|coordinate| <= 13): one 4-byte load per test instead of 16 (VSLAM_BRIEF_I8)
+__device__ unsigned g_brief_pattern_i8[8][32];
 
 // Orientation tables (filled by the host at handle creation, see upload_tables in vslam_b200.cu):
 //   g_angle_mask[o][j][r]  byte b = 0xff iff pixel u = 4j + b - (15 + o) of patch row r lies inside the 31-px disc
@@ -1209,6 +1211,9 @@ constexpr int kAngleRows = 2 * kAngleR + 1;     // 31
 constexpr int kAngleRowWords = 9;               // 31 px + up to 3 alignment bytes = 9 words
 constexpr int kPatchWords = kBriefRows * kBriefRowWords + kAngleRows * kAngleRowWords;
 
+#ifndef VSLAM_BRIEF_I8
+#define VSLAM_BRIEF_I8 1
+#endif
 #ifndef VSLAM_BRIEF_WARPS
 #define VSLAM_BRIEF_WARPS 4
 #endif
@@ -1340,7 +1345,16 @@ __global__ void __launch_bounds__(32 * kBriefWarps) k_brief(const __grid_constan
   unsigned byte = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
+#if VSLAM_BRIEF_I8
+    const unsigned pw = g_brief_pattern_i8[q][lane];  // test 8*lane + q: (x0,y0,x1,y1) as int8, exact in f32
+    float4 t;
+    t.x = (float)(int)(signed char)(pw & 0xffu);
+    t.y = (float)(int)(signed char)((pw >> 8) & 0xffu);
+    t.z = (float)(int)(signed char)((pw >> 16) & 0xffu);
+    t.w = (float)(int)(signed char)(pw >> 24);
+#else
     const float4 t = g_brief_pattern_t[q][lane];  // test 8*lane + q: (x0,y0,x1,y1)
+#endif
     const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
     const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
     const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));

@@ -188,6 +188,16 @@ int upload_tables(vslam_handle h) {
     }
   }
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_t, pat_t, sizeof(pat_t)));
+  {
+    static unsigned pat_i8[8][32];
+    for (int b = 0; b < 32; ++b)
+      for (int q = 0; q < 8; ++q) {
+        unsigned w = 0;
+        for (int c = 0; c < 4; ++c) w |= (unsigned)(uint8_t)(int8_t)pattern[4 * (8 * b + q) + c] << (8 * c);
+        pat_i8[q][b] = w;
+      }
+    CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_i8, pat_i8, sizeof(pat_i8)));
+  }
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_mask, mask, sizeof(mask)));
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_u, uu, sizeof(uu)));
   return VSLAM_OK;
