@@ -287,7 +287,7 @@ __host__ __device__ inline int fast_sp(int pitch) { return pitch + 32; }
 __host__ __device__ inline int fast_bw(int pitch) { return (pitch + 31) >> 5; }
 __host__ inline size_t fast_smem_bytes(int pitch) {
   size_t sp = fast_sp(pitch), bw = fast_bw(pitch);
-  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + VSLAM_FAST_ROWS * bw * 4 +
+  return (VSLAM_FAST_ROWS + 8) * sp + (VSLAM_FAST_ROWS + 2) * sp + ((VSLAM_FAST_ROWS * bw * 4 + 15) & ~(size_t)15) +
          kFastWarps * (kFastQ + kFastCL) * 2 + 64 + (kFastWarps + 2 + VSLAM_FAST_ROWS) * 4;
 }
 
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   // layout (byte offsets into the dynamic shared memory)
   const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*SP + 16
   const int o_bits = o_sc + (VSLAM_FAST_ROWS + 2) * SP;      // score tile: image row ys-1+r at o_sc + r*SP + 16
-  const int o_q = o_bits + VSLAM_FAST_ROWS * BW * 4;         // corner bitmask; then the per-warp candidate rings
+  const int o_q = o_bits + ((VSLAM_FAST_ROWS * BW * 4 + 15) & ~15);  // corner bitmask; then the per-warp candidate rings
   const int o_cl = o_q + kFastWarps * kFastQ * 2;            // per-warp corner lists
   const int o_misc = (o_cl + kFastWarps * kFastCL * 2 + 15) & ~15;  // mbarrier (8 B), list counts, total
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   }
   for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < VSLAM_FAST_ROWS * BW; i += kFastThreads) bits[i] = 0;
+  for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
+    reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
   if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
   {
     unsigned done = 0;
