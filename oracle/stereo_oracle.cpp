@@ -15,7 +15,7 @@
 //
 // PARITY UNPINNED for this file: the reference cannot be built here (no Rust toolchain) and holds no test
 // for these functions; the only related known-answer vectors are the popcount twins at
-// vocabulary/mod.rs:430-441 and loop_closing/corrector.rs:626-633 (checked in tests/test_oracle_kat.py).
+// vocabulary/mod.rs:430-441 and loop_closing/corrector.rs:626-633 (checked in tests/test_oracle_golden.py).
 // The BFMatcher restatement IS pinned against cv2.BFMatcher in tests.
 //
 // Rust cast semantics are coded explicitly: float->int `as` saturates (NaN -> 0), int->int `as` wraps.
