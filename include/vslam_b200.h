@@ -30,7 +30,19 @@
  * `StereoFrame` / `KeyFrame` and read from other threads exactly like the reference's values.
  *
  * Results are bit-identical to the reference's CPU path (cv::ORB as configured at stereo.rs:38-48 + the Rust loops):
- * keypoint order, coordinates, octaves, angles, responses, descriptors, match pairs, f64 points.
+ * keypoint order, coordinates, octaves, angles, responses, descriptors, match pairs, f64 points.  Caveats:
+ *   1. Keypoint capacity.  cv::ORB keeps every keypoint whose response ties with the n-th best, so a frame can hold more
+ *      than n_features keypoints.  A frame that exceeds cfg.keypoint_capacity is NOT truncated: the call returns
+ *      VSLAM_ERR_KEYPOINT_OVERFLOW (frame status set) where the reference would return the frame.  Re-create the handle
+ *      with a larger keypoint_capacity to process such input (white noise / synthetic plateaus; never seen on textured
+ *      scenes at the default capacity n_features + max(n_features / 8, 64)).
+ *   2. Host arithmetic the reference inherits from its platform.  The blur follows OpenCV's sepFilter2D on an x86 host
+ *      with FMA (AVX2 path: fused multiply-adds in the order documented in SURVEY.md 8.A5), and BRIEF steering uses
+ *      (float)cos/sin of the host libm; the device evaluates both in double precision and rounds once, which equals
+ *      glibc's result except when a rotated sample coordinate lands within ~1e-7 of x.5 (probability ~1e-8 per
+ *      descriptor bit pair; none observed).  Parity is therefore pinned to cv2 4.x on FMA-capable x86, the platform
+ *      the parity tests run on.
+ *   3. Every entry point makes cfg.device current for the duration of the call and restores the caller's device.
  */
 #ifndef VSLAM_B200_H_
 #define VSLAM_B200_H_
@@ -134,9 +146,11 @@ int vslam_process_batch(vslam_handle h, int n, const uint8_t* const* left, const
                         const uint64_t* timestamps_ns, vslam_frame_out* outs);
 
 /* Same, with the images already resident in device memory (HBM) of cfg.device: left_dev/right_dev are DEVICE
- * pointers to n images each, `image_stride` bytes apart, rows `row_stride` bytes apart (row_stride % 16 == 0 and
- * 16-byte aligned bases).  Results still land in host memory.  If outs == NULL the results stay on the device
- * (throughput measurement of the kernels alone) and only per-frame counts are validated. */
+ * pointers to n images each, `image_stride` bytes apart, rows `row_stride` bytes apart (row_stride % 16 == 0,
+ * row_stride >= width, 16-byte aligned bases; a row_stride wider than align16(width) raises k_fast's shared-memory
+ * opt-in on first use and fails with VSLAM_ERR_INVALID_ARGUMENT beyond the device limit).  Results still land in host
+ * memory.  If outs == NULL the results stay on the device (throughput measurement of the kernels alone); the per-frame
+ * status words of EVERY chunk are still read back, so a keypoint overflow anywhere in the batch is reported. */
 int vslam_process_batch_device(vslam_handle h, int n, const uint8_t* left_dev, const uint8_t* right_dev,
                                size_t image_stride, size_t row_stride, const uint64_t* timestamps_ns,
                                vslam_frame_out* outs);
@@ -151,7 +165,9 @@ int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const ui
                          const vslam_keypoint* kp_right, const uint8_t* desc_right, int n_right, vslam_dmatch* matches,
                          int* n_matches);
 
-/* triangulate on caller-provided matches.  points[n_left][3], valid[n_left]. */
+/* triangulate on caller-provided matches.  points[n_left][3], valid[n_left].  Entries with |disparity| < 0.5 are
+ * skipped exactly like stereo.rs:204-207 (they never overwrite an earlier point of the same query_idx); among the
+ * remaining entries of one query_idx the last wins, as in the reference's loop. */
 int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left, const vslam_keypoint* kp_right,
                       int n_right, const vslam_dmatch* matches, int n_matches, double* points, uint8_t* valid);
 

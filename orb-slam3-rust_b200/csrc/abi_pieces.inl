@@ -36,7 +36,7 @@ int vslam_descriptor_distance(vslam_handle h, const uint8_t* a, const uint8_t* b
   if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
   if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (n == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   const size_t nb = (size_t)n * 32;
   int rc = arena_begin(h, 2 * pad256(nb) + pad256((size_t)n * 4));
   if (rc) return rc;
@@ -88,7 +88,7 @@ int vslam_match_features(vslam_handle h, const vslam_keypoint* kp_left, const ui
   if (n_left > 65535 || n_right > 65535) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "more than 65535 keypoints");
   *n_matches = 0;
   if (n_left == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   FrameLayout F;
   int2* ml;
@@ -115,18 +115,21 @@ int vslam_triangulate(vslam_handle h, const vslam_keypoint* kp_left, int n_left,
       (n_right > 0 && !kp_right) || (n_matches > 0 && !matches))
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (n_left == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   FrameLayout F;
   int2* ml;
   int rc = stage_features(h, kp_left, nullptr, n_left, kp_right, nullptr, n_right, &F, &ml, st);
   if (rc) return rc;
-  // per-left table from the caller's match list.  match_features never emits a left index twice; if a caller does,
-  // the last entry wins (the reference's loop would keep an earlier valid point when a later one has |d| < 0.5).
+  // per-left table from the caller's match list.  match_features never emits a left index twice; if a caller does, the
+  // reference's loop (stereo.rs:196-213) lets the last entry with |disparity| >= 0.5 win: an entry it skips never
+  // overwrites an earlier point, so such entries are dropped here as well.
   std::vector<int2> tab((size_t)F.cap, make_int2(-1, 0));
   for (int i = 0; i < n_matches; ++i) {
     int q = matches[i].query_idx, t = matches[i].train_idx;
     if (q < 0 || q >= n_left || t < 0 || t >= n_right) continue;  // .get() returned None
+    const double d = (double)kp_left[q].x - (double)kp_right[t].x;
+    if (std::fabs(d) < 0.5) continue;
     tab[q] = make_int2(t, (int)matches[i].distance);
   }
   CU_TRY(h, cudaMemcpyAsync(ml, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
@@ -149,7 +152,7 @@ int vslam_grid_build(vslam_handle h, const vslam_keypoint* kps, int n, double im
                      int32_t* cell_items) {
   if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
   if (n < 0 || !cell_start || (n > 0 && (!kps || !cell_items))) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nn = (size_t)std::max(n, 1);
   int rc = arena_begin(h, pad256(nn * 28) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4));
@@ -173,7 +176,7 @@ int vslam_grid_query(vslam_handle h, const vslam_keypoint* kps, int n, double im
   if (n < 0 || nq < 0 || !out_start || (n > 0 && !kps) || (nq > 0 && !xyr) || out_capacity < 0 ||
       (out_capacity > 0 && !out_items))
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nn = (size_t)std::max(n, 1), qq = (size_t)std::max(nq, 1), oc = (size_t)std::max(out_capacity, 1);
   int rc = arena_begin(h, pad256(nn * 28) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4) + pad256(qq * 24) +
@@ -220,7 +223,7 @@ int vslam_search_by_projection(vslam_handle h, const vslam_keypoint* kps, const 
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown search mode %d", sp->mode);
   if (sp->th_high > 1024) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "th_high out of range");
   if (M == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nn = (size_t)std::max(n, 1), mm = (size_t)M;
   int rc = arena_begin(h, pad256(nn * 28) + pad256(nn * 32) + pad256((vk::kGridCells + 1) * 4) + 2 * pad256(nn * 4) +
@@ -265,7 +268,7 @@ int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query,
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   *n_matches = 0;
   if (n_query == 0 || n_train == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nq = (size_t)n_query, nt = (size_t)n_train;
   int rc = arena_begin(h, pad256(nq * 32) + pad256(nt * 32) + 2 * pad256(nq * 4) + 2 * pad256(nt * 4) + pad256(nq * 16) + 512);
@@ -298,7 +301,7 @@ int vslam_fuse_search(vslam_handle h, const vslam_keypoint* kps, const uint8_t* 
   if (n < 0 || M < 0 || (n > 0 && (!kps || !desc)) || (M > 0 && (!uvr || !mp_desc || !out_idx || !out_dist)))
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (M == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nn = (size_t)std::max(n, 1), mm = (size_t)M;
   int rc = arena_begin(h, pad256(nn * 28) + pad256(nn * 32) + pad256(mm * 24) + pad256(mm * 32) + 2 * pad256(mm * 4));
@@ -331,7 +334,7 @@ int vslam_distinctive_descriptors(vslam_handle h, const uint8_t* desc, const int
   if (offsets[0] != 0 || total < 0 || (total > 0 && !desc)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad offsets");
   for (int m = 0; m < M; ++m)
     if (offsets[m + 1] < offsets[m]) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t tt = (size_t)std::max(total, 1), mm = (size_t)M;
   int rc = arena_begin(h, pad256(tt * 32) + pad256((mm + 1) * 4) + pad256(mm * 4));
@@ -362,7 +365,7 @@ int vslam_vocab_upload(vslam_handle h, int n_nodes, const uint8_t* node_desc, co
   for (int i = 0; i < n_nodes; ++i)
     if (parent[i] != 0xffffffffu && parent[i] >= (uint32_t)n_nodes)
       return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "parent of node %d out of range", i);
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   CU_TRY(h, cudaStreamSynchronize(st));
   cudaFree(h->voc_desc); cudaFree(h->voc_child_begin); cudaFree(h->voc_child_ids); cudaFree(h->voc_parent); cudaFree(h->voc_word);
@@ -390,7 +393,7 @@ int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up
   if (n < 0 || levels_up < 0 || (n > 0 && (!desc || !out_word || !out_leaf || !out_node)))
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bow_quantize: bad argument");
   if (n == 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t st = h->slots[0].stream;
   const size_t nn = (size_t)n;
   int rc = arena_begin(h, pad256(nn * 32) + 3 * pad256(nn * 4));

@@ -65,6 +65,8 @@ struct Slot {
   int first_frame = 0;
   bool busy = false;
   bool want_results = false;
+  int rows_copied = 0;             // rows of every result array the chunk's D2H copies carried
+  int eyes = 2;
 };
 
 }  // namespace
@@ -87,6 +89,7 @@ struct vslam_handle_s {
   bool blur_after_fast = true;          // fork the blur after k_fast (it then fills the SMs under the latency-bound selection
                                         // chain) instead of right after the pyramid; VSLAM_BLUR_AFTER_FAST=0 restores the latter
   size_t fast_smem = 0;
+  size_t fast_smem_limit = 0;  // dynamic shared memory k_fast has been opted in to for this handle
   size_t fast_smem_pad = 0;  // tuning knob VSLAM_FAST_SMEM_PAD: extra bytes per k_fast block (caps its blocks per SM)
   int sel1_cap = 0, sel1_cap_latency = 0, sel2_cap = 0;  // records the selection kernels keep in shared memory
   // vocabulary tree of vslam_vocab_upload (device)
@@ -138,6 +141,38 @@ int fail(vslam_handle h, int code, const char* fmt, ...) {
                   cudaGetErrorString(_e));                                                               \
   } while (0)
 
+// Makes cfg.device current for the duration of an API call and restores the caller's device on return.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define DEVICE_SCOPE(h)                  \
+  DeviceGuard _dev_guard((h)->cfg.device); \
+  CU_TRY(h, _dev_guard.err)
+
+// The dynamic shared-memory opt-in is a per-function, per-device attribute shared by every handle of the process:
+// only ever raise it, so that handles created for smaller images do not shrink what an older handle's launches need.
+enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_NFUNC };
+cudaError_t raise_smem_limit(int device, int which, size_t want) {
+  static std::mutex mu;
+  static size_t cur_dev[64][SMEM_NFUNC] = {{0}};
+  const void* fn[SMEM_NFUNC] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
+                                (const void*)vk::k_match_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = cur_dev[device & 63][which];
+  if (want <= cur) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+  if (e == cudaSuccess) cur = want;
+  return e;
+}
+
 // cv::resize INTER_LINEAR_EXACT coefficients for one axis, packed (offset | alpha1 << 16).
 void linear_exact_coeffs(int src, int dst, uint32_t* out) {
   double inv_scale = (double)dst / (double)src;
@@ -164,8 +199,9 @@ int upload_tables(vslam_handle h) {
 #include "brief_pattern.inc"
   };
   static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-  static float pat_t[8][32][4];
-  static unsigned mask[4][9][32], uu[4][9];
+  // scratch is per call (vslam_create may run concurrently on several host threads)
+  float pat_t[8][32][4];
+  unsigned mask[4][9][32], uu[4][9];
   for (int b = 0; b < 32; ++b)
     for (int q = 0; q < 8; ++q)
       for (int c = 0; c < 4; ++c) pat_t[q][b][c] = (float)pattern[4 * (8 * b + q) + c];
@@ -189,7 +225,7 @@ int upload_tables(vslam_handle h) {
   }
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_t, pat_t, sizeof(pat_t)));
   {
-    static unsigned pat_i8[8][32];
+    unsigned pat_i8[8][32];
     for (int b = 0; b < 32; ++b)
       for (int q = 0; q < 8; ++q) {
         unsigned w = 0;
@@ -310,6 +346,7 @@ int build_params(vslam_handle h) {
   }
   if (const char* ev = getenv("VSLAM_FAST_SMEM_PAD")) h->fast_smem_pad = (size_t)std::max(atoi(ev), 0);
   h->fast_smem = vk::fast_smem_bytes(P.in_pitch) + h->fast_smem_pad;
+  h->fast_smem_limit = h->fast_smem;
   // selection scratch in shared memory: select1 sized for ~3% corner density on the largest level (typical < 2%),
   // select2 for 2N_l plus ties; anything larger is replayed in global memory.
   {
@@ -447,8 +484,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
                   long long frame_stride, int pitch) {
   PyrP P = h->P;
   P.eyes = eyes;
-  P.in_pitch = pitch;
-  P.lv[0].pitch = pitch;
+  P.in_pitch = pitch;  // pitch of the level-0 INPUT rows; the blurred level 0 keeps lv[0].pitch (sized at creation)
   P.in_frame_stride = frame_stride;
   const int nimg = frames * eyes;
   cudaStream_t st = s.stream;
@@ -577,21 +613,60 @@ int unpack_frame(const FrameLayout& L, int f, bool direct, vslam_frame_out* out,
   return VSLAM_OK;
 }
 
-// Wait for a slot's in-flight chunk and hand its results to the caller.
+// Wait for a slot's in-flight chunk and hand its results to the caller.  The per-frame headers are always read back
+// (2 KB per chunk), so a KEYPOINT_OVERFLOW of any chunk is reported even when the results stay on the device.
 int retire_slot(vslam_handle h, Slot& s, vslam_frame_out* outs, const uint64_t* ts, int* first_error) {
   if (!s.busy) return VSLAM_OK;
   CU_TRY(h, cudaEventSynchronize(s.done));
   s.busy = false;
-  if (s.want_results && outs) {
-    for (int f = 0; f < s.frames; ++f) {
-      const int gf = s.first_frame + f;
-      int rc = unpack_frame(s.h_lay, f, s.direct_out, &outs[gf], ts ? ts[gf] : 0);
-      if (rc != VSLAM_OK && *first_error == VSLAM_OK) {
-        *first_error = rc;
-        fail(h, rc, "frame %d: %s", gf,
-             rc == VSLAM_ERR_CAPACITY ? "output capacity too small"
-                                      : "more keypoints than keypoint_capacity (response ties)");
+  const FrameLayout& M = s.h_lay;
+  const FrameLayout& D = s.d_lay;
+  if (!(s.want_results && outs)) {
+    for (int f = 0; f < s.frames; ++f)
+      if (M.hdr[f].status != VSLAM_OK && *first_error == VSLAM_OK) {
+        *first_error = M.hdr[f].status;
+        fail(h, M.hdr[f].status, "frame %d: more keypoints than keypoint_capacity (response ties)", s.first_frame + f);
       }
+    return VSLAM_OK;
+  }
+  for (int f = 0; f < s.frames; ++f) {
+    const int gf = s.first_frame + f;
+    const ResHdr& hd = M.hdr[f];
+    // The chunk's D2H copies carried s.rows_copied rows of every array (n_features: the keypoint count unless
+    // responses tie at the cut).  Frames that hold more fetch the remaining rows now — rare, synchronous.
+    const int nl = hd.n_kp[0], nr = hd.n_kp[1], nm = hd.n_matches, rc0 = s.rows_copied;
+    if (hd.status == VSLAM_OK && std::max(std::max(nl, nr), nm) > rc0 && outs[gf].capacity >= std::max(std::max(nl, nr), nm)) {
+      const vslam_frame_out& o = outs[gf];
+      const size_t k = (size_t)f;
+      auto extra = [&](unsigned char* dst_base, const unsigned char* src_base, long long stride, size_t elem, int n) -> cudaError_t {
+        if (n <= rc0 || !dst_base) return cudaSuccess;
+        return cudaMemcpyAsync(dst_base + (size_t)rc0 * elem, src_base + k * (size_t)stride + (size_t)rc0 * elem,
+                               (size_t)(n - rc0) * elem, cudaMemcpyDeviceToHost, s.stream);
+      };
+      unsigned char* d0 = s.direct_out ? (unsigned char*)o.kp_left : M.kp[0] + k * M.kp_stride;
+      unsigned char* d1 = s.direct_out ? (unsigned char*)o.kp_right : M.kp[1] + k * M.kp_stride;
+      unsigned char* d2 = s.direct_out ? (unsigned char*)o.desc_left : M.desc[0] + k * M.desc_stride;
+      unsigned char* d3 = s.direct_out ? (unsigned char*)o.desc_right : M.desc[1] + k * M.desc_stride;
+      unsigned char* d4 = s.direct_out ? (unsigned char*)o.matches : M.matches + k * M.matches_stride;
+      unsigned char* d5 = s.direct_out ? (unsigned char*)o.points_cam : M.pts + k * M.pts_stride;
+      unsigned char* d6 = s.direct_out ? (unsigned char*)o.points_valid : M.valid + k * M.valid_stride;
+      CU_TRY(h, extra(d0, D.kp[0], D.kp_stride, 28, nl));
+      CU_TRY(h, extra(d2, D.desc[0], D.desc_stride, 32, nl));
+      if (s.eyes == 2) {
+        CU_TRY(h, extra(d1, D.kp[1], D.kp_stride, 28, nr));
+        CU_TRY(h, extra(d3, D.desc[1], D.desc_stride, 32, nr));
+        CU_TRY(h, extra(d4, D.matches, D.matches_stride, 16, nm));
+        CU_TRY(h, extra(d5, D.pts, D.pts_stride, 24, nl));
+        CU_TRY(h, extra(d6, D.valid, D.valid_stride, 1, nl));
+      }
+      CU_TRY(h, cudaStreamSynchronize(s.stream));
+    }
+    int rc = unpack_frame(M, f, s.direct_out, &outs[gf], ts ? ts[gf] : 0);
+    if (rc != VSLAM_OK && *first_error == VSLAM_OK) {
+      *first_error = rc;
+      fail(h, rc, "frame %d: %s", gf,
+           rc == VSLAM_ERR_CAPACITY ? "output capacity too small"
+                                    : "more keypoints than keypoint_capacity (response ties)");
     }
   }
   return VSLAM_OK;
@@ -629,23 +704,33 @@ bool outputs_are_direct(vslam_handle h, const vslam_frame_out* o, int frames) {
          is_pinned_host(a.points_valid);
 }
 
-int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
-              const uint8_t* left_dev, const uint8_t* right_dev, size_t image_stride, size_t row_stride,
-              const uint64_t* ts, vslam_frame_out* outs, bool device_input) {
-  if (n <= 0) return VSLAM_OK;
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+// After a CUDA failure inside run_batch: wait for everything in flight (copies may still be writing into the caller's
+// arrays) and forget the chunks, so that the next call starts from idle slots.
+void drain_slots(vslam_handle h) {
+  for (int k = 0; k < h->nslot; ++k) {
+    Slot& s = h->slots[k];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.stream2) cudaStreamSynchronize(s.stream2);
+    s.busy = false;
+    s.want_results = false;
+  }
+  cudaGetLastError();
+}
+
+int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
+                   const uint8_t* left_dev, const uint8_t* right_dev, size_t image_stride, size_t row_stride,
+                   const uint64_t* ts, vslam_frame_out* outs, bool device_input, int* first_error) {
   const PyrP& P = h->P;
   const int W = h->cfg.width, H = h->cfg.height;
   if (h->profiling) {
     for (int i = 0; i < 7; ++i) h->stage_ms[i] = 0.f;
   }
-  int first_error = VSLAM_OK;
   int chunk = 0;
   CU_TRY(h, cudaEventRecord(h->ev_batch[0], h->slots[0].stream));
   for (int f0 = 0; f0 < n; f0 += h->max_batch, ++chunk) {
     const int frames = std::min(h->max_batch, n - f0);
     Slot& s = h->slots[chunk % h->nslot];
-    int rc = retire_slot(h, s, outs, ts, &first_error);
+    int rc = retire_slot(h, s, outs, ts, first_error);
     if (rc != VSLAM_OK) return rc;
     const uint8_t *in_l, *in_r;
     long long fstride;
@@ -696,11 +781,12 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
     if (rc != VSLAM_OK) return rc;
     s.want_results = outs != nullptr;
     s.direct_out = false;
+    s.eyes = eyes;
+    const FrameLayout& D = s.d_lay;
+    const FrameLayout& M = s.h_lay;
+    const size_t fr = (size_t)frames;
+    CU_TRY(h, cudaMemcpyAsync(M.hdr, D.hdr, fr * sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream));
     if (outs) {
-      const FrameLayout& D = s.d_lay;
-      const FrameLayout& M = s.h_lay;
-      const size_t fr = (size_t)frames;
-      CU_TRY(h, cudaMemcpyAsync(M.hdr, D.hdr, fr * sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream));
       s.direct_out = eyes == 2 && outputs_are_direct(h, outs + f0, frames);
       const vslam_frame_out& o = outs[f0];
       void* dst[7] = {s.direct_out ? (void*)o.kp_left : (void*)M.kp[0],      s.direct_out ? (void*)o.kp_right : (void*)M.kp[1],
@@ -708,11 +794,19 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
                       s.direct_out ? (void*)o.matches : (void*)M.matches,    s.direct_out ? (void*)o.points_cam : (void*)M.pts,
                       s.direct_out ? (void*)o.points_valid : (void*)M.valid};
       const void* src[7] = {D.kp[0], D.kp[1], D.desc[0], D.desc[1], D.matches, D.pts, D.valid};
-      const size_t bytes[7] = {fr * D.kp_stride,      fr * D.kp_stride,  fr * D.desc_stride, fr * D.desc_stride,
-                               fr * D.matches_stride, fr * D.pts_stride, fr * D.valid_stride};
+      const size_t pitchb[7] = {(size_t)D.kp_stride,      (size_t)D.kp_stride,  (size_t)D.desc_stride, (size_t)D.desc_stride,
+                                (size_t)D.matches_stride, (size_t)D.pts_stride, (size_t)D.valid_stride};
+      const size_t elem[7] = {28, 28, 32, 32, 16, 24, 1};
+      // One 2-D copy per array per chunk: frame f's rows [0, rows) of [frames][capacity] arrays.  rows = n_features:
+      // cv::ORB returns exactly that many keypoints unless responses tie at the cut (retire_slot fetches the extra
+      // rows of such a frame), and matches / points never outnumber the left keypoints — the capacity - n_features
+      // tail rows (11 % of every array at the default capacity) never cross PCIe.
+      const int rows = std::min(h->kp_cap, h->cfg.n_features);
+      s.rows_copied = rows;
       for (int a = 0; a < 7; ++a) {
         if (eyes == 1 && (a == 1 || a == 3 || a >= 4)) continue;
-        CU_TRY(h, cudaMemcpyAsync(dst[a], src[a], bytes[a], cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(h, cudaMemcpy2DAsync(dst[a], pitchb[a], src[a], pitchb[a], (size_t)rows * elem[a], fr, cudaMemcpyDeviceToHost,
+                                    s.stream));
       }
     }
     CU_TRY(h, cudaEventRecord(s.done, s.stream));
@@ -729,21 +823,25 @@ int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const
   // drain in submission order
   for (int k = 0; k < h->nslot; ++k) {
     Slot& s = h->slots[(chunk + k) % h->nslot];
-    int rc = retire_slot(h, s, outs, ts, &first_error);
+    int rc = retire_slot(h, s, outs, ts, first_error);
     if (rc != VSLAM_OK) return rc;
   }
   CU_TRY(h, cudaEventSynchronize(h->ev_batch[1]));
   cudaEventElapsedTime(&h->last_batch_ms, h->ev_batch[0], h->ev_batch[1]);
-  if (!outs) {
-    // results stay on the device: still surface per-frame overflow flags of the last chunk
-    Slot& s = h->slots[h->last_slot];
-    std::vector<ResHdr> hdrs((size_t)h->last_frames);
-    CU_TRY(h, cudaMemcpy(hdrs.data(), s.d_lay.hdr, sizeof(ResHdr) * hdrs.size(), cudaMemcpyDeviceToHost));
-    for (const ResHdr& r : hdrs)
-      if (r.status != VSLAM_OK && first_error == VSLAM_OK) {
-        first_error = r.status;
-        fail(h, r.status, "keypoint overflow in a device-resident frame");
-      }
+  return VSLAM_OK;
+}
+
+int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
+              const uint8_t* left_dev, const uint8_t* right_dev, size_t image_stride, size_t row_stride,
+              const uint64_t* ts, vslam_frame_out* outs, bool device_input) {
+  if (n <= 0) return VSLAM_OK;
+  DEVICE_SCOPE(h);
+  int first_error = VSLAM_OK;
+  const int rc = run_batch_impl(h, n, eyes, left, right, stride, left_dev, right_dev, image_stride, row_stride, ts, outs,
+                                device_input, &first_error);
+  if (rc != VSLAM_OK) {  // a CUDA call failed mid-batch: leave no chunk in flight behind the caller's back
+    drain_slots(h);
+    return rc;
   }
   return first_error;
 }
@@ -839,30 +937,20 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
          h->fast_smem, max_sel, lim);
     return bail(VSLAM_ERR_INVALID_ARGUMENT);
   }
-  // The opt-in limit is a per-function (not per-handle) attribute: only ever raise it, so that handles created for
-  // smaller images do not shrink what an older handle's launches need.
+  // row-bucketed fused matcher when its tables fit in shared memory; otherwise the chunked pair of kernels
   {
-    static std::mutex mu;
-    static size_t cur_dev[64][4] = {{0}};
-    size_t* cur = cur_dev[c.device & 63];
-    std::lock_guard<std::mutex> lock(mu);
-    // row-bucketed fused matcher when its tables fit in shared memory; otherwise the chunked pair of kernels
-    {
-      const size_t need = vk::match_rows_smem_bytes(h->kp_cap, c.height);
-      h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
-    }
-    const size_t want[4] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
-    const void* fn[4] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
-                         (const void*)vk::k_match_rows};
-    for (int i = 0; i < 4; ++i)
-      if (want[i] > cur[i]) {
-        e = cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want[i]);
-        if (e != cudaSuccess) {
-          fail(h, VSLAM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-          return bail(VSLAM_ERR_CUDA);
-        }
-        cur[i] = want[i];
+    const size_t need = vk::match_rows_smem_bytes(h->kp_cap, c.height);
+    h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
+  }
+  {
+    const size_t want[SMEM_NFUNC] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
+    for (int i = 0; i < SMEM_NFUNC; ++i) {
+      e = raise_smem_limit(c.device, i, want[i]);
+      if (e != cudaSuccess) {
+        fail(h, VSLAM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return bail(VSLAM_ERR_CUDA);
       }
+    }
   }
   if (const char* ev = getenv("VSLAM_SLOTS")) h->nslot = std::min(std::max(atoi(ev), 2), MAX_SLOTS);
   for (int k = 0; k < h->nslot; ++k) {
@@ -880,7 +968,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
 
 void vslam_destroy(vslam_handle h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
   cudaFree(h->d_coef);
   cudaFree(h->arena_base);
@@ -931,8 +1019,21 @@ int vslam_process_batch_device(vslam_handle h, int n, const uint8_t* left_dev, c
   if (row_stride % 16 != 0 || row_stride < (size_t)h->cfg.width || ((uintptr_t)left_dev & 15) || ((uintptr_t)right_dev & 15) ||
       image_stride % 16 != 0 || image_stride < row_stride * (size_t)h->cfg.height)
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "device images need 16-byte aligned bases and strides");
-  if ((size_t)vk::fast_smem_bytes((int)row_stride) > h->fast_smem)
-    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "row_stride larger than the handle was sized for");
+  if (row_stride > 8192) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "row_stride too large");
+  {
+    // k_fast stages whole rows: a row stride wider than align16(width) needs a larger shared-memory opt-in
+    const size_t need = vk::fast_smem_bytes(std::max((int)row_stride, h->P.in_pitch)) + h->fast_smem_pad;
+    if (need > h->fast_smem_limit) {
+      cudaDeviceProp prop;
+      DEVICE_SCOPE(h);
+      CU_TRY(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+      if (need > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "row_stride %zu needs %zu bytes of shared memory per FAST strip (> %zu)",
+                    row_stride, need, (size_t)prop.sharedMemPerBlockOptin);
+      CU_TRY(h, raise_smem_limit(h->cfg.device, SMEM_FAST, need));
+      h->fast_smem_limit = need;
+    }
+  }
   return run_batch(h, n, 2, nullptr, nullptr, 0, left_dev, right_dev, image_stride, row_stride, timestamps_ns, outs, true);
 }
 
@@ -982,7 +1083,7 @@ int vslam_debug_level_image(vslam_handle h, int stage, int image, int level, uin
   const PyrP& P = h->P;
   const LevelP& L = P.lv[level];
   if (dst_capacity < (size_t)L.w * L.h) return fail(h, VSLAM_ERR_CAPACITY, "dst too small");
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   Slot& s = h->slots[h->last_slot];
   const uint8_t* src;
   int pitch = L.pitch;
@@ -1003,7 +1104,7 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
     return h ? fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad debug_fast_corners argument") : VSLAM_ERR_INVALID_ARGUMENT;
   const PyrP& P = h->P;
   const LevelP& L = P.lv[level];
-  CU_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   Slot& s = h->slots[h->last_slot];
   if (h->last_frames <= 0 || image >= h->last_frames * h->last_eyes)
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image %d was not part of the last chunk", image);
@@ -1012,7 +1113,6 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
     PyrP Pr = h->P;
     Pr.eyes = h->last_eyes;
     Pr.in_pitch = h->last_pitch;
-    Pr.lv[0].pitch = h->last_pitch;
     Pr.in_frame_stride = h->last_frame_stride;
     dim3 grid(Pr.total_fast_strips, h->last_frames * h->last_eyes);
     vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(h->last_pitch, h->P.in_pitch)), s.stream>>>(
