@@ -327,3 +327,51 @@ def bow_quantize(desc, vocab, levels_up):
     nl = np.zeros(max(n, 1), dtype=np.uint32)
     lib().orc_bow_quantize(_p(desc), n, _p(nd), _p(cb), _p(ci), _p(pa), _p(wi), int(levels_up), _p(w), _p(lf), _p(nl))
     return w[:n], lf[:n], nl[:n]
+
+
+class TriParams(C.Structure):
+    _fields_ = [("F", C.c_double * 9), ("epipole", C.c_double * 2), ("max_dist", C.c_uint32), ("radius", C.c_float),
+                ("image_width", C.c_uint32), ("image_height", C.c_uint32)]
+
+
+def tri_params(F, epipole, max_dist, camera, radius=100.0):
+    """image_width/height as triangulation.rs:432-433: (camera.cx * 2.0) as u32."""
+    p = TriParams()
+    p.F[:] = [float(v) for v in np.asarray(F, dtype=np.float64).reshape(9)]
+    p.epipole[:] = [float(epipole[0]), float(epipole[1])]
+    p.max_dist, p.radius = int(max_dist), float(radius)
+    p.image_width, p.image_height = int(camera["cx"] * 2.0), int(camera["cy"] * 2.0)
+    return p
+
+
+def _tri_args(kp1, desc1, flags1, kp2, desc2, flags2):
+    return (np.ascontiguousarray(kp1, dtype=KP_DTYPE), np.ascontiguousarray(desc1, dtype=np.uint8).reshape(-1, 32),
+            np.ascontiguousarray(flags1, dtype=np.uint8), np.ascontiguousarray(kp2, dtype=KP_DTYPE),
+            np.ascontiguousarray(desc2, dtype=np.uint8).reshape(-1, 32), np.ascontiguousarray(flags2, dtype=np.uint8))
+
+
+def search_for_triangulation(kp1, desc1, flags1, kp2, desc2, flags2, params):
+    """triangulation.rs:401-530 -> int32 [n, 2] pairs (idx1, idx2) in emission order."""
+    k1, d1, f1, k2, d2, f2 = _tri_args(kp1, desc1, flags1, kp2, desc2, flags2)
+    out = np.zeros((max(len(k1), 1), 2), dtype=np.int32)
+    n = lib().orc_search_for_triangulation(_p(k1), _p(d1), _p(f1), len(k1), _p(k2), _p(d2), _p(f2), len(k2),
+                                           C.byref(params), _p(out))
+    return out[:n].copy()
+
+
+def csr(lists):
+    start = np.zeros(len(lists) + 1, dtype=np.int32)
+    start[1:] = np.cumsum([len(x) for x in lists])
+    items = np.array([v for x in lists for v in x] or [0], dtype=np.int32)
+    return start, items
+
+
+def search_for_triangulation_bow(groups, kp1, desc1, flags1, kp2, desc2, flags2, params):
+    """triangulation.rs:541-658; groups = [(indices1, indices2)] in the caller's HashMap visiting order."""
+    k1, d1, f1, k2, d2, f2 = _tri_args(kp1, desc1, flags1, kp2, desc2, flags2)
+    s1, i1 = csr([g[0] for g in groups])
+    s2, i2 = csr([g[1] for g in groups])
+    out = np.zeros((max(int(s1[-1]), 1), 2), dtype=np.int32)
+    n = lib().orc_search_for_triangulation_bow(_p(k1), _p(d1), _p(f1), len(k1), _p(k2), _p(d2), _p(f2), len(k2),
+                                               C.byref(params), len(groups), _p(s1), _p(i1), _p(s2), _p(i2), _p(out))
+    return out[:n].copy()

@@ -12,6 +12,8 @@
 //                         KeyFrame::get_features_in_area of src/atlas/map/keyframe.rs:408-446      
 //   distinctive descriptor /root/reference/src/atlas/map/map.rs:917-937 (min over i of max_j Hamming)   (row f2)
 //   BoW quantisation       /root/reference/src/vocabulary/mod.rs:230-251, 263-275 (tree descent)         (row f2)
+//   search_for_triangulation[_bow]  /root/reference/src/local_mapping/triangulation.rs:339-392, 401-530, 541-658,
+//                          661-699 (epipolar-gated keyframe <-> keyframe greedy Hamming match)           (row f2)
 //
 // PARITY UNPINNED for this file: the reference cannot be built here (no Rust toolchain) and holds no test
 // for these functions; the only related known-answer vectors are the popcount twins at
@@ -20,6 +22,7 @@
 //
 // Rust cast semantics are coded explicitly: float->int `as` saturates (NaN -> 0), int->int `as` wraps.
 // Build with -ffp-contract=off so no f64/f32 expression is fused.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -370,6 +373,134 @@ void orc_bow_quantize(const uint8_t* desc, int n, const uint8_t* node_desc, cons
     }
     out_node[i] = up;
   }
+}
+
+// ---- local_mapping/triangulation.rs: search_for_triangulation (:401-530) and search_for_triangulation_bow (:541-658).
+// The pose algebra (epipole :417-428, F = K^-T [t12]x R12 K^-1 :668-680) is loop-invariant nalgebra arithmetic and stays
+// with the caller, exactly like the projection of the tracking searches: F (row-major 3x3) and the epipole come in.
+// flags1: bit 0 = feature already has a map point, bit 1 = has stereo depth; flags2: bit 0 = has a map point.
+struct OrcTriParams {
+  double F[9];
+  double epipole[2];
+  uint32_t max_dist;
+  float radius;                        // 100.0f (:440)
+  uint32_t image_width, image_height;  // (camera.cx * 2.0) as u32, (camera.cy * 2.0) as u32 (:432-433)
+};
+
+static inline uint64_t f32_as_usize(float v) {  // Rust `as usize`: saturating, NaN -> 0
+  if (!(v > 0.0f)) return 0;
+  if (v >= 18446744073709551616.0f) return ~0ull;
+  return (uint64_t)v;
+}
+
+// :661-699 check_epipolar_constraint with F given.  nalgebra: l2 = F * p1 accumulates column by column
+// ((F_i0 x + F_i1 y) + F_i2 * 1), dot of 3-vectors = (a + b) + c.
+static bool orc_epipolar_ok(const double* F, const OrcKeyPoint& k1, const OrcKeyPoint& k2) {
+  const double x1 = (double)k1.x, y1 = (double)k1.y, x2 = (double)k2.x, y2 = (double)k2.y;
+  double l2[3];
+  for (int i = 0; i < 3; ++i) {
+    double acc = F[3 * i] * x1;
+    acc = acc + F[3 * i + 1] * y1;
+    acc = acc + F[3 * i + 2] * 1.0;
+    l2[i] = acc;
+  }
+  const double num = std::fabs((l2[0] * x2 + l2[1] * y2) + l2[2] * 1.0);
+  const double den = std::sqrt(l2[0] * l2[0] + l2[1] * l2[1]);
+  if (den < 1e-10) return false;
+  const double dist = num / den;
+  return dist * dist < 3.84 * 1.0;
+}
+
+// the candidate loop both variants share (:471-523 == :601-649); returns idx2 or -1
+static int orc_tri_best(int idx1, const int* cand, int nc, const OrcKeyPoint* kp1, const uint8_t* desc1,
+                        const uint8_t* flags1, const OrcKeyPoint* kp2, const uint8_t* desc2, const uint8_t* flags2,
+                        const std::vector<uint8_t>& matched2, const OrcTriParams* P) {
+  uint32_t best_dist = P->max_dist;
+  int best_idx2 = -1;
+  const bool has_stereo1 = (flags1[idx1] & 2) != 0;
+  for (int c = 0; c < nc; ++c) {
+    const int idx2 = cand[c];
+    if (matched2[idx2] || (flags2[idx2] & 1)) continue;
+    if (!has_stereo1) {
+      const double dx = P->epipole[0] - (double)kp2[idx2].x, dy = P->epipole[1] - (double)kp2[idx2].y;
+      if (dx * dx + dy * dy < 100.0 * 1.0) continue;
+    }
+    if (!orc_epipolar_ok(P->F, kp1[idx1], kp2[idx2])) continue;
+    const uint32_t dist = orc_descriptor_distance(desc1 + (size_t)idx1 * 32, 32, desc2 + (size_t)idx2 * 32, 32);
+    if (dist < best_dist && dist <= P->max_dist) {
+      best_idx2 = idx2;
+      best_dist = dist;
+    }
+  }
+  return best_idx2;
+}
+
+// Spatial-grid variant.  out_pairs: (idx1, idx2) in emission order; returns the pair count.
+int orc_search_for_triangulation(const OrcKeyPoint* kp1, const uint8_t* desc1, const uint8_t* flags1, int n1,
+                                 const OrcKeyPoint* kp2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                 const OrcTriParams* P, int* out_pairs) {
+  const float cell = 32.0f;  // GRID_CELL_SIZE (:339)
+  const uint64_t max_dim = 64;  // MAX_GRID_DIM (:342)
+  const uint64_t cols = std::min(f32_as_usize(std::ceil((float)P->image_width / cell)), max_dim);
+  const uint64_t rows = std::min(f32_as_usize(std::ceil((float)P->image_height / cell)), max_dim);
+  if (cols == 0 || rows == 0) return 0;  // (the reference would underflow `grid_cols - 1`; not reachable with a real camera)
+  std::vector<std::vector<int>> grid(cols * rows);  // build_feature_grid (:348-363)
+  for (int i = 0; i < n2; ++i) {
+    const uint64_t col = std::min(f32_as_usize(kp2[i].x / cell), cols - 1);
+    const uint64_t row = std::min(f32_as_usize(kp2[i].y / cell), rows - 1);
+    grid[row * cols + col].push_back(i);
+  }
+  std::vector<uint8_t> matched2((size_t)std::max(n2, 1), 0);
+  std::vector<int> cand;
+  int n = 0;
+  for (int idx1 = 0; idx1 < n1; ++idx1) {
+    if (flags1[idx1] & 1) continue;
+    // get_candidates_in_radius (:368-392), f32 arithmetic
+    const float x = kp1[idx1].x, y = kp1[idx1].y, r = P->radius;
+    const uint64_t min_col = f32_as_usize(std::fmax(std::floor((x - r) / cell), 0.0f));
+    const uint64_t max_col = std::min(f32_as_usize(std::ceil((x + r) / cell)), cols - 1);
+    const uint64_t min_row = f32_as_usize(std::fmax(std::floor((y - r) / cell), 0.0f));
+    const uint64_t max_row = std::min(f32_as_usize(std::ceil((y + r) / cell)), rows - 1);
+    cand.clear();
+    for (uint64_t row = min_row; row <= max_row; ++row)
+      for (uint64_t col = min_col; col <= max_col; ++col) {
+        const uint64_t ci = row * cols + col;
+        if (ci < grid.size()) cand.insert(cand.end(), grid[ci].begin(), grid[ci].end());
+      }
+    const int j = orc_tri_best(idx1, cand.data(), (int)cand.size(), kp1, desc1, flags1, kp2, desc2, flags2, matched2, P);
+    if (j >= 0) {
+      out_pairs[2 * n] = idx1;
+      out_pairs[2 * n + 1] = j;
+      ++n;
+      matched2[j] = 1;
+    }
+  }
+  return n;
+}
+
+// FeatureVector variant.  The reference iterates a HashMap<u32, Vec<usize>> (vocabulary/mod.rs:37), so the node order is
+// an INPUT: group g = (indices1, indices2) of the g-th visited node present in both keyframes, as CSR lists.
+int orc_search_for_triangulation_bow(const OrcKeyPoint* kp1, const uint8_t* desc1, const uint8_t* flags1, int n1,
+                                     const OrcKeyPoint* kp2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                     const OrcTriParams* P, int n_groups, const int* g1_start, const int* g1_items,
+                                     const int* g2_start, const int* g2_items, int* out_pairs) {
+  std::vector<uint8_t> matched2((size_t)std::max(n2, 1), 0);
+  int n = 0;
+  for (int g = 0; g < n_groups; ++g)
+    for (int a = g1_start[g]; a < g1_start[g + 1]; ++a) {
+      const int idx1 = g1_items[a];
+      if (idx1 < 0 || idx1 >= n1) continue;  // kp1.get(idx1) -> Err
+      if (flags1[idx1] & 1) continue;
+      const int j = orc_tri_best(idx1, g2_items + g2_start[g], g2_start[g + 1] - g2_start[g], kp1, desc1, flags1, kp2, desc2,
+                                 flags2, matched2, P);
+      if (j >= 0) {
+        out_pairs[2 * n] = idx1;
+        out_pairs[2 * n + 1] = j;
+        ++n;
+        matched2[j] = 1;
+      }
+    }
+  return n;
 }
 
 }  // extern "C"
