@@ -63,11 +63,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=2000, help="stereo frames per GPU per step")
+    ap.add_argument("--total-frames", type=int, default=0,
+                    help="strong scaling (BASELINE configs[4]): this many frames in total, sharded over the ranks with "
+                         "shard.frame_range; overrides --frames and reports \"scaling\": \"strong\"")
     ap.add_argument("--batch", type=int, default=64, help="frames per pipeline chunk (vslam max_batch)")
     ap.add_argument("--unique", type=int, default=0, help="distinct synthetic frames (0 = all distinct)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parity-frames", type=int, default=4)
+    ap.add_argument("--parity-frames", type=int, default=256, help="benchmarked frames compared bit-for-bit with the CPU "
+                    "reference path on EVERY rank (spread over the batch; outside the timed regions)")
     ap.add_argument("--workload", default="euroc", choices=["euroc", "720p"],
                     help="euroc = BASELINE configs[1] (752x480, 1200 features; the headline, default); 720p = configs[2] "
                          "(1280x720, 2000 features) for the resolution sweep")
@@ -95,15 +99,135 @@ def _cpu_init(path):
 
 def _cpu_worker(args):
     """One worker = one core: cv::ORB (cv2) on L and R + restated match_features + triangulate, per frame."""
-    idx, cam = args
+    idx, cam, nfeat = args
     import numpy as np
     from oracle import cv2_ref
 
-    orb = cv2_ref.make_orb(NFEAT)
+    orb = cv2_ref.make_orb(nfeat)
     t0 = time.perf_counter()
     for i in idx:
-        cv2_ref.stereo_process(np.ascontiguousarray(_FRAMES[0, i]), np.ascontiguousarray(_FRAMES[1, i]), cam, NFEAT, orb)
+        cv2_ref.stereo_process(np.ascontiguousarray(_FRAMES[0, i]), np.ascontiguousarray(_FRAMES[1, i]), cam, nfeat, orb)
     return len(idx), time.perf_counter() - t0
+
+
+def cpu_model_string():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_single_process_profile(lefts, rights, cam, nfeat, frames=24):
+    """single process, cv2.setNumThreads(1): per-stage p50 / p95 (ms) of the reference's process() —
+    detect_features(left), detect_features(right), match_features, triangulate (stereo.rs:52-66)."""
+    import cv2
+    import numpy as np
+    from oracle import cv2_ref, orb_oracle as oo
+
+    cv2.setNumThreads(1)
+    orb = cv2_ref.make_orb(nfeat)
+    rows = []
+    for i in range(min(frames + 2, len(lefts))):
+        li, ri = np.ascontiguousarray(lefts[i]), np.ascontiguousarray(rights[i])
+        t0 = time.perf_counter()
+        kl, dl = cv2_ref.detect_and_compute(li, nfeat, orb)
+        t1 = time.perf_counter()
+        kr, dr = cv2_ref.detect_and_compute(ri, nfeat, orb)
+        t2 = time.perf_counter()
+        m = oo.match_features(kl, dl, kr, dr, cam)
+        t3 = time.perf_counter()
+        oo.triangulate(kl, kr, m, cam)
+        t4 = time.perf_counter()
+        if i >= 2:  # warm-up
+            rows.append([1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (t4 - t0)])
+    a = np.array(rows)
+    names = ["extract_left", "extract_right", "match_features", "triangulate", "process_total"]
+    return {"frames": len(rows),
+            "p50_ms": {n: round(float(np.percentile(a[:, j], 50)), 3) for j, n in enumerate(names)},
+            "p95_ms": {n: round(float(np.percentile(a[:, j], 95)), 3) for j, n in enumerate(names)},
+            "note": "cv2 keypoint marshalling into numpy is inside extract_* (the reference pays an FFI Vector<KeyPoint> too)"}
+
+
+_PAR = None
+
+
+def _parity_init(path, w, h, nfeat):
+    global _PAR
+    import numpy as np
+
+    try:
+        import cv2
+
+        cv2.setNumThreads(1)
+    except ImportError:
+        pass
+    _PAR = (np.load(path, mmap_mode="r"), w, h, nfeat)
+
+
+def _parity_worker(args):
+    """Reference result of one stereo frame as per-array SHA-1 digests: cv::ORB through cv2 when importable (the engine
+    the reference calls), else the C++ restatement, + restated match_features / triangulate."""
+    import hashlib
+
+    import numpy as np
+    from oracle import orb_oracle as oo
+
+    k, cam = args
+    frames, w, h, nfeat = _PAR
+    li, ri = np.ascontiguousarray(frames[0, k]), np.ascontiguousarray(frames[1, k])
+    try:
+        from oracle import cv2_ref
+
+        cv2_ref.cv2_module()
+        (kl, dl), (kr, dr) = cv2_ref.detect_and_compute(li, nfeat), cv2_ref.detect_and_compute(ri, nfeat)
+        engine = "cv2"
+    except ImportError:
+        (kl, dl), (kr, dr) = oo.detect_and_compute(li, nfeat), oo.detect_and_compute(ri, nfeat)
+        engine = "oracle"
+    m = oo.match_features(kl, dl, kr, dr, cam)
+    pts, valid = oo.triangulate(kl, kr, m, cam)
+    dig = [hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest() for a in (kl, kr, dl, dr, m, pts, valid)]
+    return k, dig, engine, (len(kl), len(kr), len(m))
+
+
+def check_parity(ob, host_l, host_r, idxs, cam, nproc):
+    """Compares the benchmarked frames `idxs` of the e2e pass (result arrays `ob`) bit-for-bit against the CPU reference
+    path, computed by `nproc` spawned workers — outside every timed region."""
+    import hashlib
+    import multiprocessing as mp
+    import tempfile
+
+    import numpy as np
+
+    fd, path = tempfile.mkstemp(suffix=".npy", prefix="vslam_parity_")
+    os.close(fd)
+    try:
+        np.save(path, np.stack([host_l[idxs].numpy(), host_r[idxs].numpy()]))
+        with mp.get_context("spawn").Pool(max(1, nproc), initializer=_parity_init, initargs=(path, W, H, NFEAT)) as pool:
+            res = pool.map(_parity_worker, [(k, dict(cam)) for k in range(len(idxs))], chunksize=4)
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    names = ["kp_left", "kp_right", "desc_left", "desc_right", "matches", "points_cam", "points_valid"]
+    bad, bad_fields, engine = 0, {}, "oracle"
+    for k, dig, engine, _counts in res:
+        fr = ob.frame(int(idxs[k]), copy=False)
+        arrs = (fr.left_features.keypoints, fr.right_features.keypoints, fr.left_features.descriptors,
+                fr.right_features.descriptors, fr.matches_lr, fr.points_cam, fr.points_valid)
+        mine = [hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest() for a in arrs]
+        diff = [n for n, a, b in zip(names, mine, dig) if a != b]
+        if diff:
+            bad += 1
+            for n in diff:
+                bad_fields[n] = bad_fields.get(n, 0) + 1
+    against = ("cv2 cv::ORB (the engine the reference calls) + restated match_features/triangulate, bit-exact"
+               if engine == "cv2" else "oracle restatement, bit-exact")
+    return {"frames_checked": len(idxs), "mismatching_frames": bad, "mismatching_arrays": bad_fields, "against": against}
 
 
 class CpuReference:
@@ -123,11 +247,12 @@ class CpuReference:
         os.close(fd)
         np.save(self.path, np.stack([host_l, host_r]))
         self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(self.path,))
-        self.pool.map(_cpu_worker, [([c % self.n], self.cam) for c in range(self.cores)])  # warm-up: imports, page-in
+        self.nfeat = NFEAT
+        self.pool.map(_cpu_worker, [([c % self.n], self.cam, self.nfeat) for c in range(self.cores)])  # warm-up: imports, page-in
 
     def run(self, seconds):
         per_core = max(2, int(seconds / 0.035))  # ~35 ms per stereo frame per core
-        jobs = [([(c * per_core + i) % self.n for i in range(per_core)], self.cam) for c in range(self.cores)]
+        jobs = [([(c * per_core + i) % self.n for i in range(per_core)], self.cam, self.nfeat) for c in range(self.cores)]
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
@@ -161,6 +286,7 @@ def run_reference(args, rank):
     ref.close()
     value = frames / wall
     cores = ref.cores
+    single = cpu_single_process_profile(ls.numpy(), rs.numpy(), synth.EUROC_CAMERA, NFEAT)
     sample = (f"{n} stereo frames per step ({n // cores} per core, {nuniq} distinct synthetic {W}x{H} pairs), "
               f"cv2.ORB_create({NFEAT},1.2,8,31,0,2,HARRIS,31,20).detectAndCompute on L and R (the cv::ORB the reference "
               f"calls) + C++ restatement of match_features/triangulate; one process per core, cv2.setNumThreads(1)")
@@ -169,7 +295,8 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{CONFIG_NAME}: batch of synthetic {W}x{H} stereo frames, {NFEAT} features, 8 levels, scale 1.2"},
-        "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model_string(), "single_process": single},
         "e2e": {"value": round(value, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -249,10 +376,20 @@ def main():
         torch.cuda.synchronize()
 
     cam = CameraModel(**synth.EUROC_CAMERA)
-    n = args.frames
-    nuniq = args.unique or n
-    # frames are independent units: rank r owns seeds [r*n, (r+1)*n)  (sharded, no collective on the data path)
-    seeds = shard.weak_seeds(rank, n, args.unique)
+    strong = args.total_frames > 0
+    if strong:
+        # strong scaling: a fixed set of frames (seeds 0 .. total-1) split into contiguous per-rank ranges
+        mine = shard.frame_range(rank, world, args.total_frames)
+        n = len(mine)
+        nuniq = args.unique or n
+        seeds = [mine.start + (i % nuniq) for i in range(n)]
+        if n == 0:
+            raise SystemExit("--total-frames smaller than the number of ranks")
+    else:
+        n = args.frames
+        nuniq = args.unique or n
+        # weak scaling: rank r owns seeds [r*n, (r+1)*n)  (independent frames, no collective on the data path)
+        seeds = shard.weak_seeds(rank, n, args.unique)
     t_gen = time.perf_counter()
     left = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
     right = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
@@ -283,11 +420,13 @@ def main():
     barrier()
     launches0 = sp.kernel_launches()
     t0 = time.perf_counter()
-    dev_ms = 0.0
+    dev_ms, step_ms = 0.0, []
     for _ in range(args.steps):
-        dev_ms += step_device()
+        step_ms.append(step_device())
+        dev_ms += step_ms[-1]
     barrier()
     t1 = time.perf_counter()
+    p50_frame_ms = statistics.median(step_ms) / n  # median over the timed steps of (device ms of the step / frames)
     launches = sp.kernel_launches() - launches0
     wall_ms = 1e3 * (t1 - t0)
     clocks = sampler.stop(t0, t1)
@@ -311,7 +450,9 @@ def main():
         o.kp_left, o.kp_right = ob.kpl[i].ctypes.data, ob.kpr[i].ctypes.data
         o.desc_left, o.desc_right = ob.dl[i].ctypes.data, ob.dr[i].ctypes.data
         o.matches, o.points_cam, o.points_valid = ob.m[i].ctypes.data, ob.pts[i].ctypes.data, ob.valid[i].ctypes.data
-    d2h_bytes = n * (32 + sp.capacity * (28 * 2 + 32 * 2 + 16 + 24 + 1))
+    # per frame: 32 B header + min(capacity, n_features) rows of every result array (2-D copies: the tail rows of the
+    # [frames][capacity] arrays never cross PCIe)
+    d2h_bytes = n * (32 + min(sp.capacity, NFEAT) * (28 * 2 + 32 * 2 + 16 + 24 + 1))
 
     def step_e2e():
         sp.process_batch_raw(n, lp, rp, W, ob)
@@ -388,29 +529,21 @@ def main():
                              "achieved": round(dense_gbs, 2), "frac": round(dense_gbs / peak, 4)},
     }
 
-    # ---------------- parity spot check of the benchmarked frames (outside every timed region)
+    # ---------------- parity of the benchmarked frames (outside every timed region), on EVERY rank
     parity = None
-    if rank == 0 and args.parity_frames > 0:
-        from oracle import orb_oracle as oo
+    if args.parity_frames > 0:
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        idxs = np.array(sorted(set(int(x) for x in np.linspace(0, n - 1, min(args.parity_frames, n)))))
+        parity = check_parity(ob, host_l, host_r, idxs, synth.EUROC_CAMERA, max(1, ncores // world))
+        if world > 1:  # every rank checks its own frames; rank 0 reports the totals
+            parity["frames_checked"] = int(shard.reduce_sum(parity["frames_checked"], dist, dev))
+            parity["mismatching_frames"] = int(shard.reduce_sum(parity["mismatching_frames"], dist, dev))
+            parity["ranks"] = world
 
-        bad = 0
-        idxs = sorted(set(int(x) for x in np.linspace(0, n - 1, args.parity_frames)))
-        for i in idxs:
-            fr = ob.frame(i, copy=False)
-            li, ri = host_l[i].numpy(), host_r[i].numpy()
-            kl, dl = oo.detect_and_compute(li, NFEAT)
-            kr, dr = oo.detect_and_compute(ri, NFEAT)
-            m = oo.match_features(kl, dl, kr, dr, synth.EUROC_CAMERA)
-            pts, valid = oo.triangulate(kl, kr, m, synth.EUROC_CAMERA)
-            ok = (fr.left_features.keypoints.tobytes() == kl.tobytes() and fr.right_features.keypoints.tobytes() == kr.tobytes()
-                  and np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
-                  and fr.matches_lr.tobytes() == m.tobytes() and np.array_equal(fr.points_cam, pts)
-                  and np.array_equal(fr.points_valid, valid))
-            bad += 0 if ok else 1
-        parity = {"frames_checked": len(idxs), "mismatching_frames": bad, "against": "oracle (bit-exact)"}
-
-    # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
-    cpu = None
+    # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only; at N > 1 the host cores are shared by the
+    # ranks and the driver runs `--impl reference` itself, so the line carries a note instead)
+    cpu = None if world == 1 else {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+                                   "sample": "not measured at N > 1: see the N=1 line / bench.py --impl reference"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             ref = CpuReference(host_l[: min(n, 64)].numpy(), host_r[: min(n, 64)].numpy(), synth.EUROC_CAMERA)
@@ -420,7 +553,10 @@ def main():
             cpu = {"value": round(rate, 2), "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": (f"{nf} of the benchmark's stereo frames ({nf // cores} per core) in {wall:.1f} s: cv2.ORB (the "
                               "cv::ORB the reference calls) on L and R + C++ restatement of match_features/triangulate, "
-                              "one process per core, cv2.setNumThreads(1)")}
+                              "one process per core, cv2.setNumThreads(1)"),
+                   "cpu_model": cpu_model_string(),
+                   "single_process": cpu_single_process_profile(host_l[:26].numpy(), host_r[:26].numpy(),
+                                                                synth.EUROC_CAMERA, NFEAT)}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
@@ -429,20 +565,27 @@ def main():
         return shard.reduce_max(x, dist if world > 1 else None, dev)
 
     dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms = rmax(dev_ms), rmax(wall_ms), rmax(e2e_dev_ms), rmax(e2e_wall_ms)
-    total_frames = n * world * args.steps
+    p50_frame_ms = rmax(p50_frame_ms)
+    frames_all = int(shard.reduce_sum(n, dist if world > 1 else None, dev))  # == n * world (weak) or --total-frames
+    total_frames = frames_all * args.steps
     value = shard.throughput(total_frames, dev_ms)
     e2e_value = shard.throughput(total_frames, e2e_wall_ms)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{CONFIG_NAME}: batch of {n} synthetic {W}x{H} stereo frames per GPU, {NFEAT} features, 8 levels, "
-                                   "scale 1.2: ORB extract x2 + stereo match + triangulate",
-                       "frames_per_gpu_per_step": n, "distinct_frames": nuniq, "chunk": args.batch,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": (f"configs[4]: {frames_all} synthetic {W}x{H} stereo frames in total, frame-sharded over "
+                                    f"{world} GPU(s), {NFEAT} features, 8 levels, scale 1.2: ORB extract x2 + stereo match + "
+                                    "triangulate" if strong else
+                                    f"{CONFIG_NAME}: batch of {n} synthetic {W}x{H} stereo frames per GPU, {NFEAT} features, "
+                                    "8 levels, scale 1.2: ORB extract x2 + stereo match + triangulate"),
+                       "frames_per_gpu_per_step": n, "frames_all_gpus_per_step": frames_all, "distinct_frames": nuniq,
+                       "chunk": args.batch,
                        "cache": f"inputs larger than L2 ({2 * n * img_bytes / 1e9:.2f} GB per step vs 126 MB L2); no flush needed",
                        "sharding": "independent frames per rank, no collective"},
-            "ms_per_step_wall": round(wall_ms / args.steps, 3), "p50_ms_per_frame": round(dev_ms / args.steps / n, 5),
+            "ms_per_step_wall": round(wall_ms / args.steps, 3), "mean_ms_per_frame": round(dev_ms / args.steps / n, 5),
+            "p50_ms_per_frame": round(p50_frame_ms, 5),
             "p50_ms_single_pair_latency": round(p50_single, 3),
             "timing": "CUDA events on the library's own streams (vslam_last_batch_ms), max over ranks",
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": 2 * n * img_bytes,

@@ -21,6 +21,8 @@
  *   vslam_distinctive_descriptors       <- Map::compute_distinctive_descriptors       src/atlas/map/map.rs:917-937
  *   vslam_vocab_upload / vslam_bow_quantize <- OrbVocabulary::{load_from_text, transform_descriptor,
  *                                          get_parent_at_level}                       src/vocabulary/mod.rs:109-206, 230-275
+ *   vslam_search_for_triangulation[_bow] <- search_for_triangulation[_bow]
+ *                                          src/local_mapping/triangulation.rs:401-530, 541-658 (+ :339-392, 661-699)
  *
  * All pixel/descriptor arithmetic runs in hand-written CUDA kernels for sm_100a.  There is NO CPU fallback:
  * every call fails with VSLAM_ERR_CUDA when no usable device is present.
@@ -238,6 +240,32 @@ int vslam_vocab_upload(vslam_handle h, int n_nodes, const uint8_t* node_desc, co
                        const int32_t* child_ids, const uint32_t* parent, const int32_t* word_id);
 int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up, uint32_t* out_word,
                        uint32_t* out_leaf, uint32_t* out_node);
+
+/* Epipolar-gated keyframe <-> keyframe matching for triangulation (local_mapping/triangulation.rs:401-530 and, with
+ * FeatureVector groups, :541-658).  The loop-invariant pose algebra stays in the caller (nalgebra, like the projection of
+ * the tracking searches): F = K^-T [t12]x R12 K^-1 exactly as check_epipolar_constraint builds it (:668-680, row-major
+ * here) and the epipole (:421-428).  flags1[i]: bit 0 = feature i of keyframe 1 already has a map point (skipped),
+ * bit 1 = it has stereo depth (no epipole-distance gate); flags2[j]: bit 0 = feature j of keyframe 2 has a map point.
+ * out_pairs[][2] = (idx1, idx2) in the order the reference's greedy loop emits them (a feature of keyframe 2 is taken
+ * at most once, first come first served); capacity n1 pairs (bow: g1_start[n_groups] pairs). */
+typedef struct vslam_tri_params {
+  double F[9];
+  double epipole[2];
+  uint32_t max_dist;                  /* config.max_descriptor_dist */
+  float radius;                       /* 100.0f (triangulation.rs:440); grid variant only */
+  uint32_t image_width, image_height; /* (camera.cx * 2.0) as u32, (camera.cy * 2.0) as u32 (:432-433); grid variant */
+} vslam_tri_params;
+int vslam_search_for_triangulation(vslam_handle h, const vslam_keypoint* kp1, const uint8_t* desc1, const uint8_t* flags1,
+                                   int n1, const vslam_keypoint* kp2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                   const vslam_tri_params* params, int32_t* out_pairs, int* n_pairs);
+/* FeatureVector variant: group g = the g-th vocabulary node the caller's HashMap iteration visited that is present in
+ * both keyframes (the visiting order is an input: the greedy pass depends on it); its keyframe-1 features are
+ * g1_items[g1_start[g] .. g1_start[g+1]) and its keyframe-2 features g2_items[g2_start[g] .. g2_start[g+1]). */
+int vslam_search_for_triangulation_bow(vslam_handle h, const vslam_keypoint* kp1, const uint8_t* desc1,
+                                       const uint8_t* flags1, int n1, const vslam_keypoint* kp2, const uint8_t* desc2,
+                                       const uint8_t* flags2, int n2, const vslam_tri_params* params, int n_groups,
+                                       const int32_t* g1_start, const int32_t* g1_items, const int32_t* g2_start,
+                                       const int32_t* g2_items, int32_t* out_pairs, int* n_pairs);
 
 /* ---- introspection for parity tests and profiling ---------------------------------------------------------- */
 enum {

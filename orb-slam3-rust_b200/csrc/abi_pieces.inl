@@ -413,4 +413,129 @@ int vslam_bow_quantize(vslam_handle h, const uint8_t* desc, int n, int levels_up
   return VSLAM_OK;
 }
 
+// ---- search_for_triangulation / search_for_triangulation_bow (local_mapping/triangulation.rs:401-530, 541-658)
+static int tri_search(vslam_handle h, const vslam_keypoint* kp1, const uint8_t* desc1, const uint8_t* flags1, int n1,
+                      const vslam_keypoint* kp2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                      const vslam_tri_params* tp, int n_groups, const int32_t* g1_start, const int32_t* g1_items,
+                      const int32_t* g2_start, const int32_t* g2_items, int32_t* out_pairs, int* n_pairs) {
+  const bool bow = n_groups >= 0;
+  if (n1 < 0 || n2 < 0 || !tp || !n_pairs || (n1 > 0 && (!kp1 || !desc1 || !flags1 || !out_pairs)) ||
+      (n2 > 0 && (!kp2 || !desc2 || !flags2)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (n1 > 65535 || n2 > 65535) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "more than 65535 keypoints");
+  *n_pairs = 0;
+  vk::TriP T;
+  memcpy(T.F, tp->F, sizeof(T.F));
+  T.ex = tp->epipole[0];
+  T.ey = tp->epipole[1];
+  T.max_dist = tp->max_dist;
+  T.radius = tp->radius;
+  // grid dimensions: ((image_width as f32 / 32.0).ceil() as usize).min(64)   (triangulation.rs:349-350)
+  T.cols = (int)std::min<uint64_t>((uint64_t)std::ceil((float)tp->image_width / 32.0f), 64);
+  T.rows = (int)std::min<uint64_t>((uint64_t)std::ceil((float)tp->image_height / 32.0f), 64);
+  int n_visits = n1;
+  std::vector<int> visit_idx1, visit_group;
+  if (bow) {
+    if (n_groups > 0 && (!g1_start || !g2_start)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null group offsets");
+    if (n_groups > 0 && (g1_start[0] != 0 || g2_start[0] != 0)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad group offsets");
+    for (int g = 0; g < n_groups; ++g) {
+      if (g1_start[g + 1] < g1_start[g] || g2_start[g + 1] < g2_start[g] || g2_start[g + 1] - g2_start[g] > 65535)
+        return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "group offsets must be non-decreasing (<= 65535 candidates per group)");
+      for (int a = g1_start[g]; a < g1_start[g + 1]; ++a) {
+        visit_idx1.push_back(g1_items[a]);
+        visit_group.push_back(g);
+      }
+    }
+    n_visits = (int)visit_idx1.size();
+    if ((n_visits > 0 && !g1_items) || (n_groups > 0 && g2_start[n_groups] > 0 && !g2_items))
+      return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null group items");
+  } else if (T.cols < 1 || T.rows < 1) {
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image_width / image_height must be positive");
+  }
+  if (n_visits == 0 || n2 == 0) return VSLAM_OK;
+  DEVICE_SCOPE(h);
+  cudaStream_t st = h->slots[0].stream;
+  const size_t a1 = (size_t)n1, a2 = (size_t)n2, nv = (size_t)n_visits;
+  const size_t n_g2 = bow ? (size_t)std::max(g2_start[n_groups], 1) : 1;
+  int cap = 64;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const size_t lists = nv * (size_t)cap * sizeof(uint2);
+    if (lists > ((size_t)1 << 31)) return fail(h, VSLAM_ERR_OUT_OF_MEMORY, "candidate lists of %zu bytes", 2 * lists);
+    int rc = arena_begin(h, pad256(a1 * 28) + pad256(a1 * 32) + pad256(a1) + pad256(a2 * 28) + pad256(a2 * 32) + pad256(a2) +
+                                pad256((vk::kTriMaxCells + 1) * 4) + 2 * pad256(a2 * 4) + 2 * pad256(nv * 4) +
+                                pad256(((size_t)std::max(n_groups, 0) + 1) * 4) + pad256(n_g2 * 4) + 2 * pad256(lists) +
+                                pad256(nv * 4) + pad256(nv * 8) + 512);
+    if (rc) return rc;
+    unsigned char* dk1 = arena_take<unsigned char>(h, a1 * 28);
+    unsigned* dd1 = arena_take<unsigned>(h, a1 * 8);
+    unsigned char* df1 = arena_take<unsigned char>(h, a1);
+    unsigned char* dk2 = arena_take<unsigned char>(h, a2 * 28);
+    unsigned* dd2 = arena_take<unsigned>(h, a2 * 8);
+    unsigned char* df2 = arena_take<unsigned char>(h, a2);
+    int* dcs = arena_take<int>(h, vk::kTriMaxCells + 1);
+    int* dci = arena_take<int>(h, a2);
+    int* dco = arena_take<int>(h, a2);
+    int* dvi = arena_take<int>(h, nv);
+    int* dvg = arena_take<int>(h, nv);
+    int* dgs = arena_take<int>(h, (size_t)std::max(n_groups, 0) + 1);
+    int* dgi = arena_take<int>(h, n_g2);
+    uint2* draw = arena_take<uint2>(h, nv * (size_t)cap);
+    uint2* dlist = arena_take<uint2>(h, nv * (size_t)cap);
+    int* dcnt = arena_take<int>(h, nv);
+    int* dpairs = arena_take<int>(h, nv * 2);
+    int* dnp = arena_take<int>(h, 2);
+    CU_TRY(h, cudaMemcpyAsync(dk1, kp1, a1 * 28, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(dd1, desc1, a1 * 32, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(df1, flags1, a1, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(dk2, kp2, a2 * 28, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(dd2, desc2, a2 * 32, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(df2, flags2, a2, cudaMemcpyHostToDevice, st));
+    if (bow) {
+      CU_TRY(h, cudaMemcpyAsync(dvi, visit_idx1.data(), nv * 4, cudaMemcpyHostToDevice, st));
+      CU_TRY(h, cudaMemcpyAsync(dvg, visit_group.data(), nv * 4, cudaMemcpyHostToDevice, st));
+      CU_TRY(h, cudaMemcpyAsync(dgs, g2_start, ((size_t)n_groups + 1) * 4, cudaMemcpyHostToDevice, st));
+      if (g2_start[n_groups] > 0)
+        CU_TRY(h, cudaMemcpyAsync(dgi, g2_items, (size_t)g2_start[n_groups] * 4, cudaMemcpyHostToDevice, st));
+    } else {
+      vk::k_tri_grid_build<<<1, 1024, 0, st>>>(dk2, n2, T.cols, T.rows, dcs, dci, dco);
+      h->launches++;
+    }
+    vk::k_tri_candidates<<<(unsigned)((nv * 32 + 255) / 256), 256, 0, st>>>(
+        dk1, dd1, df1, n1, dk2, dd2, df2, n2, T, dcs, dci, bow ? dvi : nullptr, dvg, dgs, dgi, n_visits, cap, draw, dlist, dcnt);
+    vk::k_tri_resolve<<<1, 32, (size_t)((n2 + 31) / 32) * 4, st>>>(dlist, dcnt, cap, bow ? dvi : nullptr, n_visits, n2, dpairs, dnp);
+    h->launches += 2;
+    int np[2] = {0, 0};
+    CU_TRY(h, cudaMemcpyAsync(np, dnp, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    CU_TRY(h, cudaGetLastError());
+    if (np[1] > cap) {  // a list was truncated (more than 64 candidates pass every gate): once more with room for all
+      cap = np[1];
+      continue;
+    }
+    *n_pairs = np[0];
+    if (np[0] > 0) CU_TRY(h, cudaMemcpy(out_pairs, dpairs, (size_t)np[0] * 8, cudaMemcpyDeviceToHost));
+    return VSLAM_OK;
+  }
+  return fail(h, VSLAM_ERR_CUDA, "search_for_triangulation: candidate lists did not converge");
+}
+
+int vslam_search_for_triangulation(vslam_handle h, const vslam_keypoint* kp1, const uint8_t* desc1, const uint8_t* flags1,
+                                   int n1, const vslam_keypoint* kp2, const uint8_t* desc2, const uint8_t* flags2, int n2,
+                                   const vslam_tri_params* params, int32_t* out_pairs, int* n_pairs) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  return tri_search(h, kp1, desc1, flags1, n1, kp2, desc2, flags2, n2, params, -1, nullptr, nullptr, nullptr, nullptr,
+                    out_pairs, n_pairs);
+}
+
+int vslam_search_for_triangulation_bow(vslam_handle h, const vslam_keypoint* kp1, const uint8_t* desc1,
+                                       const uint8_t* flags1, int n1, const vslam_keypoint* kp2, const uint8_t* desc2,
+                                       const uint8_t* flags2, int n2, const vslam_tri_params* params, int n_groups,
+                                       const int32_t* g1_start, const int32_t* g1_items, const int32_t* g2_start,
+                                       const int32_t* g2_items, int32_t* out_pairs, int* n_pairs) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (n_groups < 0) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "n_groups < 0");
+  return tri_search(h, kp1, desc1, flags1, n1, kp2, desc2, flags2, n2, params, n_groups, g1_start, g1_items, g2_start,
+                    g2_items, out_pairs, n_pairs);
+}
+
 }  // extern "C"

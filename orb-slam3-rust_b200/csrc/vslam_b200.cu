@@ -25,6 +25,7 @@
 #include "orb_kernels.cuh"
 #include "stereo_kernels.cuh"
 #include "track_kernels.cuh"
+#include "tri_kernels.cuh"
 #include "vslam_params.h"
 
 namespace {

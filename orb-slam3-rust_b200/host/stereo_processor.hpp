@@ -387,4 +387,61 @@ class OrbVocabulary {
   std::vector<VocabNode> nodes_;
 };
 
+// search_for_triangulation / search_for_triangulation_bow (local_mapping/triangulation.rs:401-530, 541-658): epipolar-gated
+// greedy keyframe <-> keyframe Hamming match.  The caller computes F (row-major, exactly as check_epipolar_constraint,
+// :668-680) and the epipole (:421-428) with its own linear algebra; has_mp*/has_stereo1 are the `is_some()` tests of the
+// reference's Option slices.  `fv_groups` (optional): the FeatureVector nodes present in both keyframes, in the order the
+// caller iterates them, as (indices1, indices2) — selects the _bow variant.  Returns (idx1, idx2) in emission order.
+struct TriangulationGeometry {
+  double F[9];
+  double epipole[2];
+};
+inline Result<std::vector<std::pair<size_t, size_t>>> search_for_triangulation(
+    StereoProcessor& p, const FeatureSet& kf1, const std::vector<bool>& has_mp1, const std::vector<bool>& has_stereo1,
+    const FeatureSet& kf2, const std::vector<bool>& has_mp2, const TriangulationGeometry& geo, uint32_t max_dist,
+    const std::vector<std::pair<std::vector<size_t>, std::vector<size_t>>>* fv_groups = nullptr) {
+  const size_t n1 = kf1.keypoints.size(), n2 = kf2.keypoints.size();
+  std::vector<uint8_t> f1(n1 + 1, 0), f2(n2 + 1, 0);
+  for (size_t i = 0; i < n1; ++i)  // mp1.get(i).map_or(false, ..): a short slice reads as None
+    f1[i] = (uint8_t)((i < has_mp1.size() && has_mp1[i] ? 1 : 0) | (i < has_stereo1.size() && has_stereo1[i] ? 2 : 0));
+  for (size_t i = 0; i < n2; ++i) f2[i] = i < has_mp2.size() && has_mp2[i] ? 1 : 0;
+  vslam_tri_params tp;
+  std::memcpy(tp.F, geo.F, sizeof(tp.F));
+  tp.epipole[0] = geo.epipole[0];
+  tp.epipole[1] = geo.epipole[1];
+  tp.max_dist = max_dist;
+  tp.radius = 100.0f;
+  tp.image_width = (uint32_t)(p.camera().cx * 2.0);
+  tp.image_height = (uint32_t)(p.camera().cy * 2.0);
+  int n = 0, rc;
+  std::vector<int32_t> pairs;
+  if (!fv_groups) {
+    pairs.resize(2 * n1 + 2);
+    rc = vslam_search_for_triangulation(p.raw(), kf1.keypoints.data(), reinterpret_cast<const uint8_t*>(kf1.descriptors.data()),
+                                        f1.data(), (int)n1, kf2.keypoints.data(),
+                                        reinterpret_cast<const uint8_t*>(kf2.descriptors.data()), f2.data(), (int)n2, &tp,
+                                        pairs.data(), &n);
+  } else {
+    std::vector<int32_t> s1{0}, i1, s2{0}, i2;
+    for (const auto& g : *fv_groups) {
+      for (size_t v : g.first) i1.push_back((int32_t)v);
+      for (size_t v : g.second) i2.push_back((int32_t)v);
+      s1.push_back((int32_t)i1.size());
+      s2.push_back((int32_t)i2.size());
+    }
+    pairs.resize(2 * i1.size() + 2);
+    if (i1.empty()) i1.push_back(0);
+    if (i2.empty()) i2.push_back(0);
+    rc = vslam_search_for_triangulation_bow(p.raw(), kf1.keypoints.data(),
+                                            reinterpret_cast<const uint8_t*>(kf1.descriptors.data()), f1.data(), (int)n1,
+                                            kf2.keypoints.data(), reinterpret_cast<const uint8_t*>(kf2.descriptors.data()),
+                                            f2.data(), (int)n2, &tp, (int)fv_groups->size(), s1.data(), i1.data(), s2.data(),
+                                            i2.data(), pairs.data(), &n);
+  }
+  if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+  std::vector<std::pair<size_t, size_t>> out((size_t)n);
+  for (int k = 0; k < n; ++k) out[k] = {(size_t)pairs[2 * k], (size_t)pairs[2 * k + 1]};
+  return out;
+}
+
 }  // namespace vslam

@@ -55,6 +55,11 @@ class SearchParams(C.Structure):
                 ("img_w", C.c_double), ("img_h", C.c_double), ("bound_w", C.c_double), ("bound_h", C.c_double)]
 
 
+class TriParams(C.Structure):
+    _fields_ = [("F", C.c_double * 9), ("epipole", C.c_double * 2), ("max_dist", C.c_uint32), ("radius", C.c_float),
+                ("image_width", C.c_uint32), ("image_height", C.c_uint32)]
+
+
 # every symbol include/vslam_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "vslam_create", "vslam_destroy", "vslam_last_error", "vslam_keypoint_capacity", "vslam_process",
@@ -63,7 +68,7 @@ SYMBOLS = [
     "vslam_search_by_projection", "vslam_bf_match_crosscheck", "vslam_level_info", "vslam_debug_level_image",
     "vslam_debug_fast_corners", "vslam_kernel_launches", "vslam_set_profiling", "vslam_last_stage_ms",
     "vslam_last_batch_ms", "vslam_fuse_search", "vslam_distinctive_descriptors", "vslam_vocab_upload",
-    "vslam_bow_quantize",
+    "vslam_bow_quantize", "vslam_search_for_triangulation", "vslam_search_for_triangulation_bow",
 ]
 
 _lib = None
@@ -101,6 +106,10 @@ def lib():
         L.vslam_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.vslam_vocab_upload.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.vslam_bow_quantize.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.vslam_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, C.POINTER(TriParams), vp,
+                                                     C.POINTER(i32)]
+        L.vslam_search_for_triangulation_bow.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, C.POINTER(TriParams), i32,
+                                                         vp, vp, vp, vp, vp, C.POINTER(i32)]
         L.vslam_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i32)]
         L.vslam_debug_level_image.argtypes = [vp, i32, i32, i32, vp, sz]
         L.vslam_debug_fast_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]

@@ -373,6 +373,45 @@ class StereoProcessor:
             self._raise(rc)
         return w[:n], lf[:n], nl[:n]
 
+    def search_for_triangulation(self, kf1: FeatureSet, flags1, kf2: FeatureSet, flags2, F, epipole, max_dist,
+                                 groups=None, radius=100.0):
+        """search_for_triangulation (local_mapping/triangulation.rs:401-530); with `groups` = [(indices1, indices2)]
+        in the caller's FeatureVector visiting order: search_for_triangulation_bow (:541-658).  F and the epipole are
+        computed by the caller (:417-428, :668-680).  flags: bit 0 = has a map point, bit 1 (kf1) = has stereo depth.
+        -> int32 [n, 2] pairs (idx1, idx2) in emission order."""
+        k1 = np.ascontiguousarray(kf1.keypoints, dtype=KP_DTYPE)
+        d1 = np.ascontiguousarray(kf1.descriptors, dtype=np.uint8).reshape(-1, 32)
+        f1 = np.ascontiguousarray(flags1, dtype=np.uint8)
+        k2 = np.ascontiguousarray(kf2.keypoints, dtype=KP_DTYPE)
+        d2 = np.ascontiguousarray(kf2.descriptors, dtype=np.uint8).reshape(-1, 32)
+        f2 = np.ascontiguousarray(flags2, dtype=np.uint8)
+        tp = _abi.TriParams()
+        tp.F[:] = [float(v) for v in np.asarray(F, dtype=np.float64).reshape(9)]
+        tp.epipole[:] = [float(epipole[0]), float(epipole[1])]
+        tp.max_dist, tp.radius = int(max_dist), float(radius)
+        tp.image_width, tp.image_height = int(self.camera.cx * 2.0), int(self.camera.cy * 2.0)  # `as u32`
+        n = C.c_int(0)
+        if groups is None:
+            out = np.zeros((max(len(k1), 1), 2), dtype=np.int32)
+            rc = self._lib.vslam_search_for_triangulation(self._h, _ptr(k1), _ptr(d1), _ptr(f1), len(k1), _ptr(k2),
+                                                          _ptr(d2), _ptr(f2), len(k2), C.byref(tp), _ptr(out), C.byref(n))
+        else:
+            def csr(lists):
+                start = np.zeros(len(lists) + 1, dtype=np.int32)
+                start[1:] = np.cumsum([len(x) for x in lists])
+                return start, np.array([v for x in lists for v in x] or [0], dtype=np.int32)
+
+            s1, i1 = csr([g[0] for g in groups])
+            s2, i2 = csr([g[1] for g in groups])
+            out = np.zeros((max(int(s1[-1]), 1), 2), dtype=np.int32)
+            rc = self._lib.vslam_search_for_triangulation_bow(self._h, _ptr(k1), _ptr(d1), _ptr(f1), len(k1), _ptr(k2),
+                                                              _ptr(d2), _ptr(f2), len(k2), C.byref(tp), len(groups),
+                                                              _ptr(s1), _ptr(i1), _ptr(s2), _ptr(i2), _ptr(out),
+                                                              C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return out[: n.value].copy()
+
     # -- introspection (parity tests / profiling)
     def level_info(self, level):
         w, h, s, n = C.c_int(), C.c_int(), C.c_float(), C.c_int()

@@ -575,3 +575,68 @@ def test_other_pyramid_shapes(oracle, camera_dict, scale, levels):
     assert_struct_equal(fr.left_features.keypoints, kl, "left keypoints")
     assert_struct_equal(fr.right_features.keypoints, kr, "right keypoints")
     assert np.array_equal(fr.left_features.descriptors, dl) and np.array_equal(fr.right_features.descriptors, dr)
+
+
+# ------------------------------------------------------------------ search_for_triangulation (the last consumer)
+@pytest.mark.parametrize("seed", range(4))
+def test_search_for_triangulation(sp752, oracle, seed):
+    """triangulation.rs:401-530 and :541-658 on adversarial synthetic keyframe pairs (rivals sharing positions and
+    descriptors, map-point / stereo flags, both max_dist settings), and on real ORB features of a stereo pair."""
+    from test_oracle_differential import CAM, fundamental, tri_scene
+    from vslam_b200 import FeatureSet
+
+    rng = np.random.default_rng(400 + seed)
+    F, epi = fundamental(rng, CAM)
+    n1, n2 = [(1500, 1500), (900, 300), (200, 1100), (3, 0)][seed]
+    kp1, d1, f1, kp2, d2, f2 = tri_scene(rng, n1, n2, F)
+    for max_dist in (50, 100):
+        P = oracle.tri_params(F, epi, max_dist, CAM)
+        ref = oracle.search_for_triangulation(kp1, d1, f1, kp2, d2, f2, P)
+        got = sp752.search_for_triangulation(FeatureSet(kp1, d1), f1, FeatureSet(kp2, d2), f2, F, epi, max_dist)
+        assert np.array_equal(got, ref)
+        if seed == 0:
+            assert len(ref) > 150
+        nodes1, nodes2 = rng.integers(0, 11, n1), rng.integers(0, 11, n2)
+        nodes2[: min(n1, n2)] = nodes1[: min(n1, n2)]
+        groups = [(list(np.flatnonzero(nodes1 == g)), list(np.flatnonzero(nodes2 == g))) for g in rng.permutation(11)
+                  if (nodes1 == g).any() and (nodes2 == g).any()]
+        ref = oracle.search_for_triangulation_bow(groups, kp1, d1, f1, kp2, d2, f2, P)
+        got = sp752.search_for_triangulation(FeatureSet(kp1, d1), f1, FeatureSet(kp2, d2), f2, F, epi, max_dist, groups=groups)
+        assert np.array_equal(got, ref)
+
+
+def test_search_for_triangulation_dense_candidates_and_real_features(sp752, oracle, pairs, camera_dict):
+    """More than 64 candidates pass every gate for one feature (list overflow -> second pass), and a pure-translation
+    stereo geometry (F of a rectified pair: epipolar lines are image rows) on real ORB features."""
+    from vslam_b200 import FeatureSet
+
+    left, right = pairs(3)
+    kl, dl = oracle.detect_and_compute(left, 1200)
+    kr, dr = oracle.detect_and_compute(right, 1200)
+    cam = camera_dict
+    Kinv = np.array([[1 / cam["fx"], 0, -cam["cx"] / cam["fx"]], [0, 1 / cam["fy"], -cam["cy"] / cam["fy"]], [0, 0, 1]])
+    t = np.array([cam["baseline"], 0.0, 0.0])
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    F = Kinv.T @ tx @ Kinv
+    epi = (1e9, cam["cy"])
+    f1 = np.zeros(len(kl), np.uint8)
+    f2 = np.zeros(len(kr), np.uint8)
+    f1[::5] = 2
+    f2[::7] = 1
+    P = oracle.tri_params(F, epi, 50, cam)
+    ref = oracle.search_for_triangulation(kl, dl, f1, kr, dr, f2, P)
+    got = sp752.search_for_triangulation(FeatureSet(kl, dl), f1, FeatureSet(kr, dr), f2, F, epi, 50)
+    assert len(ref) > 300 and np.array_equal(got, ref)
+    # 200 identical keyframe-2 features on one row: every one passes the gates for every keyframe-1 feature of that row
+    n = 200
+    k2 = np.zeros(n, dtype=kl.dtype)
+    k2["x"], k2["y"], k2["class_id"] = 300.0 + 0.25 * np.arange(n, dtype=np.float32), 240.0, -1
+    d2 = np.tile(dl[0], (n, 1))
+    k1 = np.zeros(230, dtype=kl.dtype)
+    k1["x"], k1["y"], k1["class_id"] = 330.0, 240.0, -1
+    d1 = np.tile(dl[0], (230, 1))
+    z1, z2 = np.zeros(230, np.uint8), np.zeros(n, np.uint8)
+    P = oracle.tri_params(F, epi, 100, cam)
+    ref = oracle.search_for_triangulation(k1, d1, z1, k2, d2, z2, P)
+    got = sp752.search_for_triangulation(FeatureSet(k1, d1), z1, FeatureSet(k2, d2), z2, F, epi, 100)
+    assert len(ref) == n and np.array_equal(got, ref)  # first come first served: features 0..199 take 0..199 in order
