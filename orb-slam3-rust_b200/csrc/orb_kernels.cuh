@@ -264,6 +264,139 @@ __device__ __forceinline__ void sts16(unsigned a, unsigned v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v));
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// A1, tile form — same arithmetic as k_resize, different data movement.  One BLOCK owns (rs destination rows) x (a block
+// of 4-column groups) of level l: the source rows it needs (about scale * rs + 2 rows of level l-1, the column span its
+// groups read) are copied global -> shared by the bulk-copy engine (cp.async.bulk, one instruction per row, completion
+// on an mbarrier) and every lane then walks down its 4 columns reading 3 words per source row from shared memory with
+// immediate offsets.  k_resize spends ~150 instructions per lane and destination row, most of them the 64-bit address
+// arithmetic of its three per-lane cp.async per source row; here the same row costs ~40.
+// grid = (strips * ncb, n_img), block = 32 * ceil(cgb / 32); dynamic smem = resize_tile_smem_bytes().
+// ----------------------------------------------------------------------------------------------------------
+__host__ inline size_t resize_tile_smem_bytes(int src_rows_bound, int span_bound) {
+  return (size_t)src_rows_bound * (size_t)(span_bound + 16) + 32;
+}
+template <bool WIDE>  // WIDE: some item of the level reads more than 8 source bytes (scale factors near 2): byte loads
+__global__ void __launch_bounds__(288) k_resize_tile(const __grid_constant__ PyrP P, int l, int rs, int ncb, int cgb,
+                                                     const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
+                                                     uint8_t* __restrict__ pyr, const uint32_t* __restrict__ coef) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const LevelP& D = P.lv[l];
+  const LevelP& S = P.lv[l - 1];
+  const int img = blockIdx.y, tid = threadIdx.x;
+  const int strip = blockIdx.x / ncb, cb = blockIdx.x - strip * ncb;
+  const int y0 = D.pyr_y0 + strip * rs;
+  if (y0 >= D.pyr_y1) return;
+  const int rows = min(rs, D.pyr_y1 - y0);
+  const int cg_first = D.pyr_cg0 + cb * cgb;
+  const int cg_last = min(cg_first + cgb, D.pyr_cg0 + D.pyr_ncg) - 1;  // inclusive
+  if (cg_first > cg_last) return;
+  int spitch;
+  const uint8_t* src = level_ptr(P, l - 1, img, in_l, in_r, pyr, spitch);
+  const uint32_t* yc = coef + D.ycoef_off + y0;
+  const uint32_t* xc = coef + D.xcoef_off;
+  int shm1 = S.h - 1, swm1 = S.w - 1;
+  // source window of the block: rows [srow0, srow1], bytes [sx_lo, sx_hi) of every row (16-byte granules)
+  const int srow0 = (int)(yc[0] & 0xffffu);
+  const int srow1 = min((int)(yc[rows - 1] & 0xffffu) + 1, shm1);
+  const int nsrc = srow1 - srow0 + 1;
+  const int sx_lo = (int)(xc[4 * cg_first] & 0xffffu) & ~15;
+  const int sx_hi = min(((int)(xc[min(4 * cg_last + 3, D.w - 1)] & 0xffffu) + 2 + 15) & ~15, spitch);
+  const int span = sx_hi - sx_lo, SP = span + 16;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem) + 16u;  // [0, 8) holds the mbarrier
+  const unsigned mbar = sbase - 16u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)(nsrc * span)) : "memory");
+    __syncwarp();
+    for (int r = tid; r < nsrc; r += 32) {
+      const uint8_t* g = src + (size_t)(srow0 + r) * spitch + sx_lo;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       sbase + (unsigned)(r * SP)),
+                   "l"(g), "r"((unsigned)span), "r"(mbar)
+                   : "memory");
+    }
+  }
+  const int cg = cg_first + tid;
+  if (cg > cg_last) return;  // no block-wide barrier below
+
+  // ---- per-item column setup (identical to k_resize): the (at most 8) source bytes the four pixels need start at
+  //      ox[0]; three words + two funnel shifts bring them to bytes 0..7 of (v0, v1), a per-pixel PRMT selector picks
+  //      (p[ox], p[ox+1]) and DP2A forms alpha0*p0 + alpha1*p1.  Words that reach past the staged span only ever supply
+  //      bytes whose weight is 0 (the row stride leaves 16 bytes of slack).
+  int ox[4];
+  unsigned a01[4], sel[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned c = xc[min(4 * cg + k, D.w - 1)];
+    ox[k] = (int)(c & 0xffffu);
+    const unsigned a1 = c >> 16;
+    a01[k] = (256u - a1) | (a1 << 16);
+  }
+  unsigned sh = 8u * (unsigned)(ox[0] & 3);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned e = (unsigned)(ox[k] - ox[0]) & 7u;
+    sel[k] = e | (((e + 1u) & 7u) << 4) | 0x4400u;
+  }
+  // word 0 of source row `rowB + 1` (WIDE: byte sx_lo of that row)
+  unsigned arow = WIDE ? sbase - (unsigned)sx_lo : sbase + (unsigned)((ox[0] & ~3) - sx_lo);
+  asm volatile("" : "+r"(sh), "+r"(arow));
+  uint8_t* dst = pyr + (long long)img * P.pyr_img_stride + D.pyr_off + (size_t)y0 * D.pitch + 4 * cg;
+  int dpitch = D.pitch;
+  // loop invariants pinned in registers (ptxas otherwise re-derives them through indexed constant-bank loads per row)
+  asm volatile("" : "+r"(shm1), "+r"(swm1), "+r"(dpitch));
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mbar)
+          : "memory");
+  }
+  unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+  int rowB = srow0 - 1;  // hB = h(rowB)
+  unsigned yy = yc[0];
+  for (int r = 0; r < rows; ++r) {
+    const int o = (int)(yy & 0xffffu), o1 = min(o + 1, shm1);
+    unsigned b1 = yy >> 16, b0 = 256u - b1;
+    yy = yc[min(r + 1, rows - 1)];
+#pragma unroll 1
+    while (rowB < o1) {
+      ++rowB;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hA[k] = hB[k];
+      if constexpr (!WIDE) {
+        const unsigned ux = lds32<0>(arow), uy = lds32<4>(arow), uz = lds32<8>(arow);
+        const unsigned v0 = __funnelshift_r(ux, uy, sh), v1 = __funnelshift_r(uy, uz, sh);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hB[k] = __dp2a_lo(a01[k], __byte_perm(v0, v1, sel[k]), 0u);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          hB[k] = (a01[k] & 0xffffu) * lds8(arow + (unsigned)ox[k]) + (a01[k] >> 16) * lds8(arow + (unsigned)min(ox[k] + 1, swm1));
+      }
+      arow += (unsigned)SP;
+    }
+    if (o1 == o) {  // bottom replicate: both taps are the last source row (beta1 == 0): take it from hB
+      b1 = b0;
+      b0 = 0;
+    }
+    unsigned v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = b0 * hA[k] + (b1 * hB[k] + 32768u);  // < 2^24: byte 2 = result
+    const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+    *reinterpret_cast<uint32_t*>(dst) = word;
+    dst += dpitch;
+  }
+}
+
 #ifndef VSLAM_FAST_THREADS
 #define VSLAM_FAST_THREADS 192  // 6 warps: one per 128-pixel column group of a 752-wide level
 #endif

@@ -82,6 +82,17 @@ struct vslam_handle_s {
   std::vector<uint32_t> coef;
   uint32_t* d_coef = nullptr;
   int resize_rows = VSLAM_RESIZE_ROWS;  // destination rows per k_resize lane item
+  // k_resize_tile launch geometry per level (destination rows per block, column blocks, 4-column groups per column
+  // block, threads, dynamic shared memory), for big chunks [0] and for single pairs [1] (shorter strips: more blocks)
+  struct RTile { int rs, nstr, ncb, cgb, threads; size_t smem; bool wide; };
+  RTile rtile[2][VSLAM_MAX_LEVELS];
+  // VSLAM_DEBUG_SKIP (profiling aid, results become garbage): bitmask of stages NOT launched once every slot has run a few
+  // chunks (their buffers then hold valid data of earlier chunks): 1 pyramid, 2 FAST, 4 select1+Harris+select2, 8 blur,
+  // 16 BRIEF, 32 match.  The drop in step time is that stage's marginal cost inside the 4-slot pipeline.
+  int debug_skip = 0;
+  uint64_t chunks_run = 0;
+  bool resize_tile = true;   // VSLAM_RESIZE_TILE=0 selects the per-lane cp.async ring kernel (k_resize)
+  int rtile_rows = 16;       // VSLAM_RTILE_ROWS
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
   int blur_blocks_per_sm = 0;           // persistent k_blur blocks per SM (VSLAM_BLUR_BPS)
   int sm_count = 148;
@@ -160,12 +171,13 @@ struct DeviceGuard {
 
 // The dynamic shared-memory opt-in is a per-function, per-device attribute shared by every handle of the process:
 // only ever raise it, so that handles created for smaller images do not shrink what an older handle's launches need.
-enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_NFUNC };
+enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_RTILE, SMEM_RTILE_WIDE, SMEM_NFUNC };
 cudaError_t raise_smem_limit(int device, int which, size_t want) {
   static std::mutex mu;
   static size_t cur_dev[64][SMEM_NFUNC] = {{0}};
   const void* fn[SMEM_NFUNC] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
-                                (const void*)vk::k_match_rows};
+                                (const void*)vk::k_match_rows, (const void*)vk::k_resize_tile<false>,
+                                (const void*)vk::k_resize_tile<true>};
   std::lock_guard<std::mutex> lock(mu);
   size_t& cur = cur_dev[device & 63][which];
   if (want <= cur) return cudaSuccess;
@@ -345,6 +357,36 @@ int build_params(vslam_handle h) {
     linear_exact_coeffs(Sx.w, L.w, h->coef.data() + L.xcoef_off);
     linear_exact_coeffs(Sx.h, L.h, h->coef.data() + L.ycoef_off);
   }
+  // k_resize_tile geometry: exact bounds of the staged source window from the coefficient tables
+  for (int v = 0; v < 2; ++v)
+    for (int l = 1; l < P.nlevels; ++l) {
+      const LevelP& L = P.lv[l];
+      vslam_handle_s::RTile& R = h->rtile[v][l];
+      const int ph = L.pyr_y1 - L.pyr_y0;
+      R.rs = std::max(2, std::min(v == 0 ? h->rtile_rows : std::min(h->rtile_rows, 8), ph));
+      R.nstr = (ph + R.rs - 1) / R.rs;
+      R.ncb = (L.pyr_ncg + 255) / 256;
+      R.cgb = (L.pyr_ncg + R.ncb - 1) / R.ncb;
+      R.threads = 32 * ((R.cgb + 31) / 32);
+      const uint32_t* xc = h->coef.data() + L.xcoef_off;
+      const uint32_t* yc = h->coef.data() + L.ycoef_off;
+      int rows_bound = 1, span_bound = 16;
+      for (int st = 0; st < R.nstr; ++st) {
+        const int y0 = L.pyr_y0 + st * R.rs, y1 = std::min(y0 + R.rs, L.pyr_y1) - 1;
+        rows_bound = std::max(rows_bound, (int)(yc[y1] & 0xffffu) + 1 - (int)(yc[y0] & 0xffffu) + 1);
+      }
+      for (int cb = 0; cb < R.ncb; ++cb) {
+        const int c0 = L.pyr_cg0 + cb * R.cgb, c1 = std::min(c0 + R.cgb, L.pyr_cg0 + L.pyr_ncg) - 1;
+        if (c0 > c1) continue;
+        const int lo = (int)(xc[4 * c0] & 0xffffu) & ~15;
+        const int hi = ((int)(xc[std::min(4 * c1 + 3, L.w - 1)] & 0xffffu) + 2 + 15) & ~15;
+        span_bound = std::max(span_bound, hi - lo);
+      }
+      R.smem = vk::resize_tile_smem_bytes(rows_bound, span_bound);
+      R.wide = false;  // some 4-column group spans more than 8 source bytes (scale factors near 2)
+      for (int c = L.pyr_cg0; c < L.pyr_cg0 + L.pyr_ncg; ++c)
+        if ((int)(xc[std::min(4 * c + 3, L.w - 1)] & 0xffffu) + 1 - (int)(xc[std::min(4 * c, L.w - 1)] & 0xffffu) > 7) R.wide = true;
+    }
   if (const char* ev = getenv("VSLAM_FAST_SMEM_PAD")) h->fast_smem_pad = (size_t)std::max(atoi(ev), 0);
   h->fast_smem = vk::fast_smem_bytes(P.in_pitch) + h->fast_smem_pad;
   h->fast_smem_limit = h->fast_smem;
@@ -490,6 +532,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   const int nimg = frames * eyes;
   cudaStream_t st = s.stream;
   const bool prof = h->profiling;
+  const int skip = (h->chunks_run++ >= (uint64_t)(3 * h->nslot)) ? h->debug_skip : 0;
   h->last_in_l = in_l;
   h->last_in_r = in_r;
   h->last_frame_stride = frame_stride;
@@ -501,11 +544,21 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   };
   CU_TRY(h, cudaMemsetAsync(s.d_lay.hdr, 0, sizeof(ResHdr) * (size_t)frames, st));
   mark();  // 0
-  for (int l = 1; l < P.nlevels; ++l) {
-    const int ph = P.lv[l].pyr_y1 - P.lv[l].pyr_y0;
-    const int rs = h->resize_rows, nstr = (ph + rs - 1) / rs, ncg = P.lv[l].pyr_ncg;
-    dim3 grid((ncg * nstr + 127) / 128, nimg);
-    vk::k_resize<<<grid, 128, 0, st>>>(P, l, (ph + nstr - 1) / nstr, in_l, in_r, s.d_pyr, h->d_coef);
+  for (int l = 1; l < P.nlevels && !(skip & 1); ++l) {
+    if (h->resize_tile) {
+      const vslam_handle_s::RTile& R = h->rtile[nimg >= 32 ? 0 : 1][l];
+      if (R.wide)
+        vk::k_resize_tile<true><<<dim3(R.nstr * R.ncb, nimg), R.threads, R.smem, st>>>(P, l, R.rs, R.ncb, R.cgb, in_l, in_r,
+                                                                                    s.d_pyr, h->d_coef);
+      else
+        vk::k_resize_tile<false><<<dim3(R.nstr * R.ncb, nimg), R.threads, R.smem, st>>>(P, l, R.rs, R.ncb, R.cgb, in_l, in_r,
+                                                                                     s.d_pyr, h->d_coef);
+    } else {
+      const int ph = P.lv[l].pyr_y1 - P.lv[l].pyr_y0;
+      const int rs = h->resize_rows, nstr = (ph + rs - 1) / rs, ncg = P.lv[l].pyr_ncg;
+      dim3 grid((ncg * nstr + 127) / 128, nimg);
+      vk::k_resize<<<grid, 128, 0, st>>>(P, l, (ph + nstr - 1) / nstr, in_l, in_r, s.d_pyr, h->d_coef);
+    }
     h->launches++;
   }
   mark();  // 1
@@ -516,7 +569,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   auto launch_blur_forked = [&]() -> int {
     CU_TRY(h, cudaEventRecord(s.ev_pyr, st));
     CU_TRY(h, cudaStreamWaitEvent(sb, s.ev_pyr, 0));
-    vk::k_blur<<<blur_grid(h, nimg), 128, 0, sb>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
+    if (!(skip & 8)) vk::k_blur<<<blur_grid(h, nimg), 128, 0, sb>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
     h->launches++;
     CU_TRY(h, cudaEventRecord(s.ev_blur, sb));
     return VSLAM_OK;
@@ -525,7 +578,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     int rcb = launch_blur_forked();
     if (rcb != VSLAM_OK) return rcb;
   }
-  if (P.total_fast_strips > 0) {
+  if (P.total_fast_strips > 0 && !(skip & 2)) {
     dim3 grid(P.total_fast_strips, nimg);
     vk::k_fast<<<grid, vk::kFastThreads, vk::fast_smem_bytes(std::max(pitch, h->P.in_pitch)) + h->fast_smem_pad, st>>>(P, in_l, in_r, s.d_pyr,
                                                                                       s.d_strip_cnt, s.d_strip_rec);
@@ -536,7 +589,7 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     if (rcb != VSLAM_OK) return rcb;
   }
   mark();  // 2
-  {
+  if (!(skip & 4)) {
     const int cap1 = nimg >= 32 ? h->sel1_cap : std::max(h->sel1_cap, h->sel1_cap_latency);
     vk::k_select1<<<dim3(nimg, P.nlevels), 128, vk::select1_smem_bytes(cap1), st>>>(
         P, cap1, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
@@ -554,13 +607,13 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     CU_TRY(h, cudaStreamWaitEvent(st, s.ev_blur, 0));
   }
   mark();  // 4
-  {
+  if (!(skip & 16)) {
     dim3 grid((P.kp_cap + vk::kBriefWarps - 1) / vk::kBriefWarps, nimg);
     vk::k_brief<<<grid, 32 * vk::kBriefWarps, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
     h->launches++;
   }
   mark();  // 5
-  if (eyes == 2) {
+  if (eyes == 2 && !(skip & 32)) {
     if (h->match_rows_smem) {
       vk::k_match_rows<<<frames, 1024, h->match_rows_smem, st>>>(s.d_lay, h->S, h->cfg.height);
       h->launches += 1;
@@ -903,6 +956,9 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   h->sm_count = prop.multiProcessorCount;
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
+  if (const char* ev = getenv("VSLAM_DEBUG_SKIP")) h->debug_skip = atoi(ev);
+  if (const char* ev = getenv("VSLAM_RESIZE_TILE")) h->resize_tile = atoi(ev) != 0;
+  if (const char* ev = getenv("VSLAM_RTILE_ROWS")) h->rtile_rows = std::min(std::max(atoi(ev), 2), 256);
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
   if (const char* ev = getenv("VSLAM_BLUR_FULL")) h->blur_full = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_PYR_FULL")) h->pyr_full = atoi(ev) != 0;
@@ -944,7 +1000,12 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     h->match_rows_smem = (need <= lim && c.height <= 3072 && 2 * h->kp_cap >= std::min(c.height, 3072)) ? need : 0;
   }
   {
-    const size_t want[SMEM_NFUNC] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem};
+    size_t rt = 0;
+    for (int v = 0; v < 2; ++v)
+      for (int l = 1; l < h->P.nlevels; ++l) rt = std::max(rt, h->rtile[v][l].smem);
+    if (rt > lim) h->resize_tile = false;  // extreme widths x scale factors: the ring kernel has no such limit
+    const size_t want[SMEM_NFUNC] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem,
+                                     h->resize_tile ? rt : 0, h->resize_tile ? rt : 0};
     for (int i = 0; i < SMEM_NFUNC; ++i) {
       e = raise_smem_limit(c.device, i, want[i]);
       if (e != cudaSuccess) {
