@@ -211,6 +211,34 @@ int vslam_search_by_projection(vslam_handle h, const vslam_keypoint* kps, const 
                                const uint8_t* mp_desc, int M, const vslam_search_params* params, int32_t* out_idx,
                                int32_t* out_dist);
 
+/* ---- frames resident in HBM (the `frame_id` form SURVEY.md 8 b proposes) -------------------------------------
+ * The Tracker searches the frame it has just extracted (Frame::from_stereo, tracking_frame.rs:194-215, keeps the LEFT
+ * features + FeatureGrid).  vslam_frame_retain keeps exactly that on the device: the left keypoints and descriptors of
+ * frame `index` of the most recent vslam_process / vslam_process_batch* call are copied device-to-device out of the
+ * pipeline's result arrays (no PCIe traffic) and the FeatureGrid is built there; img_w x img_h is the grid extent (the
+ * reference hard-codes 752 x 480).  Must be called before the next process* call; of a multi-chunk batch only the last
+ * chunks (4 x max_batch frames) are still resident.  vslam_frame_upload makes a resident frame from host features (a
+ * keyframe that was not retained).  Searches then move only the map points' (u, v) + descriptors up and the matched
+ * indices down.  vslam_frame_release recycles the id.  The vslam_frame_* searches are bit-identical to their
+ * host-buffer forms below / above (same kernels). */
+int vslam_frame_retain(vslam_handle h, int index, double img_w, double img_h, int* frame_id);
+int vslam_frame_upload(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, double img_w, double img_h,
+                       int* frame_id);
+int vslam_frame_release(vslam_handle h, int frame_id);
+int vslam_frame_num_features(vslam_handle h, int frame_id); /* -1 for an unknown id */
+/* tracker.rs:863-923 / 1093-1158 against a resident frame; params->img_w/img_h must equal the frame's grid extent. */
+int vslam_frame_search_by_projection(vslam_handle h, int frame_id, const double* uv, const uint8_t* mp_desc, int M,
+                                     const vslam_search_params* params, int32_t* out_idx, int32_t* out_dist);
+/* FeatureGrid::get_features_in_area of a resident frame (same output convention as vslam_grid_query). */
+int vslam_frame_grid_query(vslam_handle h, int frame_id, const double* xyr, int nq, int32_t* out_start, int32_t* out_items,
+                           int out_capacity);
+/* tracker.rs:1001-1010: BFMatcher(NORM_HAMMING, true).train_match(query = keyframe descriptors, train = frame
+ * descriptors) between two resident frames; matches[n_query]. */
+int vslam_frame_bf_match_crosscheck(vslam_handle h, int query_frame_id, int train_frame_id, vslam_dmatch* matches,
+                                    int* n_matches);
+/* Device time (ms) of the k_search launch of the last vslam_frame_search_by_projection (profiling enabled only). */
+float vslam_last_search_ms(vslam_handle h);
+
 /* BFMatcher(NORM_HAMMING, crossCheck=true).train_match(query, train): matches[n_query], ascending query index. */
 int vslam_bf_match_crosscheck(vslam_handle h, const uint8_t* query, int n_query, const uint8_t* train, int n_train,
                               vslam_dmatch* matches, int* n_matches);

@@ -538,4 +538,231 @@ int vslam_search_for_triangulation_bow(vslam_handle h, const vslam_keypoint* kp1
                     g2_items, out_pairs, n_pairs);
 }
 
+// ---- frames resident in HBM for the tracking-side searches (SURVEY.md 8 b: search_by_projection(handle, frame_id, ..))
+static int retained_slot(vslam_handle h, int need, int* id_out) {
+  int id = -1;
+  for (size_t i = 0; i < h->retained.size() && id < 0; ++i)
+    if (!h->retained[i].used) id = (int)i;
+  if (id < 0) {
+    if (h->retained.size() >= 4096) return fail(h, VSLAM_ERR_OUT_OF_MEMORY, "more than 4096 retained frames");
+    h->retained.emplace_back();
+    id = (int)h->retained.size() - 1;
+  }
+  vslam_handle_s::Retained& R = h->retained[id];
+  if (R.cap < need) {
+    cudaFree(R.kp); cudaFree(R.desc); cudaFree(R.cell_start); cudaFree(R.cell_items); cudaFree(R.cell_of);
+    R = vslam_handle_s::Retained();
+    const size_t c = (size_t)std::max(need, 1);
+    if (cudaMalloc(&R.kp, c * 28) != cudaSuccess || cudaMalloc(&R.desc, c * 32) != cudaSuccess ||
+        cudaMalloc(&R.cell_start, (vk::kGridCells + 1) * 4) != cudaSuccess || cudaMalloc(&R.cell_items, c * 4) != cudaSuccess ||
+        cudaMalloc(&R.cell_of, c * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, VSLAM_ERR_OUT_OF_MEMORY, "retained frame allocation failed");
+    }
+    R.cap = (int)c;
+  }
+  *id_out = id;
+  return VSLAM_OK;
+}
+
+static vslam_handle_s::Retained* retained_get(vslam_handle h, int id) {
+  if (id < 0 || id >= (int)h->retained.size() || !h->retained[id].used) return nullptr;
+  return &h->retained[id];
+}
+
+int vslam_frame_retain(vslam_handle h, int index, double img_w, double img_h, int* frame_id) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (!frame_id || !(img_w > 0.0) || !(img_h > 0.0)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad argument");
+  *frame_id = -1;
+  Slot* src = nullptr;
+  for (int k = 0; k < h->nslot && !src; ++k) {
+    Slot& s = h->slots[k];
+    if (!s.busy && s.frames > 0 && s.serial == h->call_serial && h->call_serial > 0 && index >= s.first_frame &&
+        index < s.first_frame + s.frames)
+      src = &s;
+  }
+  if (!src)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT,
+                "frame %d of the last process call is no longer resident (only the last %d chunks of a batch are)", index,
+                h->nslot);
+  const int f = index - src->first_frame;
+  const ResHdr& hd = src->h_lay.hdr[f];
+  if (hd.status != VSLAM_OK) return fail(h, hd.status, "frame %d did not complete (status %d)", index, hd.status);
+  const int n = hd.n_kp[0];
+  DEVICE_SCOPE(h);
+  int id;
+  int rc = retained_slot(h, std::max(n, h->kp_cap), &id);
+  if (rc) return rc;
+  vslam_handle_s::Retained& R = h->retained[id];
+  cudaStream_t st = h->slots[0].stream;
+  const FrameLayout& D = src->d_lay;
+  if (n > 0) {
+    CU_TRY(h, cudaMemcpyAsync(R.kp, D.kp[0] + (size_t)f * D.kp_stride, (size_t)n * 28, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(R.desc, D.desc[0] + (size_t)f * D.desc_stride, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  vk::k_grid_build<<<1, 1024, 0, st>>>(R.kp, n, grid_params(img_w, img_h), R.cell_start, R.cell_items, R.cell_of);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  R.n = n;
+  R.img_w = img_w;
+  R.img_h = img_h;
+  R.used = true;
+  *frame_id = id;
+  return VSLAM_OK;
+}
+
+int vslam_frame_upload(vslam_handle h, const vslam_keypoint* kps, const uint8_t* desc, int n, double img_w, double img_h,
+                       int* frame_id) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (!frame_id || n < 0 || n > 65535 || (n > 0 && (!kps || !desc)) || !(img_w > 0.0) || !(img_h > 0.0))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad argument");
+  *frame_id = -1;
+  DEVICE_SCOPE(h);
+  int id;
+  int rc = retained_slot(h, std::max(n, h->kp_cap), &id);
+  if (rc) return rc;
+  vslam_handle_s::Retained& R = h->retained[id];
+  cudaStream_t st = h->slots[0].stream;
+  if (n > 0) {
+    CU_TRY(h, cudaMemcpyAsync(R.kp, kps, (size_t)n * 28, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(R.desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  }
+  vk::k_grid_build<<<1, 1024, 0, st>>>(R.kp, n, grid_params(img_w, img_h), R.cell_start, R.cell_items, R.cell_of);
+  h->launches++;
+  CU_TRY(h, cudaStreamSynchronize(st));  // the caller's arrays may go away
+  R.n = n;
+  R.img_w = img_w;
+  R.img_h = img_h;
+  R.used = true;
+  *frame_id = id;
+  return VSLAM_OK;
+}
+
+int vslam_frame_release(vslam_handle h, int frame_id) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  vslam_handle_s::Retained* R = retained_get(h, frame_id);
+  if (!R) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown frame id %d", frame_id);
+  R->used = false;  // the device arrays are kept for the next retain; stream order protects pending searches
+  return VSLAM_OK;
+}
+
+int vslam_frame_num_features(vslam_handle h, int frame_id) {
+  vslam_handle_s::Retained* R = h ? retained_get(h, frame_id) : nullptr;
+  return R ? R->n : -1;
+}
+
+int vslam_frame_search_by_projection(vslam_handle h, int frame_id, const double* uv, const uint8_t* mp_desc, int M,
+                                     const vslam_search_params* sp, int32_t* out_idx, int32_t* out_dist) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  vslam_handle_s::Retained* R = retained_get(h, frame_id);
+  if (!R) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown frame id %d", frame_id);
+  if (M < 0 || !sp || (M > 0 && (!uv || !mp_desc || !out_idx || !out_dist)))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (sp->mode != VSLAM_SEARCH_LOCAL_MAP && sp->mode != VSLAM_SEARCH_MOTION_MODEL)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown search mode %d", sp->mode);
+  if (sp->th_high > 1024) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "th_high out of range");
+  if (sp->img_w != R->img_w || sp->img_h != R->img_h)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "search grid extent %gx%g differs from the retained frame's %gx%g", sp->img_w,
+                sp->img_h, R->img_w, R->img_h);
+  if (M == 0) return VSLAM_OK;
+  DEVICE_SCOPE(h);
+  cudaStream_t st = h->slots[0].stream;
+  const size_t mm = (size_t)M;
+  int rc = arena_begin(h, pad256(mm * 16) + pad256(mm * 32) + 2 * pad256(mm * 4));
+  if (rc) return rc;
+  double* duv = arena_take<double>(h, mm * 2);
+  unsigned* dmd = arena_take<unsigned>(h, mm * 8);
+  int* doi = arena_take<int>(h, mm);
+  int* dod = arena_take<int>(h, mm);
+  vk::SearchP S;
+  S.mode = sp->mode;
+  S.radius = sp->radius;
+  S.th_high = sp->th_high;
+  S.nn_ratio = sp->nn_ratio;
+  S.bound_w = sp->bound_w;
+  S.bound_h = sp->bound_h;
+  CU_TRY(h, cudaMemcpyAsync(duv, uv, mm * 16, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(dmd, mp_desc, mm * 32, cudaMemcpyHostToDevice, st));
+  if (h->profiling) cudaEventRecord(h->ev[0], st);
+  vk::k_search<<<(M * 32 + 255) / 256, 256, 0, st>>>(R->cell_start, R->cell_items, R->desc, grid_params(R->img_w, R->img_h), S, duv,
+                                                      dmd, M, doi, dod);
+  h->launches++;
+  if (h->profiling) cudaEventRecord(h->ev[1], st);
+  CU_TRY(h, cudaMemcpyAsync(out_idx, doi, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out_dist, dod, mm * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  if (h->profiling) cudaEventElapsedTime(&h->last_search_ms, h->ev[0], h->ev[1]);
+  return VSLAM_OK;
+}
+
+int vslam_frame_grid_query(vslam_handle h, int frame_id, const double* xyr, int nq, int32_t* out_start, int32_t* out_items,
+                           int out_capacity) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  vslam_handle_s::Retained* R = retained_get(h, frame_id);
+  if (!R) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown frame id %d", frame_id);
+  if (nq < 0 || !out_start || (nq > 0 && !xyr) || out_capacity < 0 || (out_capacity > 0 && !out_items))
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  DEVICE_SCOPE(h);
+  cudaStream_t st = h->slots[0].stream;
+  const size_t qq = (size_t)std::max(nq, 1), oc = (size_t)std::max(out_capacity, 1);
+  int rc = arena_begin(h, pad256(qq * 24) + 2 * pad256((qq + 1) * 4) + pad256(oc * 4));
+  if (rc) return rc;
+  double* dq = arena_take<double>(h, qq * 3);
+  int* dcnt = arena_take<int>(h, qq + 1);
+  int* dstart = arena_take<int>(h, qq + 1);
+  int* dout = arena_take<int>(h, oc);
+  const vk::GridP G = grid_params(R->img_w, R->img_h);
+  if (nq > 0) {
+    CU_TRY(h, cudaMemcpyAsync(dq, xyr, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+    vk::k_grid_count<<<(nq + 255) / 256, 256, 0, st>>>(R->cell_start, G, dq, nq, dcnt);
+    h->launches++;
+  }
+  vk::k_scan_counts<<<1, 1024, 0, st>>>(dcnt, nq, dstart);
+  h->launches++;
+  if (nq > 0) {
+    vk::k_grid_fill<<<(nq * 32 + 255) / 256, 256, 0, st>>>(R->cell_start, R->cell_items, G, dq, nq, dstart, dout, out_capacity);
+    h->launches++;
+  }
+  CU_TRY(h, cudaMemcpyAsync(out_start, dstart, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  const int total = out_start[nq];
+  if (total > out_capacity) return fail(h, VSLAM_ERR_CAPACITY, "grid query needs %d items, capacity %d", total, out_capacity);
+  if (total > 0) CU_TRY(h, cudaMemcpy(out_items, dout, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_frame_bf_match_crosscheck(vslam_handle h, int query_frame_id, int train_frame_id, vslam_dmatch* matches,
+                                    int* n_matches) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  vslam_handle_s::Retained* Q = retained_get(h, query_frame_id);
+  vslam_handle_s::Retained* T = retained_get(h, train_frame_id);
+  if (!Q || !T) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "unknown frame id");
+  if (!n_matches || (Q->n > 0 && !matches)) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  *n_matches = 0;
+  if (Q->n == 0 || T->n == 0) return VSLAM_OK;
+  DEVICE_SCOPE(h);
+  cudaStream_t st = h->slots[0].stream;
+  const size_t nq = (size_t)Q->n, nt = (size_t)T->n;
+  int rc = arena_begin(h, 2 * pad256(nq * 4) + 2 * pad256(nt * 4) + pad256(nq * 16) + 512);
+  if (rc) return rc;
+  int* sidx = arena_take<int>(h, nq);
+  int* sdist = arena_take<int>(h, nq);
+  int* tidx = arena_take<int>(h, nt);
+  int* tdist = arena_take<int>(h, nt);
+  int4* dm = arena_take<int4>(h, nq);
+  int* dn = arena_take<int>(h, 1);
+  vk::k_nearest<<<(Q->n + 7) / 8, 256, 0, st>>>(Q->desc, Q->n, T->desc, T->n, sidx, sdist);
+  vk::k_nearest<<<(T->n + 7) / 8, 256, 0, st>>>(T->desc, T->n, Q->desc, Q->n, tidx, tdist);
+  vk::k_cross<<<1, 256, 0, st>>>(sidx, sdist, tidx, Q->n, dm, dn);
+  h->launches += 3;
+  int nm = 0;
+  CU_TRY(h, cudaMemcpyAsync(&nm, dn, 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  *n_matches = nm;
+  if (nm > 0) CU_TRY(h, cudaMemcpy(matches, dm, (size_t)nm * 16, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+float vslam_last_search_ms(vslam_handle h) { return h ? h->last_search_ms : 0.f; }
+
 }  // extern "C"

@@ -68,6 +68,7 @@ struct Slot {
   bool want_results = false;
   int rows_copied = 0;             // rows of every result array the chunk's D2H copies carried
   int eyes = 2;
+  uint64_t serial = 0;             // vslam_handle_s::call_serial of the call whose chunk the slot holds
 };
 
 }  // namespace
@@ -128,6 +129,23 @@ struct vslam_handle_s {
   const uint8_t* last_in_r = nullptr;
   long long last_frame_stride = 0;
   int last_pitch = 0, last_eyes = 2;
+  // frames kept in HBM for the tracking-side searches (vslam_frame_*): LEFT keypoints + descriptors + CSR FeatureGrid
+  struct Retained {
+    unsigned char* kp = nullptr;
+    unsigned* desc = nullptr;
+    int *cell_start = nullptr, *cell_items = nullptr, *cell_of = nullptr;
+    int n = 0, cap = 0;
+    bool used = false;
+    double img_w = 0, img_h = 0;
+  };
+  std::vector<Retained> retained;
+  uint64_t call_serial = 0;   // incremented by every process* call; slots remember the call that filled them
+  // single-pair latency path (vslam_process): H2D, the 14-launch chain with its forked blur stream and the D2H copies of
+  // one stereo pair captured once into a CUDA graph over slot 0's fixed staging buffers (VSLAM_GRAPH=0 disables)
+  bool use_graph = true;
+  cudaGraphExec_t pair_graph = nullptr;
+  uint64_t pair_graph_kernels = 0;
+  float last_search_ms = 0.f;
   unsigned char* arena_base = nullptr;  // grow-only device scratch of the stand-alone entry points
   size_t arena_cap = 0, arena_used = 0;
 };
@@ -758,6 +776,26 @@ bool outputs_are_direct(vslam_handle h, const vslam_frame_out* o, int frames) {
          is_pinned_host(a.points_valid);
 }
 
+// D2H of one chunk's result arrays: one 2-D copy per array, frame f's rows [0, rows) of the [frames][capacity] arrays.
+int enqueue_result_copies(vslam_handle h, Slot& s, int frames, int eyes, void* const dst[7]) {
+  const FrameLayout& D = s.d_lay;
+  const void* src[7] = {D.kp[0], D.kp[1], D.desc[0], D.desc[1], D.matches, D.pts, D.valid};
+  const size_t pitchb[7] = {(size_t)D.kp_stride,      (size_t)D.kp_stride,  (size_t)D.desc_stride, (size_t)D.desc_stride,
+                            (size_t)D.matches_stride, (size_t)D.pts_stride, (size_t)D.valid_stride};
+  const size_t elem[7] = {28, 28, 32, 32, 16, 24, 1};
+  // rows = n_features: cv::ORB returns exactly that many keypoints unless responses tie at the cut (retire_slot
+  // fetches the extra rows of such a frame), and matches / points never outnumber the left keypoints — the
+  // capacity - n_features tail rows (11 % of every array at the default capacity) never cross PCIe.
+  const int rows = std::min(h->kp_cap, h->cfg.n_features);
+  s.rows_copied = rows;
+  for (int a = 0; a < 7; ++a) {
+    if (eyes == 1 && (a == 1 || a == 3 || a >= 4)) continue;
+    CU_TRY(h, cudaMemcpy2DAsync(dst[a], pitchb[a], src[a], pitchb[a], (size_t)rows * elem[a], (size_t)frames,
+                                cudaMemcpyDeviceToHost, s.stream));
+  }
+  return VSLAM_OK;
+}
+
 // After a CUDA failure inside run_batch: wait for everything in flight (copies may still be writing into the caller's
 // arrays) and forget the chunks, so that the next call starts from idle slots.
 void drain_slots(vslam_handle h) {
@@ -847,26 +885,14 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
                       s.direct_out ? (void*)o.desc_left : (void*)M.desc[0],  s.direct_out ? (void*)o.desc_right : (void*)M.desc[1],
                       s.direct_out ? (void*)o.matches : (void*)M.matches,    s.direct_out ? (void*)o.points_cam : (void*)M.pts,
                       s.direct_out ? (void*)o.points_valid : (void*)M.valid};
-      const void* src[7] = {D.kp[0], D.kp[1], D.desc[0], D.desc[1], D.matches, D.pts, D.valid};
-      const size_t pitchb[7] = {(size_t)D.kp_stride,      (size_t)D.kp_stride,  (size_t)D.desc_stride, (size_t)D.desc_stride,
-                                (size_t)D.matches_stride, (size_t)D.pts_stride, (size_t)D.valid_stride};
-      const size_t elem[7] = {28, 28, 32, 32, 16, 24, 1};
-      // One 2-D copy per array per chunk: frame f's rows [0, rows) of [frames][capacity] arrays.  rows = n_features:
-      // cv::ORB returns exactly that many keypoints unless responses tie at the cut (retire_slot fetches the extra
-      // rows of such a frame), and matches / points never outnumber the left keypoints — the capacity - n_features
-      // tail rows (11 % of every array at the default capacity) never cross PCIe.
-      const int rows = std::min(h->kp_cap, h->cfg.n_features);
-      s.rows_copied = rows;
-      for (int a = 0; a < 7; ++a) {
-        if (eyes == 1 && (a == 1 || a == 3 || a >= 4)) continue;
-        CU_TRY(h, cudaMemcpy2DAsync(dst[a], pitchb[a], src[a], pitchb[a], (size_t)rows * elem[a], fr, cudaMemcpyDeviceToHost,
-                                    s.stream));
-      }
+      rc = enqueue_result_copies(h, s, frames, eyes, dst);
+      if (rc != VSLAM_OK) return rc;
     }
     CU_TRY(h, cudaEventRecord(s.done, s.stream));
     s.busy = true;
     s.frames = frames;
     s.first_frame = f0;
+    s.serial = h->call_serial;
     h->last_slot = chunk % h->nslot;
     h->last_frames = frames;
   }
@@ -885,11 +911,93 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
   return VSLAM_OK;
 }
 
+// vslam_process, latency form: one stereo pair through a CUDA graph captured once per handle.  Everything the graph
+// touches has a fixed address (slot 0: pinned input staging, device buffers, pinned result mirror), so the per-call
+// work is: stage the two images, one cudaGraphLaunch, one synchronize, unpack.
+int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
+                     uint64_t ts, vslam_frame_out* out) {
+  DEVICE_SCOPE(h);
+  Slot& s = h->slots[0];
+  const PyrP& P = h->P;
+  const int W = h->cfg.width, H = h->cfg.height;
+  const size_t ib = h->in_img_bytes;
+  int first_error = VSLAM_OK;
+  int rc = retire_slot(h, s, nullptr, nullptr, &first_error);  // never busy here; keeps the invariant explicit
+  if (rc != VSLAM_OK) return rc;
+  h->call_serial++;
+  for (int e = 0; e < 2; ++e) {
+    const uint8_t* src = e ? right : left;
+    const size_t st = e ? rstride : lstride;
+    uint8_t* dst = s.h_in + (size_t)e * ib;
+    if (st == (size_t)P.in_pitch) memcpy(dst, src, ib);
+    else
+      for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * P.in_pitch, src + (size_t)y * st, (size_t)W);
+  }
+  if (!h->pair_graph) {
+    cudaGraph_t g = nullptr;
+    const uint64_t l0 = h->launches;
+    CU_TRY(h, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    rc = VSLAM_OK;
+    do {
+      if (cudaMemcpyAsync(s.d_in, s.h_in, 2 * ib, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { rc = VSLAM_ERR_CUDA; break; }
+      rc = enqueue_chunk(h, s, 1, 2, s.d_in, s.d_in + ib, (long long)ib, P.in_pitch);
+      if (rc != VSLAM_OK) break;
+      if (cudaMemcpyAsync(s.h_lay.hdr, s.d_lay.hdr, sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) { rc = VSLAM_ERR_CUDA; break; }
+      const FrameLayout& M = s.h_lay;
+      void* dst[7] = {M.kp[0], M.kp[1], M.desc[0], M.desc[1], M.matches, M.pts, M.valid};
+      rc = enqueue_result_copies(h, s, 1, 2, dst);
+    } while (false);
+    cudaError_t ce = cudaStreamEndCapture(s.stream, &g);
+    if (rc != VSLAM_OK || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      h->use_graph = false;  // fall back to plain stream launches for this handle (same kernels)
+      return rc != VSLAM_OK ? rc : fail(h, VSLAM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&h->pair_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) {
+      h->pair_graph = nullptr;
+      h->use_graph = false;
+      return fail(h, VSLAM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    }
+    h->pair_graph_kernels = h->launches - l0;
+    h->launches = l0;
+  }
+  CU_TRY(h, cudaEventRecord(h->ev_batch[0], s.stream));
+  CU_TRY(h, cudaGraphLaunch(h->pair_graph, s.stream));
+  CU_TRY(h, cudaEventRecord(h->ev_batch[1], s.stream));
+  CU_TRY(h, cudaEventRecord(s.done, s.stream));
+  h->launches += h->pair_graph_kernels;
+  s.busy = true;
+  s.frames = 1;
+  s.first_frame = 0;
+  s.serial = h->call_serial;
+  s.want_results = true;
+  s.direct_out = false;
+  s.eyes = 2;
+  h->last_slot = 0;
+  h->last_frames = 1;
+  h->last_in_l = s.d_in;
+  h->last_in_r = s.d_in + ib;
+  h->last_frame_stride = (long long)ib;
+  h->last_pitch = P.in_pitch;
+  h->last_eyes = 2;
+  rc = retire_slot(h, s, out, &ts, &first_error);
+  if (rc != VSLAM_OK) {
+    drain_slots(h);
+    return rc;
+  }
+  cudaEventElapsedTime(&h->last_batch_ms, h->ev_batch[0], h->ev_batch[1]);
+  return first_error;
+}
+
 int run_batch(vslam_handle h, int n, int eyes, const uint8_t* const* left, const uint8_t* const* right, size_t stride,
               const uint8_t* left_dev, const uint8_t* right_dev, size_t image_stride, size_t row_stride,
               const uint64_t* ts, vslam_frame_out* outs, bool device_input) {
   if (n <= 0) return VSLAM_OK;
   DEVICE_SCOPE(h);
+  h->call_serial++;
   int first_error = VSLAM_OK;
   const int rc = run_batch_impl(h, n, eyes, left, right, stride, left_dev, right_dev, image_stride, row_stride, ts, outs,
                                 device_input, &first_error);
@@ -957,6 +1065,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_DEBUG_SKIP")) h->debug_skip = atoi(ev);
+  if (const char* ev = getenv("VSLAM_GRAPH")) h->use_graph = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_RESIZE_TILE")) h->resize_tile = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_RTILE_ROWS")) h->rtile_rows = std::min(std::max(atoi(ev), 2), 256);
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
@@ -1032,8 +1141,12 @@ void vslam_destroy(vslam_handle h) {
   if (!h) return;
   DeviceGuard guard(h->cfg.device);
   for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
+  if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
   cudaFree(h->d_coef);
   cudaFree(h->arena_base);
+  for (auto& r : h->retained) {
+    cudaFree(r.kp); cudaFree(r.desc); cudaFree(r.cell_start); cudaFree(r.cell_items); cudaFree(r.cell_of);
+  }
   cudaFree(h->voc_desc); cudaFree(h->voc_child_begin); cudaFree(h->voc_child_ids); cudaFree(h->voc_parent); cudaFree(h->voc_word);
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1048,6 +1161,7 @@ int vslam_process(vslam_handle h, const uint8_t* left, size_t left_stride, const
   if (!left || !right || !out) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (left_stride < (size_t)h->cfg.width || right_stride < (size_t)h->cfg.width)
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "row stride smaller than the image width");
+  if (h->use_graph && !h->profiling) return run_single_graph(h, left, left_stride, right, right_stride, timestamp_ns, out);
   if (left_stride != right_stride) {
     // stage the right image with the left stride semantics by processing through the generic path twice is
     // wasteful; copy rows into the pinned staging instead (handled by run_batch via per-image stride)

@@ -69,6 +69,9 @@ SYMBOLS = [
     "vslam_debug_fast_corners", "vslam_kernel_launches", "vslam_set_profiling", "vslam_last_stage_ms",
     "vslam_last_batch_ms", "vslam_fuse_search", "vslam_distinctive_descriptors", "vslam_vocab_upload",
     "vslam_bow_quantize", "vslam_search_for_triangulation", "vslam_search_for_triangulation_bow",
+    "vslam_frame_retain", "vslam_frame_upload", "vslam_frame_release", "vslam_frame_num_features",
+    "vslam_frame_search_by_projection", "vslam_frame_grid_query", "vslam_frame_bf_match_crosscheck",
+    "vslam_last_search_ms",
 ]
 
 _lib = None
@@ -110,6 +113,15 @@ def lib():
                                                      C.POINTER(i32)]
         L.vslam_search_for_triangulation_bow.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, C.POINTER(TriParams), i32,
                                                          vp, vp, vp, vp, vp, C.POINTER(i32)]
+        L.vslam_frame_retain.argtypes = [vp, i32, C.c_double, C.c_double, C.POINTER(i32)]
+        L.vslam_frame_upload.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.POINTER(i32)]
+        L.vslam_frame_release.argtypes = [vp, i32]
+        L.vslam_frame_num_features.argtypes = [vp, i32]
+        L.vslam_frame_search_by_projection.argtypes = [vp, i32, vp, vp, i32, C.POINTER(SearchParams), vp, vp]
+        L.vslam_frame_grid_query.argtypes = [vp, i32, vp, i32, vp, vp, i32]
+        L.vslam_frame_bf_match_crosscheck.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
+        L.vslam_last_search_ms.argtypes = [vp]
+        L.vslam_last_search_ms.restype = C.c_float
         L.vslam_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i32)]
         L.vslam_debug_level_image.argtypes = [vp, i32, i32, i32, vp, sz]
         L.vslam_debug_fast_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]

@@ -309,6 +309,72 @@ class StereoProcessor:
             self._raise(rc)
         return idx[:M], dist[:M]
 
+    # -- frames resident in HBM: Frame::from_stereo (tracking_frame.rs:194-215) without a PCIe round trip of the features
+    def frame_retain(self, index=0, img_w=752.0, img_h=480.0) -> int:
+        """Keeps the left features + FeatureGrid of frame `index` of the last process* call on the device -> frame id."""
+        fid = C.c_int(-1)
+        rc = self._lib.vslam_frame_retain(self._h, int(index), float(img_w), float(img_h), C.byref(fid))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return fid.value
+
+    def frame_upload(self, features: FeatureSet, img_w=752.0, img_h=480.0) -> int:
+        kp = np.ascontiguousarray(features.keypoints, dtype=KP_DTYPE)
+        d = np.ascontiguousarray(features.descriptors, dtype=np.uint8).reshape(-1, 32)
+        fid = C.c_int(-1)
+        rc = self._lib.vslam_frame_upload(self._h, _ptr(kp), _ptr(d), len(kp), float(img_w), float(img_h), C.byref(fid))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return fid.value
+
+    def frame_release(self, frame_id):
+        rc = self._lib.vslam_frame_release(self._h, int(frame_id))
+        if rc != _abi.OK:
+            self._raise(rc)
+
+    def frame_num_features(self, frame_id):
+        return int(self._lib.vslam_frame_num_features(self._h, int(frame_id)))
+
+    def frame_search_by_projection(self, frame_id, uv, mp_desc, mode=_abi.SEARCH_LOCAL_MAP, radius=15.0, th_high=TH_HIGH,
+                                   nn_ratio=NN_RATIO, img_w=752.0, img_h=480.0, bound_w=None, bound_h=None):
+        """tracker.rs:863-923 / 1093-1158 against a resident frame: only (u, v) + map-point descriptors go up."""
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        md = np.ascontiguousarray(mp_desc, dtype=np.uint8).reshape(-1, 32)
+        M = len(uv)
+        sp = _abi.SearchParams(int(mode), float(radius), int(th_high), float(nn_ratio), float(img_w), float(img_h),
+                               float(2.0 * self.camera.cx if bound_w is None else bound_w),
+                               float(2.0 * self.camera.cy if bound_h is None else bound_h))
+        idx = np.full(max(M, 1), -1, dtype=np.int32)
+        dist = np.full(max(M, 1), -1, dtype=np.int32)
+        rc = self._lib.vslam_frame_search_by_projection(self._h, int(frame_id), _ptr(uv), _ptr(md), M, C.byref(sp),
+                                                        _ptr(idx), _ptr(dist))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return idx[:M], dist[:M]
+
+    def frame_grid_query(self, frame_id, xyr):
+        q = np.ascontiguousarray(xyr, dtype=np.float64).reshape(-1, 3)
+        n = max(self.frame_num_features(frame_id), 0)
+        cap = max(n * max(len(q), 1), 1)
+        start = np.zeros(len(q) + 1, dtype=np.int32)
+        items = np.zeros(cap, dtype=np.int32)
+        rc = self._lib.vslam_frame_grid_query(self._h, int(frame_id), _ptr(q), len(q), _ptr(start), _ptr(items), cap)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return [items[start[i]: start[i + 1]].copy() for i in range(len(q))]
+
+    def frame_bf_match_crosscheck(self, query_frame_id, train_frame_id):
+        nq = max(self.frame_num_features(query_frame_id), 1)
+        m = np.zeros(nq, dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        rc = self._lib.vslam_frame_bf_match_crosscheck(self._h, int(query_frame_id), int(train_frame_id), _ptr(m), C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return m[: n.value].copy()
+
+    def last_search_ms(self):
+        return float(self._lib.vslam_last_search_ms(self._h))
+
     # -- BFMatcher(NORM_HAMMING, crossCheck=true) (tracker.rs:1001-1010)
     def bf_match_crosscheck(self, query, train):
         q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)

@@ -39,12 +39,14 @@ def _blur(img: torch.Tensor, sigma: float) -> torch.Tensor:
     return img
 
 
-def make_stereo_pair(seed: int, width: int = 752, height: int = 480, device="cpu"):
-    """Returns (left, right) uint8 tensors of shape [height, width] on `device`."""
+def make_stereo_pair(seed: int, width: int = 752, height: int = 480, device="cpu", extra: int = 0, offsets=(0,)):
+    """Returns (left, right) uint8 tensors of shape [height, width] on `device`.
+    extra / offsets (config 4): the canvas is `extra` px wider and one pair is cut per offset (camera translated
+    `offset` px to the right, independent sensor noise per frame): returns ([n, H, W], [n, H, W])."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(1_000_003 * int(seed) + 12345)
-    cw = width + _MARGIN
+    cw = width + _MARGIN + int(extra)
     scale = width / 752.0  # config 3 (1280x720) scales the scene with the image
     canvas = torch.zeros(1, 1, height, cw, dtype=torch.float32, device=dev)
     for sigma, amp in ((1.0, 30.0), (3.0, 50.0), (9.0, 60.0)):
@@ -63,19 +65,33 @@ def make_stereo_pair(seed: int, width: int = 752, height: int = 480, device="cpu
         y0 = int(rng.integers(0, height - rh))
         canvas[y0 : y0 + int(rh), x0 : x0 + int(rw)] = float(rng.integers(0, 256))
 
-    left = canvas[:, _CROP_X : _CROP_X + width]
-    right = torch.empty_like(left)
-    bands = len(_DISPARITIES)
-    for i, d in enumerate(_DISPARITIES):
-        d = int(round(d * scale))
-        y0 = (height * i) // bands
-        y1 = (height * (i + 1)) // bands
-        right[y0:y1] = canvas[y0:y1, _CROP_X + d : _CROP_X + d + width]
-    nl = torch.rand(height, width, generator=g, device=dev) * 6.0 - 3.0
-    nr = torch.rand(height, width, generator=g, device=dev) * 6.0 - 3.0
-    left = (left + nl).round().clamp(0, 255).to(torch.uint8)
-    right = (right + nr).round().clamp(0, 255).to(torch.uint8)
-    return left.contiguous(), right.contiguous()
+    def cut(off):
+        x0 = _CROP_X + int(off)
+        left = canvas[:, x0 : x0 + width]
+        right = torch.empty_like(left)
+        bands = len(_DISPARITIES)
+        for i, d in enumerate(_DISPARITIES):
+            d = int(round(d * scale))
+            y0 = (height * i) // bands
+            y1 = (height * (i + 1)) // bands
+            right[y0:y1] = canvas[y0:y1, x0 + d : x0 + d + width]
+        nl = torch.rand(height, width, generator=g, device=dev) * 6.0 - 3.0
+        nr = torch.rand(height, width, generator=g, device=dev) * 6.0 - 3.0
+        left = (left + nl).round().clamp(0, 255).to(torch.uint8)
+        right = (right + nr).round().clamp(0, 255).to(torch.uint8)
+        return left.contiguous(), right.contiguous()
+
+    if extra == 0 and tuple(offsets) == (0,):
+        return cut(0)
+    pairs = [cut(o) for o in offsets]
+    return torch.stack([p[0] for p in pairs]), torch.stack([p[1] for p in pairs])
+
+
+def make_sequence(seed: int, n_frames: int, step_px: int = 2, width: int = 752, height: int = 480, device="cpu"):
+    """BASELINE config 4: one scene, the camera translated `step_px` px per frame (image content moves LEFT by step_px per
+    frame: a point seen at (u, v) in frame 0 is at (u - step_px * t, v) in frame t).  -> ([n, H, W], [n, H, W]) uint8."""
+    return make_stereo_pair(seed, width, height, device, extra=step_px * (n_frames - 1) + 2,
+                            offsets=[step_px * t for t in range(n_frames)])
 
 
 def make_stereo_batch(seeds, width: int = 752, height: int = 480, device="cpu"):

@@ -640,3 +640,64 @@ def test_search_for_triangulation_dense_candidates_and_real_features(sp752, orac
     ref = oracle.search_for_triangulation(k1, d1, z1, k2, d2, z2, P)
     got = sp752.search_for_triangulation(FeatureSet(k1, d1), z1, FeatureSet(k2, d2), z2, F, epi, 100)
     assert len(ref) == n and np.array_equal(got, ref)  # first come first served: features 0..199 take 0..199 in order
+
+
+# ------------------------------------------------------------------ frames resident in HBM (SURVEY 8 b: frame_id searches)
+def test_resident_frame_searches(sp752, oracle, camera_dict):
+    """vslam_frame_retain / _upload + the frame_id forms of FeatureGrid queries, both projection searches and the ref-KF
+    BFMatcher, on a short sequence: compared per map point (trap 11) with the oracle and with the host-buffer entry points."""
+    from vslam_b200 import VslamError, synth
+
+    seqL, seqR = synth.make_sequence(60, 4)
+    seqL, seqR = seqL.numpy(), seqR.numpy()
+    f0 = sp752.process(seqL[0], seqR[0])
+    kf = sp752.frame_retain(0)
+    assert sp752.frame_num_features(kf) == len(f0.left_features.keypoints)
+    good = np.flatnonzero(f0.points_valid)
+    mp_desc = f0.left_features.descriptors[good]
+    rng = np.random.default_rng(60)
+    ids = [kf]
+    for t in (1, 2, 3):
+        fr = sp752.process(seqL[t], seqR[t])
+        fid = sp752.frame_retain(0)
+        ids.append(fid)
+        kl, dl = fr.left_features.keypoints, fr.left_features.descriptors
+        uv = np.c_[f0.left_features.keypoints["x"][good].astype(np.float64) - 2 * t,
+                   f0.left_features.keypoints["y"][good].astype(np.float64)]
+        uv[:8] += rng.uniform(-900, 900, (8, 2))  # out-of-image projections: negative-cell wrap / empty ranges
+        for mode in (0, 1):
+            gi, gd = sp752.frame_search_by_projection(fid, uv, mp_desc, mode=mode)
+            hi, hd = sp752.search_by_projection(fr.left_features, uv, mp_desc, mode=mode)
+            oi, od = oracle.search_by_projection(kl, dl, uv, mp_desc, mode, bound_w=2 * sp752.camera.cx,
+                                                 bound_h=2 * sp752.camera.cy)
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od) and np.array_equal(hi, oi)
+            assert (gi >= 0).sum() > 300
+        q = np.c_[rng.uniform(-60, 820, 64), rng.uniform(-60, 540, 64), np.full(64, 15.0)]
+        cs, items = oracle.grid_build(kl)
+        for a, (x, y, r) in zip(sp752.frame_grid_query(fid, q), q):
+            assert np.array_equal(a, oracle.grid_query(cs, items, x, y, r))
+        assert_struct_equal(sp752.frame_bf_match_crosscheck(kf, fid),
+                            oracle.bf_match_crosscheck(f0.left_features.descriptors, dl), "ref-KF BFMatcher")
+    # an uploaded keyframe behaves like a retained one
+    up = sp752.frame_upload(f0.left_features)
+    assert_struct_equal(sp752.frame_bf_match_crosscheck(up, ids[-1]), sp752.frame_bf_match_crosscheck(kf, ids[-1]), "upload")
+    gi, _ = sp752.frame_search_by_projection(up, uv, mp_desc)
+    oi, _ = oracle.search_by_projection(f0.left_features.keypoints, f0.left_features.descriptors, uv, mp_desc, 0)
+    assert np.array_equal(gi, oi)
+    # ids are recycled; stale / unknown ids and a mismatching grid extent fail loudly
+    sp752.frame_release(ids[1])
+    with pytest.raises(VslamError):
+        sp752.frame_search_by_projection(ids[1], uv, mp_desc)
+    with pytest.raises(VslamError):
+        sp752.frame_search_by_projection(ids[2], uv, mp_desc, img_w=1280.0, img_h=720.0)
+    with pytest.raises(VslamError):
+        sp752.frame_retain(5)  # the last call processed one frame
+    again = sp752.frame_retain(0)
+    assert again == ids[1]
+    for i in (kf, up, again, ids[2], ids[3]):
+        sp752.frame_release(i)
+    # empty frame
+    e = sp752.frame_upload(type(f0.left_features)(f0.left_features.keypoints[:0], f0.left_features.descriptors[:0]))
+    gi, gd = sp752.frame_search_by_projection(e, uv[:5], mp_desc[:5])
+    assert list(gi) == [-1] * 5
+    sp752.frame_release(e)
