@@ -912,8 +912,9 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
 }
 
 // vslam_process, latency form: one stereo pair through a CUDA graph captured once per handle.  Everything the graph
-// touches has a fixed address (slot 0: pinned input staging, device buffers, pinned result mirror), so the per-call
-// work is: stage the two images, one cudaGraphLaunch, one synchronize, unpack.
+// touches has a fixed address (slot 0: device input, scratch and result buffers, pinned result mirror), so the per-call
+// work is: the two H2D copies, one cudaGraphLaunch (14 kernels with the forked blur + the D2H copies), one synchronize,
+// unpack.
 int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
                      uint64_t ts, vslam_frame_out* out) {
   DEVICE_SCOPE(h);
@@ -925,13 +926,21 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
   int rc = retire_slot(h, s, nullptr, nullptr, &first_error);  // never busy here; keeps the invariant explicit
   if (rc != VSLAM_OK) return rc;
   h->call_serial++;
+  // H2D outside the graph: straight from the caller's images when they are page-locked, else through the pinned staging
   for (int e = 0; e < 2; ++e) {
     const uint8_t* src = e ? right : left;
     const size_t st = e ? rstride : lstride;
-    uint8_t* dst = s.h_in + (size_t)e * ib;
-    if (st == (size_t)P.in_pitch) memcpy(dst, src, ib);
-    else
-      for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * P.in_pitch, src + (size_t)y * st, (size_t)W);
+    uint8_t* dev = s.d_in + (size_t)e * ib;
+    if (is_pinned_host(src)) {
+      if (st == (size_t)P.in_pitch) CU_TRY(h, cudaMemcpyAsync(dev, src, ib, cudaMemcpyHostToDevice, s.stream));
+      else CU_TRY(h, cudaMemcpy2DAsync(dev, P.in_pitch, src, st, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      uint8_t* dst = s.h_in + (size_t)e * ib;
+      if (st == (size_t)P.in_pitch) memcpy(dst, src, ib);
+      else
+        for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * P.in_pitch, src + (size_t)y * st, (size_t)W);
+      CU_TRY(h, cudaMemcpyAsync(dev, dst, ib, cudaMemcpyHostToDevice, s.stream));
+    }
   }
   if (!h->pair_graph) {
     cudaGraph_t g = nullptr;
@@ -939,7 +948,6 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
     CU_TRY(h, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
     rc = VSLAM_OK;
     do {
-      if (cudaMemcpyAsync(s.d_in, s.h_in, 2 * ib, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) { rc = VSLAM_ERR_CUDA; break; }
       rc = enqueue_chunk(h, s, 1, 2, s.d_in, s.d_in + ib, (long long)ib, P.in_pitch);
       if (rc != VSLAM_OK) break;
       if (cudaMemcpyAsync(s.h_lay.hdr, s.d_lay.hdr, sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) { rc = VSLAM_ERR_CUDA; break; }

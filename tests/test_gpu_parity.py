@@ -701,3 +701,69 @@ def test_resident_frame_searches(sp752, oracle, camera_dict):
     gi, gd = sp752.frame_search_by_projection(e, uv[:5], mp_desc[:5])
     assert list(gi) == [-1] * 5
     sp752.frame_release(e)
+
+
+# ------------------------------------------------------------------ wide sweeps behind the bench number
+def _sweep(width, height, nfeat, seeds, batch):
+    """`seeds` distinct synthetic frames through vslam_process_batch_device (the entry point that produces the bench's
+    headline) against cv2's cv::ORB directly + the restated matcher, computed by a process pool; returns the report."""
+    import torch
+
+    import bench
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    n = len(seeds)
+    left = torch.empty((n, height, width), dtype=torch.uint8, device="cuda")
+    right = torch.empty_like(left)
+    for i, s in enumerate(seeds):
+        left[i], right[i] = synth.make_stereo_pair(int(s), width, height, "cuda")
+    bench.W, bench.H, bench.NFEAT = width, height, nfeat
+    with StereoProcessor(CameraModel(**synth.EUROC_CAMERA), nfeat, width, height, max_batch=batch) as sp:
+        ob = sp.new_output_buffers(n)
+        sp.process_batch_device(n, left.data_ptr(), right.data_ptr(), width * height, width, ob)
+        host_l, host_r = left.cpu(), right.cpu()
+        rep = bench.check_parity(ob, host_l, host_r, np.arange(n), synth.EUROC_CAMERA, len(os.sched_getaffinity(0)))
+        rep["matches"] = int(sum(ob.outs[i].n_matches for i in range(n)))
+    return rep
+
+
+def test_sweep_1000_frames_752x480_against_cv2():
+    """VERDICT r01 'weak' 1: a large-sample sweep is what catches a rare sincos / overflow / fallback path."""
+    rep = _sweep(752, 480, 1200, range(5000, 6000), 64)
+    assert rep["frames_checked"] == 1000 and rep["mismatching_frames"] == 0, rep
+    assert "cv2" in rep["against"] and rep["matches"] > 900 * 1000
+
+
+def test_sweep_96_frames_720p_against_cv2():
+    rep = _sweep(1280, 720, 2000, range(7000, 7096), 16)
+    assert rep["frames_checked"] == 96 and rep["mismatching_frames"] == 0, rep
+
+
+@pytest.mark.parametrize("name", ["china.jpg", "flower.jpg"])
+def test_natural_images(name, oracle, cv2mod, camera_dict):
+    """The only natural photographs this image ships (scikit-learn's sample images, 640x427): as a stereo pair cut with
+    a 16 px disparity at native size, and resampled to the EuRoC shape — against cv2's cv::ORB directly."""
+    import sklearn.datasets
+
+    from oracle import cv2_ref
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    path = os.path.join(os.path.dirname(sklearn.datasets.__file__), "images", name)
+    gray = cv2mod.imread(path, cv2mod.IMREAD_GRAYSCALE)
+    if gray is None:
+        pytest.skip(f"{path} is not present / not decodable on this box")
+    cases = [(np.ascontiguousarray(gray[:, 16:624]), np.ascontiguousarray(gray[:, 0:608]))]
+    big = cv2mod.resize(gray, (784, 480), interpolation=cv2mod.INTER_CUBIC)
+    cases.append((np.ascontiguousarray(big[:, 32:784]), np.ascontiguousarray(big[:, 0:752])))
+    for left, right in cases:
+        h, w = left.shape
+        with StereoProcessor(CameraModel(**camera_dict), 1200, w, h, max_batch=2) as sp:
+            fr = sp.process(left, right)
+        ref = cv2_ref.stereo_process(left, right, camera_dict, 1200)
+        assert len(ref["kp_left"]) > 800, "the photograph should be feature-rich"
+        assert_struct_equal(fr.left_features.keypoints, ref["kp_left"], f"{name} {w}x{h} left keypoints")
+        assert_struct_equal(fr.right_features.keypoints, ref["kp_right"], f"{name} {w}x{h} right keypoints")
+        assert np.array_equal(fr.left_features.descriptors, ref["desc_left"])
+        assert np.array_equal(fr.right_features.descriptors, ref["desc_right"])
+        assert_struct_equal(fr.matches_lr, ref["matches"], f"{name} matches")
+        assert np.array_equal(fr.points_cam, ref["points"]) and np.array_equal(fr.points_valid, ref["points_valid"])
