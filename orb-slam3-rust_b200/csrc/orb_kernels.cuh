@@ -841,6 +841,166 @@ __device__ int warp_retain_best(T* rec, int n, int n_points, IdxT* Ll, IdxT* Rl,
   return n_points + nB;
 }
 
+// ---- the same replay by a whole BLOCK of 128 threads (4 warps).  The stopper lists are ordered by scan position, so
+//      warp w builds the part of both lists that falls into its quarter of the positions: a counting pass, a 4-entry
+//      prefix over the warps, then the writing pass; K is found by every thread with the same binary search (the
+//      predicate L[k] < R[k] is a prefix), the swaps are spread over the block.  Ranges shorter than 128 fall back to
+//      the single-warp pass (warp 0; the other warps wait at the barrier that publishes the cut).
+//      All 128 threads must call these functions with identical arguments.  s_w: shared int[12].
+template <typename T, typename IdxT>
+__device__ int block_partition_pivot(T* rec, int first, int last, IdxT* Ll, IdxT* Rl, int* s_w) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = last - first;
+  if (len < 128) {
+    if (warp == 0) {
+      const int cut = warp_partition_pivot<T, IdxT>(rec, first, last, Ll, Rl, lane);
+      if (lane == 0) s_w[8] = cut;
+    }
+    __syncthreads();
+    const int cut = s_w[8];
+    __syncthreads();  // s_w[8] is rewritten by the next pass
+    return cut;
+  }
+  if (tid == 0) vsel::median_to_first(rec, first, first + 1, first + len / 2, last - 1);
+  __syncthreads();
+  const T pivot = rec[first];
+  const unsigned lt = (1u << lane) - 1u;
+  const int chunk = ((len + 127) >> 7) << 5;  // scan positions per warp (multiple of 32)
+  const int o_beg = warp * chunk, o_end = min(o_beg + chunk, len);
+  int nR = 0, nL = 0;
+  for (int o = o_beg; o < o_end; o += 32) {
+    const int j = last - 1 - o - lane, i = first + 1 + o + lane;
+    const bool inj = j >= first, ini = i < last;  // (o + lane < len <=> j >= first; i < last is the tighter bound for L)
+    const T vj = inj ? rec[j] : pivot, vi = ini ? rec[i] : pivot;
+    nR += __popc(__ballot_sync(VSLAM_FULL, inj && !vsel::comp(pivot, vj)));
+    nL += __popc(__ballot_sync(VSLAM_FULL, ini && !vsel::comp(vi, pivot)));
+  }
+  if (lane == 0) {
+    s_w[warp] = nR;
+    s_w[4 + warp] = nL;
+  }
+  __syncthreads();
+  int baseR = 0, baseL = 0, totR = 0, totL = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int r = s_w[w], l = s_w[4 + w];
+    if (w < warp) {
+      baseR += r;
+      baseL += l;
+    }
+    totR += r;
+    totL += l;
+  }
+  nR = baseR;
+  nL = baseL;
+  for (int o = o_beg; o < o_end; o += 32) {
+    const int j = last - 1 - o - lane, i = first + 1 + o + lane;
+    const bool inj = j >= first, ini = i < last;
+    const T vj = inj ? rec[j] : pivot, vi = ini ? rec[i] : pivot;
+    const bool sr = inj && !vsel::comp(pivot, vj);
+    const bool sl = ini && !vsel::comp(vi, pivot);
+    const unsigned mr = __ballot_sync(VSLAM_FULL, sr), ml = __ballot_sync(VSLAM_FULL, sl);
+    if (sr) Rl[nR + __popc(mr & lt)] = (IdxT)j;
+    if (sl) Ll[nL + __popc(ml & lt)] = (IdxT)i;
+    nR += __popc(mr);
+    nL += __popc(ml);
+  }
+  __syncthreads();
+  const int nmin = min(totL, totR);
+  int lo = 0, hi = nmin;  // smallest k with !(L[k] < R[k]); every thread runs the same search
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)Ll[mid] < (int)Rl[mid]) lo = mid + 1;
+    else hi = mid;
+  }
+  const int K = lo;
+  int cut = last;
+  if (K < totL) cut = min(cut, (int)Ll[K]);
+  if (K > 0) cut = min(cut, (int)Rl[K - 1]);
+  for (int k = tid; k < K; k += 128) {
+    const int a = (int)Ll[k], b = (int)Rl[k];
+    const T t = rec[a];
+    rec[a] = rec[b];
+    rec[b] = t;
+  }
+  __syncthreads();
+  return cut;
+}
+
+template <typename T, typename IdxT>
+__device__ int block_retain_best(T* rec, int n, int n_points, IdxT* Ll, IdxT* Rl, int* s_w) {
+  if (n_points < 0 || n <= n_points) return n;
+  if (n_points == 0) return 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nth = n_points - 1;
+  int first = 0, last = n;
+  int depth = 2 * vsel::floor_log2(n);
+  bool sorted_tail = true;
+  while (last - first > 3) {
+    if (depth == 0) {  // std::__heap_select fallback (serial; practically never taken)
+      if (tid == 0) vsel::heap_select_fallback(rec, first, nth, last);
+      sorted_tail = false;
+      break;
+    }
+    --depth;
+    const int cut = block_partition_pivot<T, IdxT>(rec, first, last, Ll, Rl, s_w);
+    if (cut <= nth) first = cut;
+    else last = cut;
+  }
+  if (sorted_tail && tid == 0) vsel::insertion_sort(rec, first, last);
+  __syncthreads();
+  // std::partition(v + n_points, end, resp >= thr), block-parallel like the Hoare pass
+  const T thr = rec[nth];
+  const unsigned lt = (1u << lane) - 1u;
+  const int len = n - n_points;
+  const int chunk = ((len + 127) >> 7) << 5;
+  const int o_beg = warp * chunk, o_end = min(o_beg + chunk, len);
+  int nB = 0, nA = 0;
+  for (int o = o_beg; o < o_end; o += 32) {
+    const int j = n - 1 - o - lane, i = n_points + o + lane;
+    const bool inj = j >= n_points, ini = i < n;
+    nB += __popc(__ballot_sync(VSLAM_FULL, inj && !vsel::comp(thr, rec[inj ? j : nth])));
+    nA += __popc(__ballot_sync(VSLAM_FULL, ini && vsel::comp(thr, rec[ini ? i : nth])));
+  }
+  if (lane == 0) {
+    s_w[warp] = nB;
+    s_w[4 + warp] = nA;
+  }
+  __syncthreads();
+  int baseB = 0, baseA = 0, totB = 0, totA = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int b = s_w[w], a = s_w[4 + w];
+    if (w < warp) {
+      baseB += b;
+      baseA += a;
+    }
+    totB += b;
+    totA += a;
+  }
+  nB = baseB;
+  nA = baseA;
+  for (int o = o_beg; o < o_end; o += 32) {
+    const int j = n - 1 - o - lane, i = n_points + o + lane;
+    const bool inj = j >= n_points, ini = i < n;
+    const bool sb = inj && !vsel::comp(thr, rec[inj ? j : nth]);
+    const bool sa = ini && vsel::comp(thr, rec[ini ? i : nth]);
+    const unsigned mb = __ballot_sync(VSLAM_FULL, sb), ma = __ballot_sync(VSLAM_FULL, sa);
+    if (sb) Rl[nB + __popc(mb & lt)] = (IdxT)j;
+    if (sa) Ll[nA + __popc(ma & lt)] = (IdxT)i;
+    nB += __popc(mb);
+    nA += __popc(ma);
+  }
+  __syncthreads();
+  const int nmin = min(totA, totB);
+  for (int k = tid; k < nmin; k += 128) {
+    const int a = (int)Ll[k], b = (int)Rl[k];
+    if (a < b) rec[a] = rec[b];
+  }
+  __syncthreads();
+  return n_points + totB;
+}
+
 // A3(iii) — HarrisResponses (blockSize 7, k = 0.04) on the un-blurred level; float formula without FMA.
 __device__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y, float scale4) {
   // Ix = [1 2 1]^T (rows) applied to dx[r][j] = v[r][j+1] - v[r][j-1];  Iy = sm[r+1][j] - sm[r-1][j] with
@@ -1061,6 +1221,125 @@ __global__ void __launch_bounds__(32) k_select2(const __grid_constant__ PyrP P, 
     out[i] = k;
   }
   if (lane == 0) lvl_cnt[(long long)img * P.nlevels + l] = m2;
+}
+
+// A3, fused: retainBest(2 N_l) on the FAST score -> HarrisResponses of the survivors -> retainBest(N_l) on the Harris
+// response, one block of 128 threads per (image, level), every phase spread over the four warps.  The three-kernel
+// form above costs two grid-wide dependencies per chunk (k_harris waits for the slowest k_select1 block, k_select2
+// for the slowest k_harris block); here a level's chain runs back to back.
+// grid = (n_img, nlevels), block = 128.  Dynamic smem = select_fused_smem_bytes(cap1, cap2): cap1 FAST-score records
+// (+ index lists) for the first replay, cap2 Harris records for the second; a problem larger than its budget is
+// replayed in global memory (sel1 / cand as the work arrays, glists for the index lists) — slower, same result.
+__host__ inline size_t select_fused_smem_bytes(int cap1, int cap2) {
+  const size_t a = (size_t)cap1 * (sizeof(uint32_t) + 2 * sizeof(uint16_t));
+  const size_t b = (size_t)cap2 * (sizeof(vrec_t) + 2 * sizeof(uint16_t));
+  return (a > b ? a : b) + 16;
+}
+__global__ void __launch_bounds__(128) k_select_fused(const __grid_constant__ PyrP P, int cap1, int cap2,
+                                                      const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
+                                                      const uint8_t* __restrict__ pyr, const int* __restrict__ strip_cnt,
+                                                      const uint32_t* __restrict__ strip_rec, uint32_t* __restrict__ sel1,
+                                                      vrec_t* __restrict__ cand, uint32_t* __restrict__ glists,
+                                                      int* __restrict__ sel1_cnt, LvlKp* __restrict__ lvl_kp,
+                                                      int* __restrict__ lvl_cnt, float harris_scale4, const FrameLayout F) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_off[129];
+  __shared__ int s_w[12];
+  const int img = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const LevelP& L = P.lv[l];
+  const int* cnt = strip_cnt + (long long)img * P.total_fast_strips + L.fast_strip0;
+  const long long base = (long long)img * P.rec_img_stride + L.rec_off;
+  const uint32_t* lrec = strip_rec + base;
+  uint32_t* out1 = sel1 + base;
+  uint32_t* gl32 = glists + 2 * base;
+  const long long gl_half = (long long)L.fast_nstrips * L.strip_cap;
+  if (tid < 32) {  // strip offsets (nstrips <= 128)
+    int run = 0;
+    for (int b = 0; b < L.fast_nstrips; b += 32) {
+      const int i = b + lane;
+      const int c = i < L.fast_nstrips ? cnt[i] : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(VSLAM_FULL, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (i < L.fast_nstrips) s_off[i] = run + incl - c;
+      run += __shfl_sync(VSLAM_FULL, incl, 31);
+    }
+    if (lane == 0) s_off[L.fast_nstrips] = run;
+  }
+  __syncthreads();
+  const int n_in = s_off[L.fast_nstrips];
+  // ---- gather: element e of the level's raster-ordered list lives in strip s with s_off[s] <= e < s_off[s+1]; four
+  //      independent loads per thread are in flight
+  const bool smem1 = n_in <= cap1 && n_in <= 65535;
+  uint32_t* rec = smem1 ? reinterpret_cast<uint32_t*>(smem) : out1;
+  {
+    int st = 0;
+    for (int e0 = tid; e0 < n_in; e0 += 4 * 128) {
+      uint32_t v[4];
+      int st_k = st;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 128;
+        if (e < n_in) {
+          while (s_off[st_k + 1] <= e) ++st_k;
+          v[k] = lrec[(long long)st_k * L.strip_cap + (e - s_off[st_k])];
+        }
+      }
+      st = st_k;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e0 + k * 128 < n_in) rec[e0 + k * 128] = v[k];
+    }
+  }
+  __syncthreads();
+  // ---- retainBest(2 N_l) on the FAST score
+  int m1;
+  if (smem1) {
+    uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)cap1 * sizeof(uint32_t));
+    m1 = block_retain_best<uint32_t, uint16_t>(rec, n_in, 2 * L.nfeat, l16, l16 + cap1, s_w);
+    for (int i = tid; i < m1; i += 128) out1[i] = rec[i];
+  } else {
+    m1 = block_retain_best<uint32_t, uint32_t>(rec, n_in, 2 * L.nfeat, gl32, gl32 + gl_half, s_w);
+  }
+  if (tid == 0) sel1_cnt[(long long)img * P.nlevels + l] = m1;
+  __syncthreads();  // out1[0 .. m1) is visible to the whole block; the first replay's shared memory is free
+  // ---- HarrisResponses of the survivors (thread per survivor)
+  int pitch;
+  const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
+  const bool smem2 = m1 <= cap2 && m1 <= 65535;
+  vrec_t* gcand = cand + base;
+  vrec_t* rec2 = smem2 ? reinterpret_cast<vrec_t*>(smem) : gcand;
+  for (int i = tid; i < m1; i += 128) {
+    const uint32_t r = out1[i];
+    const int x = (int)(r & 0xfffu), y = (int)((r >> 12) & 0xfffu);
+    const float hr = harris_response(img_base, pitch, x, y, harris_scale4);
+    rec2[i] = ((vrec_t)__float_as_uint(hr) << 32) | ((unsigned)y << 16) | (unsigned)x;
+  }
+  __syncthreads();
+  // ---- retainBest(N_l) on the Harris response
+  int m2;
+  if (smem2) {
+    uint16_t* l16 = reinterpret_cast<uint16_t*>(smem + (size_t)cap2 * sizeof(vrec_t));
+    m2 = block_retain_best<vrec_t, uint16_t>(rec2, m1, L.nfeat, l16, l16 + cap2, s_w);
+  } else {
+    m2 = block_retain_best<vrec_t, uint32_t>(rec2, m1, L.nfeat, gl32, gl32 + gl_half, s_w);
+  }
+  if (m2 > P.kp_cap) {  // more ties than the handle was sized for: flag, keep the first kp_cap
+    if (tid == 0) atomicMax(&F.hdr[img / P.eyes].status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
+    m2 = P.kp_cap;
+  }
+  LvlKp* out = lvl_kp + ((long long)img * P.nlevels + l) * P.kp_cap;
+  for (int i = tid; i < m2; i += 128) {
+    const vrec_t r = rec2[i];
+    LvlKp k;
+    k.xy = (unsigned)r;
+    k.resp = __uint_as_float((unsigned)(r >> 32));
+    out[i] = k;
+  }
+  if (tid == 0) lvl_cnt[(long long)img * P.nlevels + l] = m2;
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -92,6 +92,7 @@ struct vslam_handle_s {
   // 16 BRIEF, 32 match.  The drop in step time is that stage's marginal cost inside the 4-slot pipeline.
   int debug_skip = 0;
   uint64_t chunks_run = 0;
+  bool select_fused = true;  // VSLAM_SELECT_FUSED=0: the three-kernel selection chain (k_select1, k_harris, k_select2)
   bool resize_tile = true;   // VSLAM_RESIZE_TILE=0 selects the per-lane cp.async ring kernel (k_resize)
   int rtile_rows = 16;       // VSLAM_RTILE_ROWS
   int blur_rows = VSLAM_BLUR_ROWS;      // max output rows per k_blur lane item
@@ -189,13 +190,13 @@ struct DeviceGuard {
 
 // The dynamic shared-memory opt-in is a per-function, per-device attribute shared by every handle of the process:
 // only ever raise it, so that handles created for smaller images do not shrink what an older handle's launches need.
-enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_RTILE, SMEM_RTILE_WIDE, SMEM_NFUNC };
+enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_RTILE, SMEM_RTILE_WIDE, SMEM_SELF, SMEM_NFUNC };
 cudaError_t raise_smem_limit(int device, int which, size_t want) {
   static std::mutex mu;
   static size_t cur_dev[64][SMEM_NFUNC] = {{0}};
   const void* fn[SMEM_NFUNC] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
                                 (const void*)vk::k_match_rows, (const void*)vk::k_resize_tile<false>,
-                                (const void*)vk::k_resize_tile<true>};
+                                (const void*)vk::k_resize_tile<true>, (const void*)vk::k_select_fused};
   std::lock_guard<std::mutex> lock(mu);
   size_t& cur = cur_dev[device & 63][which];
   if (want <= cur) return cudaSuccess;
@@ -607,7 +608,13 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     if (rcb != VSLAM_OK) return rcb;
   }
   mark();  // 2
-  if (!(skip & 4)) {
+  if (!(skip & 4) && h->select_fused) {
+    const int cap1 = nimg >= 32 ? h->sel1_cap : std::max(h->sel1_cap, h->sel1_cap_latency);
+    vk::k_select_fused<<<dim3(nimg, P.nlevels), 128, vk::select_fused_smem_bytes(cap1, h->sel2_cap), st>>>(
+        P, cap1, h->sel2_cap, in_l, in_r, s.d_pyr, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_cand, s.d_glists, s.d_sel1_cnt,
+        s.d_lvl_kp, s.d_lvl_cnt, h->harris_scale4, s.d_lay);
+    h->launches += 1;
+  } else if (!(skip & 4)) {
     const int cap1 = nimg >= 32 ? h->sel1_cap : std::max(h->sel1_cap, h->sel1_cap_latency);
     vk::k_select1<<<dim3(nimg, P.nlevels), 128, vk::select1_smem_bytes(cap1), st>>>(
         P, cap1, s.d_strip_cnt, s.d_strip_rec, s.d_sel1, s.d_glists, s.d_sel1_cnt);
@@ -1074,6 +1081,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_DEBUG_SKIP")) h->debug_skip = atoi(ev);
   if (const char* ev = getenv("VSLAM_GRAPH")) h->use_graph = atoi(ev) != 0;
+  if (const char* ev = getenv("VSLAM_SELECT_FUSED")) h->select_fused = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_RESIZE_TILE")) h->resize_tile = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_RTILE_ROWS")) h->rtile_rows = std::min(std::max(atoi(ev), 2), 256);
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs
@@ -1104,7 +1112,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   cudaEventCreate(&h->ev_batch[1]);
   // opt in to large dynamic shared memory where needed
   const size_t max_sel1 = vk::select1_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency));
-  const size_t max_sel = std::max(max_sel1, vk::select2_smem_bytes(h->sel2_cap));
+  const size_t max_sel = std::max(std::max(max_sel1, vk::select2_smem_bytes(h->sel2_cap)),
+                                  vk::select_fused_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency), h->sel2_cap));
   const size_t lim = (size_t)prop.sharedMemPerBlockOptin;
   if (h->fast_smem > lim || max_sel > lim) {
     fail(h, VSLAM_ERR_INVALID_ARGUMENT, "image too wide for the shared-memory tiles (%zu/%zu > %zu bytes)",
@@ -1122,7 +1131,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
       for (int l = 1; l < h->P.nlevels; ++l) rt = std::max(rt, h->rtile[v][l].smem);
     if (rt > lim) h->resize_tile = false;  // extreme widths x scale factors: the ring kernel has no such limit
     const size_t want[SMEM_NFUNC] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem,
-                                     h->resize_tile ? rt : 0, h->resize_tile ? rt : 0};
+                                     h->resize_tile ? rt : 0, h->resize_tile ? rt : 0,
+                                     vk::select_fused_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency), h->sel2_cap)};
     for (int i = 0; i < SMEM_NFUNC; ++i) {
       e = raise_smem_limit(c.device, i, want[i]);
       if (e != cudaSuccess) {
