@@ -15,6 +15,7 @@
 // Everything is integer / explicitly rounded float: the file is compiled with -fmad=false and uses the
 // __f*_rn intrinsics wherever the rounding sequence is part of the specification.
 #pragma once
+#include <cuda.h>  // CUtensorMap (the tensor maps are encoded by the host through the driver entry point, no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1768,6 +1769,167 @@ __global__ void __launch_bounds__(32 * kBriefWarps) k_brief(const __grid_constan
 #else
     const float4 t = g_brief_pattern_t[q][lane];  // test 8*lane + q: (x0,y0,x1,y1)
 #endif
+    const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
+    const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
+    const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
+    const unsigned iy1 = raw(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
+    const unsigned t0 = lds8(center + iy0 * kRowB + ix0), t1 = lds8(center + iy1 * kRowB + ix1);
+    byte |= (unsigned)(t0 < t1) << q;
+  }
+  unsigned char* descbase = eye ? F.desc[1] : F.desc[0];
+  (descbase + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// A4/A6 with the patches staged by TMA (cp.async.bulk.tensor): k_brief is bound by L1 wavefronts, and almost half of
+// them are the two patch copies (68 image rows = 68 cache lines per keypoint through the LSU).  Here lane 0 of a warp
+// issues two tensor-tile loads — kTmaBriefW x 37 bytes of the blurred level and 48 x 31 bytes of the un-blurred level —
+// that travel L2 -> shared memory without touching L1 or a register, and signal an mbarrier.  The box must start on a
+// 16-byte boundary of the row (measured: tools/ubench/tma_probe.cu — an unaligned innermost coordinate of a u8 tensor
+// raises an illegal-instruction fault on sm_100a), so the boxes start at x & ~15 and are 15 bytes wider than the
+// windows.  The arithmetic is k_brief's, bit for bit.
+// Orientation mapping: lane = (word j = lane & 7, row group g = lane >> 3) reduces word j of the 31-px window of rows
+// g, g + 4, ...: two shared-memory words and a funnel shift bring the window's word j into place whatever the
+// alignment, so one mask table serves every keypoint.
+// ----------------------------------------------------------------------------------------------------------
+struct BriefMaps {
+  CUtensorMap blur[VSLAM_MAX_LEVELS];  // blurred slab, level l: (pitch, h, image)
+  CUtensorMap pyr[VSLAM_MAX_LEVELS];   // pyramid slab, levels >= 1: (pitch, h, image)
+  CUtensorMap in_l, in_r;              // level 0 of the left / right eye: (pitch, H, frame)
+};
+#ifndef VSLAM_TMA_BRIEF_W
+#define VSLAM_TMA_BRIEF_W 64
+#endif
+constexpr int kTmaBriefW = VSLAM_TMA_BRIEF_W, kTmaAngleW = 48;  // >= 37 + 15 and 31 + 15, multiples of 16
+static_assert(kTmaBriefW % 16 == 0 && kTmaBriefW >= kBriefRows + 15, "BRIEF box: 16-byte granules, window + alignment slack");
+constexpr int kTmaBriefBytes = kTmaBriefW * kBriefRows, kTmaAngleBytes = kTmaAngleW * kAngleRows;  // 1776, 992
+constexpr int kTmaBriefSlot = (kTmaBriefBytes + 127) & ~127, kTmaAngleSlot = (kTmaAngleBytes + 127) & ~127;  // 1792, 1024
+
+// g_angle_mask_t[k][lane]: byte b = 0xff iff pixel u = 4 j + b - 15 of patch row r = g + 4 k (j = lane & 7, g = lane >> 3)
+// lies inside the 31-px disc (0 for r > 30).  Filled by upload_tables.
+__device__ unsigned g_angle_mask_t[8][32];
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(mbar)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kBriefWarps) k_brief_tma(const __grid_constant__ PyrP P, const __grid_constant__ BriefMaps M,
+                                                                 const LvlKp* __restrict__ lvl_kp, const int* __restrict__ lvl_cnt,
+                                                                 const FrameLayout F) {
+  __shared__ __align__(128) uint8_t s_patch[kBriefWarps][kTmaBriefSlot + kTmaAngleSlot];
+  __shared__ __align__(8) unsigned long long s_bar[kBriefWarps];
+  const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * kBriefWarps + warp;
+  const int frame = P.eyes == 2 ? img >> 1 : img, eye = P.eyes == 2 ? (img & 1) : 0;
+  const int* cnt = lvl_cnt + (long long)img * P.nlevels;
+  int total = 0, l = -1, jl = 0;
+  {
+    int c[VSLAM_MAX_LEVELS];
+#pragma unroll
+    for (int k = 0; k < VSLAM_MAX_LEVELS; ++k) c[k] = k < P.nlevels ? cnt[k] : 0;
+#pragma unroll
+    for (int k = 0; k < VSLAM_MAX_LEVELS; ++k) {
+      if (l < 0 && j < total + c[k]) {
+        l = k;
+        jl = j - total;
+      }
+      total += c[k];
+    }
+  }
+  ResHdr* hdr = F.hdr + frame;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->n_kp[eye] = min(total, P.kp_cap);
+    if (total > P.kp_cap) atomicMax(&hdr->status, 4 /* VSLAM_ERR_KEYPOINT_OVERFLOW */);
+  }
+  if (l < 0 || j >= P.kp_cap) return;  // warp-uniform; no block-wide barrier in this kernel
+  const LevelP& L = P.lv[l];
+  const LvlKp kp = lvl_kp[((long long)img * P.nlevels + l) * P.kp_cap + jl];
+  const int cx = (int)(kp.xy & 0xffffu), cy = (int)(kp.xy >> 16);
+
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(s_patch[warp]);
+  const unsigned sa = sb + kTmaBriefSlot;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)(kTmaBriefBytes + kTmaAngleBytes))
+                 : "memory");
+    tma_load_3d(sb, &M.blur[l], (cx - kBriefR) & ~15, cy - kBriefR, img, mbar);
+    if (l == 0) tma_load_3d(sa, eye ? &M.in_r : &M.in_l, (cx - kAngleR) & ~15, cy - kAngleR, frame, mbar);
+    else tma_load_3d(sa, &M.pyr[l], (cx - kAngleR) & ~15, cy - kAngleR, img, mbar);
+  }
+  __syncwarp();
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mbar)
+          : "memory");
+  }
+
+  // ---- A4: intensity-centroid angle.  lane = (j = lane & 7, g = lane >> 3): word j of rows g + 4 k
+  int m10 = 0, m01 = 0;
+  {
+    const int jw = lane & 7, g = lane >> 3;
+    unsigned uw = 0;  // (int8) u of the four pixels of word jw
+#pragma unroll
+    for (int b = 0; b < 4; ++b) uw |= (unsigned)(uint8_t)(int8_t)(4 * jw + b - kAngleR) << (8 * b);
+    const unsigned oa = (unsigned)(cx - kAngleR) & 15u;            // byte offset of the window inside the box
+    const unsigned wa = sa + (oa & ~3u) + 4u * (unsigned)jw, sha = 8u * (oa & 3u);
+    int su = 0, sv = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = g + 4 * k;
+      if (r < kAngleRows) {
+        const unsigned a = wa + (unsigned)(r * kTmaAngleW);
+        const unsigned wv = __funnelshift_r(lds32<0>(a), lds32<4>(a), sha) & g_angle_mask_t[k][lane];
+        su = dp4a_u8_s8(wv, uw, su);
+        sv += (r - kAngleR) * dp4a_u8_s8(wv, 0x01010101u, 0);
+      }
+    }
+    m10 = su;
+    m01 = sv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(VSLAM_FULL, m10, o);
+    m01 += __shfl_xor_sync(VSLAM_FULL, m01, o);
+  }
+  const float angle = fast_atan2_deg(__int2float_rn(m01), __int2float_rn(m10));
+
+  if (lane == 0) {
+    KeyPoint28 o;
+    o.x = __fmul_rn(__int2float_rn(cx), L.scale);
+    o.y = __fmul_rn(__int2float_rn(cy), L.scale);
+    o.size = __fmul_rn(31.0f, L.scale);
+    o.angle = angle;
+    o.response = kp.resp;
+    o.octave = l;
+    o.class_id = -1;
+    unsigned char* kpbase = eye ? F.kp[1] : F.kp[0];
+    reinterpret_cast<KeyPoint28*>(kpbase + (long long)frame * F.kp_stride)[j] = o;
+  }
+  const float rad = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.0));
+  float a, b;
+  sincos_f64_to_f32(rad, a, b);
+  // sample address = patch centre + 48 * iy + ix with the cvRound bias folded in (see k_brief)
+  constexpr unsigned kRowB = kTmaBriefW;
+  const unsigned center = sb + kBriefR * kRowB + (unsigned)kBriefR + ((unsigned)(cx - kBriefR) & 15u) - (kRowB + 1u) * 0x4B400000u;
+  auto raw = [](float v) -> unsigned { return __float_as_uint(__fadd_rn(v, 12582912.0f)); };
+  unsigned byte = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const unsigned pw = g_brief_pattern_i8[q][lane];
+    float4 t;
+    t.x = (float)(int)(signed char)(pw & 0xffu);
+    t.y = (float)(int)(signed char)((pw >> 8) & 0xffu);
+    t.z = (float)(int)(signed char)((pw >> 16) & 0xffu);
+    t.w = (float)(int)(signed char)(pw >> 24);
     const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
     const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
     const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));

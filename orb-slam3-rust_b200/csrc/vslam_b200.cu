@@ -55,6 +55,7 @@ struct Slot {
   int* d_lvl_cnt = nullptr;
   unsigned char* d_res = nullptr;  // one block, carved into the SoA result arrays (d_lay)
   FrameLayout d_lay;
+  vk::BriefMaps maps;              // TMA tensor maps of this slot's blurred / pyramid slabs (k_brief_tma)
   int2* d_ml = nullptr;
   uint8_t* h_in = nullptr;         // pinned
   unsigned char* h_res = nullptr;  // pinned mirror of d_res (h_lay)
@@ -92,6 +93,11 @@ struct vslam_handle_s {
   // 16 BRIEF, 32 match.  The drop in step time is that stage's marginal cost inside the 4-slot pipeline.
   int debug_skip = 0;
   uint64_t chunks_run = 0;
+  // VSLAM_BRIEF_TMA=1: BRIEF / orientation patches through TMA tensor-tile loads (k_brief_tma) instead of per-lane
+  // cp.async (k_brief).  Measured on B200 (profiles/r02_summary.md): the TMA kernel is 14 % faster alone (4.12 vs 4.79 ms
+  // per 2000 frames) but 1 % slower inside the 4-slot pipeline (87.1k vs 88.0k frames/s: larger shared-memory footprint,
+  // and it shares the bulk-copy engine with k_fast's row staging), so the cp.async kernel stays the default.
+  bool brief_tma = false;
   bool select_fused = true;  // VSLAM_SELECT_FUSED=0: the three-kernel selection chain (k_select1, k_harris, k_select2)
   bool resize_tile = true;   // VSLAM_RESIZE_TILE=0 selects the per-lane cp.async ring kernel (k_resize)
   int rtile_rows = 16;       // VSLAM_RTILE_ROWS
@@ -225,6 +231,37 @@ void linear_exact_coeffs(int src, int dst, uint32_t* out) {
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// u8 tensor (x = bytes of a row, y = rows, z = images) with a box of box_w x box_h x 1; OOB reads fill with zero.
+bool encode_u8_map(CUtensorMap* m, const void* base, size_t pitch, size_t rows, size_t images, size_t image_stride, unsigned box_w,
+                   unsigned box_h) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dim[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)std::max<size_t>(images, 1)};
+  const cuuint64_t stride[2] = {(cuuint64_t)pitch, (cuuint64_t)image_stride};
+  const cuuint32_t box[3] = {box_w, box_h, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Tables of k_brief (see orb_kernels.cuh): transposed float rBRIEF pattern, disc masks and packed int8 column offsets.
 int upload_tables(vslam_handle h) {
   static const int pattern[1024] = {
@@ -265,6 +302,23 @@ int upload_tables(vslam_handle h) {
         pat_i8[q][b] = w;
       }
     CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_i8, pat_i8, sizeof(pat_i8)));
+  }
+  {
+    unsigned mask_t[8][32];  // k_brief_tma: [k][lane], lane = (j = lane & 7, g = lane >> 3), row r = g + 4 k
+    for (int k = 0; k < 8; ++k)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int j = lane & 7, r = (lane >> 3) + 4 * k;
+        unsigned m = 0;
+        if (r < 31) {
+          const int d = umax[r < 15 ? 15 - r : r - 15];
+          for (int b = 0; b < 4; ++b) {
+            const int u = 4 * j + b - 15;
+            if (u >= -d && u <= d) m |= 0xffu << (8 * b);
+          }
+        }
+        mask_t[k][lane] = m;
+      }
+    CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_mask_t, mask_t, sizeof(mask_t)));
   }
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_mask, mask, sizeof(mask)));
   CU_TRY(h, cudaMemcpyToSymbol(vk::g_angle_u, uu, sizeof(uu)));
@@ -516,6 +570,16 @@ int alloc_slot(vslam_handle h, Slot& s) {
   CU_TRY(h, cudaMemset(s.d_res, 0, s.res_bytes));
   carve_results(s.d_res, nfr, h->kp_cap, &s.d_lay);
   carve_results(s.h_res, nfr, h->kp_cap, &s.h_lay);
+  memset(&s.maps, 0, sizeof(s.maps));
+  for (int l = 0; l < P.nlevels && h->brief_tma; ++l) {
+    const LevelP& L = P.lv[l];
+    bool ok = encode_u8_map(&s.maps.blur[l], s.d_blur + L.blur_off, (size_t)L.pitch, (size_t)L.h, nimg, (size_t)P.blur_img_stride,
+                            vk::kTmaBriefW, vk::kBriefRows);
+    if (ok && l > 0)
+      ok = encode_u8_map(&s.maps.pyr[l], s.d_pyr + L.pyr_off, (size_t)L.pitch, (size_t)L.h, nimg, (size_t)P.pyr_img_stride,
+                         vk::kTmaAngleW, vk::kAngleRows);
+    if (!ok) h->brief_tma = false;
+  }
   return VSLAM_OK;
 }
 
@@ -634,7 +698,15 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
   mark();  // 4
   if (!(skip & 16)) {
     dim3 grid((P.kp_cap + vk::kBriefWarps - 1) / vk::kBriefWarps, nimg);
-    vk::k_brief<<<grid, 32 * vk::kBriefWarps, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    bool tma = h->brief_tma;
+    if (tma) {  // level 0 of the un-blurred pyramid is the caller's / the staged input: its maps follow the chunk
+      tma = encode_u8_map(&s.maps.in_l, in_l, (size_t)pitch, (size_t)h->cfg.height, (size_t)frames, (size_t)frame_stride,
+                          vk::kTmaAngleW, vk::kAngleRows) &&
+            encode_u8_map(&s.maps.in_r, eyes == 2 ? in_r : in_l, (size_t)pitch, (size_t)h->cfg.height, (size_t)frames,
+                          (size_t)frame_stride, vk::kTmaAngleW, vk::kAngleRows);
+    }
+    if (tma) vk::k_brief_tma<<<grid, 32 * vk::kBriefWarps, 0, st>>>(P, s.maps, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    else vk::k_brief<<<grid, 32 * vk::kBriefWarps, 0, st>>>(P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
     h->launches++;
   }
   mark();  // 5
@@ -1082,6 +1154,8 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (const char* ev = getenv("VSLAM_DEBUG_SKIP")) h->debug_skip = atoi(ev);
   if (const char* ev = getenv("VSLAM_GRAPH")) h->use_graph = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_SELECT_FUSED")) h->select_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("VSLAM_BRIEF_TMA")) h->brief_tma = atoi(ev) != 0;
+  if (!tensor_map_encoder()) h->brief_tma = false;  // driver without cuTensorMapEncodeTiled: the cp.async kernel
   if (const char* ev = getenv("VSLAM_RESIZE_TILE")) h->resize_tile = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_RTILE_ROWS")) h->rtile_rows = std::min(std::max(atoi(ev), 2), 256);
   if (const char* ev = getenv("VSLAM_RESIZE_ROWS")) h->resize_rows = std::min(std::max(atoi(ev), 4), 4096);  // tuning knobs

@@ -767,3 +767,16 @@ def test_natural_images(name, oracle, cv2mod, camera_dict):
         assert np.array_equal(fr.right_features.descriptors, ref["desc_right"])
         assert_struct_equal(fr.matches_lr, ref["matches"], f"{name} matches")
         assert np.array_equal(fr.points_cam, ref["points"]) and np.array_equal(fr.points_valid, ref["points_valid"])
+
+
+def test_brief_tma_variant_is_bit_identical(oracle, pairs, camera_dict, monkeypatch):
+    """k_brief_tma (patches staged by cp.async.bulk.tensor tile loads) is kept as a measured alternative to k_brief
+    (VSLAM_BRIEF_TMA=1): same bits, including keypoints whose 16-byte aligned boxes hang over the right image edge."""
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    monkeypatch.setenv("VSLAM_BRIEF_TMA", "1")
+    for (w, h, seed) in ((752, 480, 4), (640, 427, 9)):
+        l, r = pairs(seed, w, h)
+        with StereoProcessor(CameraModel(**camera_dict), 1200, w, h, max_batch=2) as sp:
+            fr = sp.process(l, r)
+        check_frame(fr, oracle.detect_and_compute(l, 1200), oracle.detect_and_compute(r, 1200), oracle, camera_dict)
