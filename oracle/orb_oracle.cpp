@@ -145,6 +145,9 @@ static inline int fast_arc_score(const uint8_t* p, int stride) {
   return best;
 }
 
+// S of one pixel (>= 3 px inside the image), for the classic-mode model (oracle/classic_model.cpp).
+int orc_fast_score_at(const uint8_t* img, int stride, int x, int y) { return fast_arc_score(img + (size_t)y * stride + x, stride); }
+
 // FAST(threshold, nonmaxSuppression=true, TYPE_9_16): writes corners in raster order.
 // score map holds (S-1) for corners, 0 otherwise. Returns the number of corners (may exceed cap; only cap written).
 int orc_fast_nms(const uint8_t* img, int w, int h, int stride, int threshold, OrcCorner* out, int cap) {

@@ -31,7 +31,7 @@ class Camera(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed recipe (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "stereo_oracle.cpp", "brief_pattern.inc", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "stereo_oracle.cpp", "classic_model.cpp", "brief_pattern.inc", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "liborb_oracle.so"], check=True, capture_output=True)
@@ -375,3 +375,49 @@ def search_for_triangulation_bow(groups, kp1, desc1, flags1, kp2, desc2, flags2,
     n = lib().orc_search_for_triangulation_bow(_p(k1), _p(d1), _p(f1), len(k1), _p(k2), _p(d2), _p(f2), len(k2),
                                                C.byref(params), len(groups), _p(s1), _p(i1), _p(s2), _p(i2), _p(out))
     return out[:n].copy()
+
+
+# ------------------------------------------------------------------ classic mode model (classic_model.cpp) — NOT reference parity
+def classic_detect_and_compute(img, nfeatures=1200, nlevels=8, scale_factor=1.2, ini_th=20, min_th=7):
+    """Own CPU model of the upstream-ORB-SLAM3 style extraction (per-cell FAST with threshold retry + quadtree)."""
+    img = _u8(img)
+    cap = 4 * nfeatures + 256
+    kps = np.zeros(cap, dtype=KP_DTYPE)
+    desc = np.zeros((cap, 32), dtype=np.uint8)
+    n = lib().orc_classic_detect_and_compute(_p(img), img.shape[1], img.shape[0], img.strides[0], int(nfeatures), int(nlevels),
+                                             C.c_float(scale_factor), int(ini_th), int(min_th), _p(kps), _p(desc), cap)
+    assert n <= cap
+    return kps[:n].copy(), desc[:n].copy()
+
+
+def classic_level_candidates(level_img, nfeat, ini_th=20, min_th=7):
+    """-> (candidates int32 [n,3] (x, y, resp) in cell-row-major / raster order, kept indices) of one pyramid level."""
+    img = _u8(level_img)
+    cap = img.size // 4 + 16
+    xyr = np.zeros((cap, 3), dtype=np.int32)
+    keep = np.zeros(cap, dtype=np.int32)
+    nk = C.c_int(0)
+    n = lib().orc_classic_level_candidates(_p(img), img.shape[1], img.shape[0], img.strides[0], int(nfeat), int(ini_th),
+                                           int(min_th), _p(xyr), cap, _p(keep), C.byref(nk))
+    return xyr[:n].copy(), keep[: nk.value].copy()
+
+
+def classic_stereo(kl, dl, kr, dr, left, right, camera, nfeatures=1200, nlevels=8, scale_factor=1.2):
+    """Own CPU model of ComputeStereoMatches: row-band Hamming match (octave-scaled radius, +-1 level), 11x11 SAD over 11
+    shifts on the keypoint's pyramid level, parabola, median filter -> (match_idx, orb_dist, u_right, depth) per left kp."""
+    kl = np.ascontiguousarray(kl, dtype=KP_DTYPE)
+    kr = np.ascontiguousarray(kr, dtype=KP_DTYPE)
+    dl = np.ascontiguousarray(dl, dtype=np.uint8).reshape(-1, 32)
+    dr = np.ascontiguousarray(dr, dtype=np.uint8).reshape(-1, 32)
+    lv = level_geometry(left.shape[1], left.shape[0], nfeatures, nlevels, scale_factor)
+    pl = np.concatenate([p.ravel() for p in build_pyramid(left, lv)])
+    pr = np.concatenate([p.ravel() for p in build_pyramid(right, lv)])
+    n = max(len(kl), 1)
+    mi = np.full(n, -1, dtype=np.int32)
+    od = np.full(n, -1, dtype=np.int32)
+    ur = np.full(n, -1, dtype=np.float32)
+    dp = np.full(n, -1, dtype=np.float32)
+    lib().orc_classic_stereo(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(pl), _p(pr), _p(lv), int(nlevels),
+                             C.c_double(camera["fx"]), C.c_double(camera["baseline"]), _p(mi), _p(od), _p(ur), _p(dp))
+    k = len(kl)
+    return mi[:k], od[:k], ur[:k], dp[:k]
