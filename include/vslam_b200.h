@@ -108,8 +108,25 @@ typedef struct vslam_config {
   int32_t device;       /* CUDA device ordinal */
   int32_t max_batch;    /* stereo frames resident per pipeline stage; 0 -> 64 */
   int32_t keypoint_capacity; /* per image; 0 -> n_features + max(n_features/8, 64) */
-  int32_t reserved[8];
+  int32_t mode;             /* VSLAM_MODE_REFERENCE (0, default) or VSLAM_MODE_CLASSIC; was reserved[0] */
+  int32_t classic_ini_fast; /* classic mode: iniThFAST, 0 -> 20 */
+  int32_t classic_min_fast; /* classic mode: minThFAST, 0 -> 7 */
+  int32_t reserved[5];
 } vslam_config;
+
+/* Extraction / stereo algorithm of a handle.
+ *   VSLAM_MODE_REFERENCE  what jurmy24/orb-slam3-rust computes: stock cv::ORB (global FAST threshold, retainBest x2 with
+ *                         Harris) + the gated brute-force matcher of stereo.rs:80-161.  Bit-exact with the reference.
+ *   VSLAM_MODE_CLASSIC    the upstream-ORB-SLAM3 style front end `north_star` also names and the reference does NOT contain:
+ *                         per-cell FAST (35-px cells, iniThFAST with a minThFAST retry), quadtree keypoint distribution,
+ *                         row-band stereo matching with an octave-scaled radius and +-1 level consistency, 11x11 SAD
+ *                         refinement over 11 shifts, parabolic sub-pixel disparity and the median SAD outlier filter.
+ *                         NOT REFERENCE PARITY — there is no reference code for it; it is specified by this repository's
+ *                         own CPU model (oracle/classic_model.cpp, published ORB-SLAM3 algorithm, deterministic
+ *                         tie-breaks) and tested bit-for-bit against that model only.  Same outputs (keypoints,
+ *                         descriptors, matches_lr, points_cam) + vslam_classic_stereo_extra for the refined u_right / depth.
+ *                         The tracking-side entry points are mode-independent. */
+enum { VSLAM_MODE_REFERENCE = 0, VSLAM_MODE_CLASSIC = 1 };
 
 /* Caller-owned, capacity-checked result of one stereo frame == StereoFrame (stereo.rs:21-29). */
 typedef struct vslam_frame_out {
@@ -156,6 +173,12 @@ int vslam_process_batch(vslam_handle h, int n, const uint8_t* const* left, const
 int vslam_process_batch_device(vslam_handle h, int n, const uint8_t* left_dev, const uint8_t* right_dev,
                                size_t image_stride, size_t row_stride, const uint64_t* timestamps_ns,
                                vslam_frame_out* outs);
+
+/* Classic mode only: the sub-pixel right coordinate (mvuRight) and depth (mvDepth) of every LEFT keypoint of frame
+ * `index` of the most recent process* call, -1 where the keypoint has no stereo match.  u_right[capacity], depth[capacity]. */
+int vslam_classic_stereo_extra(vslam_handle h, int index, float* u_right, float* depth, int capacity);
+/* Classic mode only (tests): candidates of `image` / `level` after the per-cell FAST as (x, y, response) triples. */
+int vslam_debug_classic_candidates(vslam_handle h, int image, int level, int32_t* xyr, int capacity, int* n_out);
 
 /* ---- the pieces of process(), individually --------------------------------------------------------------- */
 /* detect_features: ORB keypoints + descriptors of one image.  kps[capacity], desc[capacity][32]. */

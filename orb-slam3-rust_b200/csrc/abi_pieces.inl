@@ -765,4 +765,61 @@ int vslam_frame_bf_match_crosscheck(vslam_handle h, int query_frame_id, int trai
 
 float vslam_last_search_ms(vslam_handle h) { return h ? h->last_search_ms : 0.f; }
 
+// ---- classic mode accessors (NOT reference parity; include/vslam_b200.h)
+static Slot* slot_of_last_call(vslam_handle h, int index) {
+  for (int k = 0; k < h->nslot; ++k) {
+    Slot& s = h->slots[k];
+    if (!s.busy && s.frames > 0 && s.serial == h->call_serial && h->call_serial > 0 && index >= s.first_frame &&
+        index < s.first_frame + s.frames)
+      return &s;
+  }
+  return nullptr;
+}
+
+int vslam_classic_stereo_extra(vslam_handle h, int index, float* u_right, float* depth, int capacity) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (!h->classic) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "the handle was not created with VSLAM_MODE_CLASSIC");
+  if (!u_right || !depth || capacity < 0) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  Slot* s = slot_of_last_call(h, index);
+  if (!s) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "frame %d of the last process call is no longer resident", index);
+  const int f = index - s->first_frame;
+  const int n = std::min(s->h_lay.hdr[f].n_kp[0], h->kp_cap);
+  if (capacity < n) return fail(h, VSLAM_ERR_CAPACITY, "capacity %d < %d left keypoints", capacity, n);
+  DEVICE_SCOPE(h);
+  if (n > 0) {
+    CU_TRY(h, cudaMemcpy(u_right, s->d_uright + (size_t)f * h->kp_cap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(depth, s->d_depth + (size_t)f * h->kp_cap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  return VSLAM_OK;
+}
+
+int vslam_debug_classic_candidates(vslam_handle h, int image, int level, int32_t* xyr, int capacity, int* n_out) {
+  if (!h) return VSLAM_ERR_INVALID_ARGUMENT;
+  if (!h->classic) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "the handle was not created with VSLAM_MODE_CLASSIC");
+  if (!xyr || !n_out || level < 0 || level >= h->P.nlevels || image < 0 || image >= h->last_frames * h->last_eyes)
+    return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad debug_classic_candidates argument");
+  DEVICE_SCOPE(h);
+  Slot& s = h->slots[h->last_slot];
+  const vk::CLevel& CL = h->CP.lv[level];
+  std::vector<int> cnt((size_t)std::max(CL.ncells, 1));
+  CU_TRY(h, cudaMemcpy(cnt.data(), s.d_ccell_cnt + (size_t)image * h->CP.total_cells + CL.cell0, sizeof(int) * CL.ncells,
+                       cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> rec((size_t)std::max(CL.rec_cap, 1));
+  CU_TRY(h, cudaMemcpy(rec.data(), s.d_ccell_rec + (size_t)image * (size_t)h->CP.rec_img_stride + CL.rec_off,
+                       sizeof(uint32_t) * CL.rec_cap, cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int c = 0; c < CL.ncells; ++c) {
+    const vk::CCell& cc = h->ccells[CL.cell0 + c];
+    for (int i = 0; i < cnt[c]; ++i, ++n) {
+      if (n >= capacity) continue;
+      const uint32_t r = rec[(size_t)cc.rec_off + i];
+      xyr[3 * n] = (int)(r & 0xfffu);
+      xyr[3 * n + 1] = (int)((r >> 12) & 0xfffu);
+      xyr[3 * n + 2] = (int)(r >> 24);
+    }
+  }
+  *n_out = n;
+  return n > capacity ? fail(h, VSLAM_ERR_CAPACITY, "candidate buffer too small (%d > %d)", n, capacity) : VSLAM_OK;
+}
+
 }  // extern "C"

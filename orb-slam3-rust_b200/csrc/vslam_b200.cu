@@ -26,6 +26,7 @@
 #include "stereo_kernels.cuh"
 #include "track_kernels.cuh"
 #include "tri_kernels.cuh"
+#include "classic_kernels.cuh"
 #include "vslam_params.h"
 
 namespace {
@@ -55,6 +56,13 @@ struct Slot {
   int* d_lvl_cnt = nullptr;
   unsigned char* d_res = nullptr;  // one block, carved into the SoA result arrays (d_lay)
   FrameLayout d_lay;
+  // classic mode (VSLAM_MODE_CLASSIC) scratch: per-cell candidates, quadtree keys / node ids, refined stereo outputs
+  int* d_ccell_cnt = nullptr;
+  uint32_t* d_ccell_rec = nullptr;
+  unsigned long long* d_ckeys = nullptr;
+  uint32_t* d_cnode = nullptr;
+  float* d_uright = nullptr;
+  float* d_depth = nullptr;
   vk::BriefMaps maps;              // TMA tensor maps of this slot's blurred / pyramid slabs (k_brief_tma)
   int2* d_ml = nullptr;
   uint8_t* h_in = nullptr;         // pinned
@@ -149,6 +157,14 @@ struct vslam_handle_s {
   uint64_t call_serial = 0;   // incremented by every process* call; slots remember the call that filled them
   // single-pair latency path (vslam_process): H2D, the 14-launch chain with its forked blur stream and the D2H copies of
   // one stereo pair captured once into a CUDA graph over slot 0's fixed staging buffers (VSLAM_GRAPH=0 disables)
+  // classic mode tables
+  bool classic = false;
+  vk::ClassicP CP;
+  std::vector<vk::CCell> ccells;
+  vk::CCell* d_ccells = nullptr;
+  int quad_ncap = 0;
+  size_t cstereo_smem = 0;
+  int cstereo_band = 9;
   bool use_graph = true;
   cudaGraphExec_t pair_graph = nullptr;
   uint64_t pair_graph_kernels = 0;
@@ -196,13 +212,14 @@ struct DeviceGuard {
 
 // The dynamic shared-memory opt-in is a per-function, per-device attribute shared by every handle of the process:
 // only ever raise it, so that handles created for smaller images do not shrink what an older handle's launches need.
-enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_RTILE, SMEM_RTILE_WIDE, SMEM_SELF, SMEM_NFUNC };
+enum { SMEM_FAST = 0, SMEM_SEL1, SMEM_SEL2, SMEM_MATCH_ROWS, SMEM_RTILE, SMEM_RTILE_WIDE, SMEM_SELF, SMEM_QUAD, SMEM_CSTEREO, SMEM_NFUNC };
 cudaError_t raise_smem_limit(int device, int which, size_t want) {
   static std::mutex mu;
   static size_t cur_dev[64][SMEM_NFUNC] = {{0}};
   const void* fn[SMEM_NFUNC] = {(const void*)vk::k_fast, (const void*)vk::k_select1, (const void*)vk::k_select2,
                                 (const void*)vk::k_match_rows, (const void*)vk::k_resize_tile<false>,
-                                (const void*)vk::k_resize_tile<true>, (const void*)vk::k_select_fused};
+                                (const void*)vk::k_resize_tile<true>, (const void*)vk::k_select_fused,
+                                (const void*)vk::k_quadtree, (const void*)vk::k_cstereo};
   std::lock_guard<std::mutex> lock(mu);
   size_t& cur = cur_dev[device & 63][which];
   if (want <= cur) return cudaSuccess;
@@ -340,7 +357,8 @@ int build_params(vslam_handle h) {
   size_t pyr_off = 0, blur_off = 0, ncoef = 0;
   long long rec_off = 0;
   int strip0 = 0, tile0 = 0;
-  const int eb = std::max(c.edge_threshold, 4);
+  // classic mode: keypoints live >= 19 px (EDGE_THRESHOLD) from the border, so the rings the dense kernels may skip shrink
+  const int eb = h->classic ? vk::kCEdge : std::max(c.edge_threshold, 4);
   for (int l = 0; l < P.nlevels; ++l) {
     LevelP& L = P.lv[l];
     float scale = (float)std::pow(sf, (double)l);
@@ -421,6 +439,61 @@ int build_params(vslam_handle h) {
       nd *= factor;
     }
     P.lv[P.nlevels - 1].nfeat = std::max(c.n_features - sum, 0);
+  }
+  if (h->classic) {
+    // cell tables of ComputeKeyPointsOctTree (oracle/classic_model.cpp: classic_cells) and the quadtree roots
+    vk::ClassicP& CP = h->CP;
+    memset(&CP, 0, sizeof(CP));
+    CP.ini_th = c.classic_ini_fast;
+    CP.min_th = c.classic_min_fast;
+    h->ccells.clear();
+    long long rec = 0;
+    int maxn = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+      const LevelP& L = P.lv[l];
+      vk::CLevel& CL = CP.lv[l];
+      const int minB = vk::kCEdge - 3, maxBX = L.w - vk::kCEdge + 3, maxBY = L.h - vk::kCEdge + 3;
+      if (maxBX - minB < 8 || maxBY - minB < 8)
+        return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "classic mode: pyramid level %d is too small (%dx%d)", l, L.w, L.h);
+      const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+      const int nCols = std::max((int)(width / vk::kCCell), 1), nRows = std::max((int)(height / vk::kCCell), 1);
+      const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+      CL.cell0 = (int)h->ccells.size();
+      CL.rec_off = (int)rec;
+      int lrec = 0;
+      for (int i = 0; i < nRows; ++i) {
+        const int iniY = minB + i * hCell;
+        int maxY = iniY + hCell + 6;
+        if (iniY >= maxBY - 3) continue;
+        if (maxY > maxBY) maxY = maxBY;
+        for (int j = 0; j < nCols; ++j) {
+          const int iniX = minB + j * wCell;
+          int maxX = iniX + wCell + 6;
+          if (iniX >= maxBX - 6) continue;
+          if (maxX > maxBX) maxX = maxBX;
+          const int x0 = iniX + 3, x1 = maxX - 3, y0 = iniY + 3, y1 = maxY - 3;
+          if (x1 <= x0 || y1 <= y0) continue;
+          vk::CCell cc;
+          cc.x0 = (short)x0; cc.x1 = (short)x1; cc.y0 = (short)y0; cc.y1 = (short)y1;
+          cc.rec_off = lrec;
+          cc.cap = ((x1 - x0 + 1) / 2) * ((y1 - y0 + 1) / 2);
+          lrec += cc.cap;
+          h->ccells.push_back(cc);
+        }
+      }
+      CL.ncells = (int)h->ccells.size() - CL.cell0;
+      CL.rec_cap = lrec;
+      rec += lrec;
+      CL.W = maxBX - minB;
+      CL.H = maxBY - minB;
+      CL.nini = std::max((int)std::round((float)CL.W / (float)CL.H), 1);
+      CL.hx = (float)CL.W / (float)CL.nini;
+      maxn = std::max(maxn, P.lv[l].nfeat);
+    }
+    CP.total_cells = (int)h->ccells.size();
+    CP.rec_img_stride = (rec + 1) & ~1LL;
+    h->quad_ncap = (maxn + 16 + 7) & ~7;
+    h->cstereo_band = (int)std::ceil(2.0f * P.lv[P.nlevels - 1].scale) + 2;
   }
   // resize coefficient table
   h->coef.assign(std::max<size_t>(ncoef, 1), 0);
@@ -553,12 +626,22 @@ int alloc_slot(vslam_handle h, Slot& s) {
   CU_TRY(h, cudaMalloc(&s.d_in, nimg * h->in_img_bytes));
   CU_TRY(h, cudaMalloc(&s.d_pyr, nimg * (size_t)P.pyr_img_stride));
   CU_TRY(h, cudaMalloc(&s.d_blur, nimg * (size_t)P.blur_img_stride));
-  CU_TRY(h, cudaMalloc(&s.d_strip_cnt, nimg * std::max(P.total_fast_strips, 1) * sizeof(int)));
-  CU_TRY(h, cudaMalloc(&s.d_strip_rec, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
-  CU_TRY(h, cudaMalloc(&s.d_sel1, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
-  CU_TRY(h, cudaMalloc(&s.d_sel1_cnt, nimg * P.nlevels * sizeof(int)));
-  CU_TRY(h, cudaMalloc(&s.d_cand, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(vrec_t)));
-  CU_TRY(h, cudaMalloc(&s.d_glists, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * 2 * sizeof(uint32_t)));
+  if (!h->classic) {
+    CU_TRY(h, cudaMalloc(&s.d_strip_cnt, nimg * std::max(P.total_fast_strips, 1) * sizeof(int)));
+    CU_TRY(h, cudaMalloc(&s.d_strip_rec, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
+    CU_TRY(h, cudaMalloc(&s.d_sel1, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(uint32_t)));
+    CU_TRY(h, cudaMalloc(&s.d_sel1_cnt, nimg * P.nlevels * sizeof(int)));
+    CU_TRY(h, cudaMalloc(&s.d_cand, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * sizeof(vrec_t)));
+    CU_TRY(h, cudaMalloc(&s.d_glists, nimg * std::max<size_t>((size_t)P.rec_img_stride, 2) * 2 * sizeof(uint32_t)));
+  } else {
+    const size_t rs = std::max<size_t>((size_t)h->CP.rec_img_stride, 2);
+    CU_TRY(h, cudaMalloc(&s.d_ccell_cnt, nimg * (size_t)std::max(h->CP.total_cells, 1) * sizeof(int)));
+    CU_TRY(h, cudaMalloc(&s.d_ccell_rec, nimg * rs * sizeof(uint32_t)));
+    CU_TRY(h, cudaMalloc(&s.d_ckeys, nimg * rs * sizeof(unsigned long long)));
+    CU_TRY(h, cudaMalloc(&s.d_cnode, nimg * rs * sizeof(uint32_t)));
+    CU_TRY(h, cudaMalloc(&s.d_uright, nfr * (size_t)h->kp_cap * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&s.d_depth, nfr * (size_t)h->kp_cap * sizeof(float)));
+  }
   CU_TRY(h, cudaMalloc(&s.d_lvl_kp, nimg * P.nlevels * (size_t)h->kp_cap * sizeof(vk::LvlKp)));
   CU_TRY(h, cudaMalloc(&s.d_lvl_cnt, nimg * P.nlevels * sizeof(int)));
   FrameLayout tmp;
@@ -588,6 +671,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_in); cudaFree(s.d_pyr); cudaFree(s.d_blur); cudaFree(s.d_strip_cnt); cudaFree(s.d_strip_rec);
   cudaFree(s.d_sel1); cudaFree(s.d_sel1_cnt); cudaFree(s.d_cand);
   cudaFree(s.d_glists); cudaFree(s.d_lvl_kp); cudaFree(s.d_lvl_cnt); cudaFree(s.d_res); cudaFree(s.d_ml);
+  cudaFree(s.d_ccell_cnt); cudaFree(s.d_ccell_rec); cudaFree(s.d_ckeys); cudaFree(s.d_cnode); cudaFree(s.d_uright); cudaFree(s.d_depth);
   if (s.h_in) cudaFreeHost(s.h_in);
   if (s.h_res) cudaFreeHost(s.h_res);
   if (s.done) cudaEventDestroy(s.done);
@@ -645,6 +729,54 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     h->launches++;
   }
   mark();  // 1
+  if (h->classic) {
+    // classic mode (NOT reference parity): per-cell FAST -> quadtree -> blur -> BRIEF -> row-band / SAD / parabola stereo.
+    // The score maps live in the blurred slab until the quadtree is done, so the blur follows on the same stream.
+    for (int l = 0; l < P.nlevels; ++l) {
+      const int nwx = ((P.lv[l].w - vk::kCEdge + 3) >> 2) - ((vk::kCEdge & ~3) >> 2), rows = P.lv[l].h - 2 * vk::kCEdge;
+      if (nwx <= 0 || rows <= 0) continue;
+      vk::k_cfast_score<<<dim3((nwx * rows + 255) / 256, nimg), 256, 0, st>>>(P, l, h->CP.min_th, in_l, in_r, s.d_pyr, s.d_blur);
+      h->launches++;
+    }
+    vk::k_cell_select<<<dim3((h->CP.total_cells + 3) / 4, nimg), 128, 0, st>>>(P, h->CP, h->d_ccells, s.d_blur, s.d_ccell_cnt,
+                                                                         s.d_ccell_rec);
+    h->launches++;
+    mark();  // 2
+    vk::k_quadtree<<<dim3(nimg, P.nlevels), 256, vk::quadtree_smem_bytes(h->quad_ncap), st>>>(
+        P, h->CP, h->quad_ncap, h->d_ccells, s.d_ccell_cnt, s.d_ccell_rec, s.d_ckeys, s.d_cnode, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    h->launches++;
+    mark();  // 3
+    vk::k_blur<<<blur_grid(h, nimg), 128, 0, st>>>(P, nimg, in_l, in_r, s.d_pyr, s.d_blur);
+    h->launches++;
+    mark();  // 4
+    vk::k_brief<<<dim3((P.kp_cap + vk::kBriefWarps - 1) / vk::kBriefWarps, nimg), 32 * vk::kBriefWarps, 0, st>>>(
+        P, in_l, in_r, s.d_pyr, s.d_blur, s.d_lvl_kp, s.d_lvl_cnt, s.d_lay);
+    h->launches++;
+    mark();  // 5
+    if (eyes == 2) {
+      vk::CStereoP CS;
+      CS.mbf = (float)(h->cfg.camera.fx * h->cfg.camera.baseline);
+      CS.mb = (float)h->cfg.camera.baseline;
+      CS.fx = h->cfg.camera.fx; CS.fy = h->cfg.camera.fy; CS.cx = h->cfg.camera.cx; CS.cy = h->cfg.camera.cy;
+      vk::k_cstereo<<<frames, 1024, h->cstereo_smem, st>>>(P, s.d_lay, CS, h->cfg.height, h->cstereo_band, in_l, in_r, s.d_pyr,
+                                                           s.d_uright, s.d_depth);
+      h->launches++;
+    }
+    mark();  // 6
+    CU_TRY(h, cudaGetLastError());
+    if (prof) {
+      CU_TRY(h, cudaStreamSynchronize(st));
+      float total = 0.f;
+      for (int i = 0; i < 6; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+        h->stage_ms[i] += ms;
+        total += ms;
+      }
+      h->stage_ms[6] += total;
+    }
+    return VSLAM_OK;
+  }
   // The blur only needs the pyramid: outside profiling it runs on the slot's second stream, overlapping the
   // latency-bound selection chain (k_select1/k_harris/k_select2 keep the SMs mostly idle).
   const bool fork = !prof;
@@ -1118,6 +1250,14 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (c.edge_threshold == 0) c.edge_threshold = 31;
   if (c.fast_threshold == 0) c.fast_threshold = 20;
   if (c.max_batch == 0) c.max_batch = 64;
+  if (c.mode != VSLAM_MODE_REFERENCE && c.mode != VSLAM_MODE_CLASSIC)
+    return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "unknown mode %d", c.mode);
+  if (c.classic_ini_fast == 0) c.classic_ini_fast = 20;
+  if (c.classic_min_fast == 0) c.classic_min_fast = 7;
+  if (c.mode == VSLAM_MODE_CLASSIC &&
+      (c.classic_min_fast < 1 || c.classic_ini_fast < c.classic_min_fast || c.classic_ini_fast > 127 || c.n_features > 5000))
+    return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT,
+                "classic mode: need 1 <= min_fast <= ini_fast <= 127 and n_features <= 5000");
   if (c.width < 64 || c.height < 64 || c.width > 4096 || c.height > 2100)  // corner records pack x,y in 12 bits
     return fail(nullptr, VSLAM_ERR_INVALID_ARGUMENT, "unsupported image size %dx%d", c.width, c.height);
   if (c.n_features < 1 || c.n_features > 60000)
@@ -1147,6 +1287,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
 
   vslam_handle h = new vslam_handle_s();
   h->cfg = c;
+  h->classic = c.mode == VSLAM_MODE_CLASSIC;
   h->max_batch = c.max_batch;
   h->sm_count = prop.multiProcessorCount;
   h->kp_cap = c.keypoint_capacity > 0 ? c.keypoint_capacity : c.n_features + std::max(c.n_features / 8, 64);
@@ -1181,6 +1322,15 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     return bail(VSLAM_ERR_CUDA);
   }
   if (upload_tables(h) != VSLAM_OK) return bail(VSLAM_ERR_CUDA);
+  if (h->classic) {
+    const size_t nb = std::max<size_t>(h->ccells.size(), 1) * sizeof(vk::CCell);
+    if (cudaMalloc(&h->d_ccells, nb) != cudaSuccess ||
+        cudaMemcpy(h->d_ccells, h->ccells.data(), h->ccells.size() * sizeof(vk::CCell), cudaMemcpyHostToDevice) != cudaSuccess) {
+      fail(h, VSLAM_ERR_CUDA, "classic cell table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return bail(VSLAM_ERR_CUDA);
+    }
+    h->cstereo_smem = vk::cstereo_smem_bytes(h->kp_cap, c.height);
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   cudaEventCreate(&h->ev_batch[0]);
   cudaEventCreate(&h->ev_batch[1]);
@@ -1206,7 +1356,13 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     if (rt > lim) h->resize_tile = false;  // extreme widths x scale factors: the ring kernel has no such limit
     const size_t want[SMEM_NFUNC] = {h->fast_smem, max_sel1, vk::select2_smem_bytes(h->sel2_cap), h->match_rows_smem,
                                      h->resize_tile ? rt : 0, h->resize_tile ? rt : 0,
-                                     vk::select_fused_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency), h->sel2_cap)};
+                                     vk::select_fused_smem_bytes(std::max(h->sel1_cap, h->sel1_cap_latency), h->sel2_cap),
+                                     h->classic ? vk::quadtree_smem_bytes(h->quad_ncap) : 0, h->classic ? h->cstereo_smem : 0};
+    if (h->classic && (want[SMEM_QUAD] > lim || want[SMEM_CSTEREO] > lim)) {
+      fail(h, VSLAM_ERR_INVALID_ARGUMENT, "classic mode: %zu / %zu bytes of shared memory exceed the device limit %zu",
+           want[SMEM_QUAD], want[SMEM_CSTEREO], lim);
+      return bail(VSLAM_ERR_INVALID_ARGUMENT);
+    }
     for (int i = 0; i < SMEM_NFUNC; ++i) {
       e = raise_smem_limit(c.device, i, want[i]);
       if (e != cudaSuccess) {
@@ -1234,6 +1390,7 @@ void vslam_destroy(vslam_handle h) {
   DeviceGuard guard(h->cfg.device);
   for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
   if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
+  cudaFree(h->d_ccells);
   cudaFree(h->d_coef);
   cudaFree(h->arena_base);
   for (auto& r : h->retained) {
@@ -1372,6 +1529,7 @@ int vslam_debug_fast_corners(vslam_handle h, int image, int level, int32_t* xys,
     return h ? fail(h, VSLAM_ERR_INVALID_ARGUMENT, "bad debug_fast_corners argument") : VSLAM_ERR_INVALID_ARGUMENT;
   const PyrP& P = h->P;
   const LevelP& L = P.lv[level];
+  if (h->classic) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "debug_fast_corners is a reference-mode accessor");
   DEVICE_SCOPE(h);
   Slot& s = h->slots[h->last_slot];
   if (h->last_frames <= 0 || image >= h->last_frames * h->last_eyes)

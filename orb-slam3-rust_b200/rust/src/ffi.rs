@@ -22,7 +22,8 @@ pub struct vslam_camera { pub fx: f64, pub fy: f64, pub cx: f64, pub cy: f64, pu
 pub struct vslam_config {
     pub abi_version: i32, pub width: i32, pub height: i32, pub n_features: i32, pub n_levels: i32,
     pub scale_factor: f32, pub edge_threshold: i32, pub fast_threshold: i32, pub camera: vslam_camera,
-    pub device: i32, pub max_batch: i32, pub keypoint_capacity: i32, pub reserved: [i32; 8],
+    pub device: i32, pub max_batch: i32, pub keypoint_capacity: i32, pub mode: i32, pub classic_ini_fast: i32,
+    pub classic_min_fast: i32, pub reserved: [i32; 5],
 }
 
 #[repr(C)]

@@ -17,6 +17,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_CAPACITY, ERR_KEYPOINT_OVERFLOW, ERR_OUT_OF_MEMORY = range(6)
 STAGE_PYRAMID, STAGE_BLURRED = 0, 1
 SEARCH_LOCAL_MAP, SEARCH_MOTION_MODEL = 0, 1
+MODE_REFERENCE, MODE_CLASSIC = 0, 1
 GRID_COLS, GRID_ROWS = 64, 48
 
 KP_DTYPE = np.dtype(
@@ -37,7 +38,8 @@ class Config(C.Structure):
         ("abi_version", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("n_features", C.c_int32),
         ("n_levels", C.c_int32), ("scale_factor", C.c_float), ("edge_threshold", C.c_int32),
         ("fast_threshold", C.c_int32), ("camera", Camera), ("device", C.c_int32), ("max_batch", C.c_int32),
-        ("keypoint_capacity", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("keypoint_capacity", C.c_int32), ("mode", C.c_int32), ("classic_ini_fast", C.c_int32),
+        ("classic_min_fast", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -71,7 +73,7 @@ SYMBOLS = [
     "vslam_bow_quantize", "vslam_search_for_triangulation", "vslam_search_for_triangulation_bow",
     "vslam_frame_retain", "vslam_frame_upload", "vslam_frame_release", "vslam_frame_num_features",
     "vslam_frame_search_by_projection", "vslam_frame_grid_query", "vslam_frame_bf_match_crosscheck",
-    "vslam_last_search_ms",
+    "vslam_last_search_ms", "vslam_classic_stereo_extra", "vslam_debug_classic_candidates",
 ]
 
 _lib = None
@@ -122,6 +124,8 @@ def lib():
         L.vslam_frame_bf_match_crosscheck.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
         L.vslam_last_search_ms.argtypes = [vp]
         L.vslam_last_search_ms.restype = C.c_float
+        L.vslam_classic_stereo_extra.argtypes = [vp, i32, vp, vp, i32]
+        L.vslam_debug_classic_candidates.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
         L.vslam_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i32)]
         L.vslam_debug_level_image.argtypes = [vp, i32, i32, i32, vp, sz]
         L.vslam_debug_fast_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]

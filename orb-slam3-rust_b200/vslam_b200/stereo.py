@@ -120,7 +120,8 @@ class StereoProcessor:
 
     def __init__(self, camera: CameraModel, n_features: int, width: int = 752, height: int = 480, device: int = 0,
                  max_batch: int = 64, n_levels: int = 8, scale_factor: float = 1.2, edge_threshold: int = 31,
-                 fast_threshold: int = 20, keypoint_capacity: int = 0):
+                 fast_threshold: int = 20, keypoint_capacity: int = 0, mode: str = "reference", classic_ini_fast: int = 0,
+                 classic_min_fast: int = 0):
         self._lib = _abi.lib()
         self._h = C.c_void_p()
         cfg = _abi.Config()
@@ -130,6 +131,12 @@ class StereoProcessor:
         cfg.edge_threshold, cfg.fast_threshold = int(edge_threshold), int(fast_threshold)
         cfg.camera = _abi.Camera(camera.fx, camera.fy, camera.cx, camera.cy, camera.baseline)
         cfg.device, cfg.max_batch, cfg.keypoint_capacity = int(device), int(max_batch), int(keypoint_capacity)
+        if mode not in ("reference", "classic"):
+            raise VslamError(_abi.ERR_INVALID_ARGUMENT, f"unknown mode {mode!r}")
+        # "classic" = upstream-ORB-SLAM3 style per-cell FAST / quadtree / SAD + parabola: NOT reference parity (header)
+        cfg.mode = _abi.MODE_CLASSIC if mode == "classic" else _abi.MODE_REFERENCE
+        cfg.classic_ini_fast, cfg.classic_min_fast = int(classic_ini_fast), int(classic_min_fast)
+        self.mode = mode
         rc = self._lib.vslam_create(C.byref(cfg), C.byref(self._h))
         if rc != _abi.OK:
             msg = self._lib.vslam_last_error(None).decode()
@@ -477,6 +484,26 @@ class StereoProcessor:
         if rc != _abi.OK:
             self._raise(rc)
         return out[: n.value].copy()
+
+    # -- classic mode extras (NOT reference parity; see include/vslam_b200.h)
+    def classic_stereo_extra(self, index=0):
+        """(u_right, depth) float32 per left keypoint of frame `index` of the last process* call; -1 = no stereo match."""
+        ur = np.full(self.capacity, -1, dtype=np.float32)
+        dp = np.full(self.capacity, -1, dtype=np.float32)
+        rc = self._lib.vslam_classic_stereo_extra(self._h, int(index), _ptr(ur), _ptr(dp), self.capacity)
+        if rc != _abi.OK:
+            self._raise(rc)
+        return ur, dp
+
+    def debug_classic_candidates(self, image, level):
+        w, h, _, _ = self.level_info(level)
+        cap = w * h // 4 + 1024
+        buf = np.zeros((cap, 3), dtype=np.int32)
+        n = C.c_int(0)
+        rc = self._lib.vslam_debug_classic_candidates(self._h, image, level, _ptr(buf), cap, C.byref(n))
+        if rc != _abi.OK:
+            self._raise(rc)
+        return buf[: n.value].copy()
 
     # -- introspection (parity tests / profiling)
     def level_info(self, level):
