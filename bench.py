@@ -76,6 +76,10 @@ def parse():
                     help="euroc = BASELINE configs[1] (752x480, 1200 features; the headline, default); 720p = configs[2] "
                          "(1280x720, 2000 features) for the resolution sweep; tracking = configs[3]: a synthetic sequence "
                          "through extraction + stereo depth + FeatureGrid + both projection searches (+ ref-KF BFMatcher)")
+    ap.add_argument("--mode", default="reference", choices=["reference", "classic"],
+                    help="reference = what jurmy24/orb-slam3-rust computes (bit-exact parity; the headline); classic = the "
+                         "upstream-ORB-SLAM3 style per-cell FAST / quadtree / SAD + parabola front end north_star also names: "
+                         "NOT reference parity, checked against this repository's own CPU model")
     ap.add_argument("--seq-frames", type=int, default=240, help="frames of the tracking sequence (per replica)")
     a = ap.parse_args()
     if a.workload == "720p":
@@ -156,7 +160,7 @@ def cpu_single_process_profile(lefts, rights, cam, nfeat, frames=24):
 _PAR = None
 
 
-def _parity_init(path, w, h, nfeat):
+def _parity_init(path, w, h, nfeat, mode="reference"):
     global _PAR
     import numpy as np
 
@@ -166,7 +170,7 @@ def _parity_init(path, w, h, nfeat):
         cv2.setNumThreads(1)
     except ImportError:
         pass
-    _PAR = (np.load(path, mmap_mode="r"), w, h, nfeat)
+    _PAR = (np.load(path, mmap_mode="r"), w, h, nfeat, mode)
 
 
 def _parity_worker(args):
@@ -178,8 +182,21 @@ def _parity_worker(args):
     from oracle import orb_oracle as oo
 
     k, cam = args
-    frames, w, h, nfeat = _PAR
+    frames, w, h, nfeat, mode = _PAR
     li, ri = np.ascontiguousarray(frames[0, k]), np.ascontiguousarray(frames[1, k])
+    if mode == "classic":  # NOT reference parity: this repository's own CPU model of the classic mode
+        (kl, dl), (kr, dr) = oo.classic_detect_and_compute(li, nfeat), oo.classic_detect_and_compute(ri, nfeat)
+        mi, od, ur, dp = oo.classic_stereo(kl, dl, kr, dr, li, ri, cam, nfeat)
+        ok = np.flatnonzero(mi >= 0)
+        m = np.zeros(len(ok), dtype=oo.DMATCH_DTYPE)
+        m["query_idx"], m["train_idx"], m["distance"] = ok, mi[ok], od[ok].astype(np.float32)
+        z = dp[ok].astype(np.float64)
+        pts = np.zeros((len(kl), 3), dtype=np.float64)
+        pts[ok] = np.c_[(kl["x"][ok].astype(np.float64) - cam["cx"]) * z / cam["fx"],
+                        (kl["y"][ok].astype(np.float64) - cam["cy"]) * z / cam["fy"], z]
+        valid = (mi >= 0).astype(np.uint8)
+        dig = [hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest() for a in (kl, kr, dl, dr, m, pts, valid)]
+        return k, dig, "classic model", (len(kl), len(kr), len(m))
     try:
         from oracle import cv2_ref
 
@@ -195,7 +212,7 @@ def _parity_worker(args):
     return k, dig, engine, (len(kl), len(kr), len(m))
 
 
-def check_parity(ob, host_l, host_r, idxs, cam, nproc):
+def check_parity(ob, host_l, host_r, idxs, cam, nproc, mode="reference"):
     """Compares the benchmarked frames `idxs` of the e2e pass (result arrays `ob`) bit-for-bit against the CPU reference
     path, computed by `nproc` spawned workers — outside every timed region."""
     import hashlib
@@ -208,7 +225,7 @@ def check_parity(ob, host_l, host_r, idxs, cam, nproc):
     os.close(fd)
     try:
         np.save(path, np.stack([host_l[idxs].numpy(), host_r[idxs].numpy()]))
-        with mp.get_context("spawn").Pool(max(1, nproc), initializer=_parity_init, initargs=(path, W, H, NFEAT)) as pool:
+        with mp.get_context("spawn").Pool(max(1, nproc), initializer=_parity_init, initargs=(path, W, H, NFEAT, mode)) as pool:
             res = pool.map(_parity_worker, [(k, dict(cam)) for k in range(len(idxs))], chunksize=4)
     finally:
         try:
@@ -229,6 +246,8 @@ def check_parity(ob, host_l, host_r, idxs, cam, nproc):
                 bad_fields[n] = bad_fields.get(n, 0) + 1
     against = ("cv2 cv::ORB (the engine the reference calls) + restated match_features/triangulate, bit-exact"
                if engine == "cv2" else "oracle restatement, bit-exact")
+    if mode == "classic":
+        against = "oracle/classic_model.cpp — this repository's own CPU model of the classic mode (NOT reference parity), bit-exact"
     return {"frames_checked": len(idxs), "mismatching_frames": bad, "mismatching_arrays": bad_fields, "against": against}
 
 
@@ -653,7 +672,8 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
 
-    sp = StereoProcessor(cam, NFEAT, W, H, device=local_rank, max_batch=args.batch)
+    sp = StereoProcessor(cam, NFEAT, W, H, device=local_rank, max_batch=args.batch, mode=args.mode)
+    classic = args.mode == "classic"
     img_bytes = W * H
 
     def step_device():
@@ -740,6 +760,8 @@ def main():
     nchunks = (n + args.batch - 1) // args.batch
     names = ["pyramid(k_resize x7)", "k_fast", "k_select x8 (retainBest+Harris+angle)", "k_blur", "k_brief",
              "k_match+k_match_finalize"]
+    if classic:
+        names = ["pyramid(k_resize x7)", "k_cfast_score x8 + k_cell_select", "k_quadtree", "k_blur", "k_brief", "k_cstereo"]
     # algorithmic bytes per IMAGE and stage (SURVEY.md §8 d): pyramid P, FAST P, blur 2P; sparse stages listed apart
     alg = [LEVEL_PIXELS, LEVEL_PIXELS, 2 * NFEAT * 81 + NFEAT * 749, 2 * LEVEL_PIXELS, NFEAT * (512 + 60), NFEAT * 40]
     total_ms = float(stage[6])
@@ -767,14 +789,41 @@ def main():
             traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
     except Exception:
         pass
+    # matching roofline (SURVEY.md 8 d): popc.b32 of the gated pairs / device time of the match stage vs the POPC issue rate
+    matching = None
+    if not classic:
+        try:
+            cam32 = synth.EUROC_CAMERA
+            maxd, mind = np.float32(cam32["fx"] * cam32["baseline"] / 0.1), np.float32(cam32["fx"] * cam32["baseline"] / 40.0)
+            gated = []
+            for i in np.linspace(0, n - 1, 8).astype(int):
+                fr = ob.frame(int(i), copy=False)
+                kl, kr = fr.left_features.keypoints, fr.right_features.keypoints
+                ul, vl, ur, vr = kl["x"][:, None], kl["y"][:, None], kr["x"][None, :], kr["y"][None, :]
+                min_u = np.maximum(ul - maxd, np.float32(0))
+                max_u = np.minimum(ul - mind, np.float32(len(kr)) * ul / np.float32(max(len(kl), 1)))
+                gated.append(int(((np.abs(vl - vr) <= 2) & (ur >= min_u) & (ur <= max_u) & (ul > ur)).sum()))
+            g = float(np.mean(gated))
+            popc_per_step = 8.0 * g * n
+            sm_hz = 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
+            popc_peak = 148 * 4 * 4 * sm_hz  # POPC: one warp instruction per 8 clk per SM sub-partition (tools/ubench/pipe_rates.cu)
+            t_match = float(stage[5]) * 1e-3
+            matching = {"bound": "integer pipe (popc.b32)", "kernel": names[5], "gated_pairs_per_frame": round(g, 1),
+                        "achieved": round(popc_per_step / t_match / 1e9, 2), "peak": round(popc_peak / 1e9, 1),
+                        "unit": "Gpopc.b32/s", "frac": round(popc_per_step / t_match / popc_peak, 5),
+                        "note": "only ~14 of the 1200 right keypoints pass the gates of stereo.rs:117-129 per left keypoint: the "
+                                "kernel is bound by the row-bucket sort, the gate tests and latency, not by POPC"}
+        except Exception as e:
+            matching = {"error": str(e)}
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r01s_summary.md: ALU pipe "
+        "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r02_summary.md: ALU pipe "
                  "63 %, issue 59 %, DRAM 5 %), not by HBM; the HBM fraction is reported because SURVEY.md 8(d) defines "
                  "the roofline in algorithmic bytes"),
         "algorithmic_bytes_per_launch": alg[dom] * images_per_launch, "launch_ms": round(per_launch_ms, 4),
         "stage_ms_per_step": {names[i]: round(float(stage[i]), 3) for i in range(6)}, "stage_share": shares,
+        "matching": matching,
         "extraction_dense": {"stages": "pyramid+FAST+blur", "algorithmic_bytes_per_stereo_frame": 8 * LEVEL_PIXELS,
                              "achieved": round(dense_gbs, 2), "frac": round(dense_gbs / peak, 4)},
     }
@@ -784,7 +833,9 @@ def main():
     if args.parity_frames > 0:
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         idxs = np.array(sorted(set(int(x) for x in np.linspace(0, n - 1, min(args.parity_frames, n)))))
-        parity = check_parity(ob, host_l, host_r, idxs, synth.EUROC_CAMERA, max(1, ncores // world))
+        if classic:  # the model scores every pixel without a pre-test: ~0.4 s per frame per core
+            idxs = idxs[:: max(1, len(idxs) // 32)]
+        parity = check_parity(ob, host_l, host_r, idxs, synth.EUROC_CAMERA, max(1, ncores // world), args.mode)
         if world > 1:  # every rank checks its own frames; rank 0 reports the totals
             parity["frames_checked"] = int(shard.reduce_sum(parity["frames_checked"], dist, dev))
             parity["mismatching_frames"] = int(shard.reduce_sum(parity["mismatching_frames"], dist, dev))
@@ -794,7 +845,10 @@ def main():
     # ranks and the driver runs `--impl reference` itself, so the line carries a note instead)
     cpu = None if world == 1 else {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
                                    "sample": "not measured at N > 1: see the N=1 line / bench.py --impl reference"}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if classic:
+        cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+               "sample": "classic mode has no reference implementation (SURVEY.md 0.1); its CPU model is a checker, not a baseline"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not classic:
         try:
             ref = CpuReference(host_l[: min(n, 64)].numpy(), host_r[: min(n, 64)].numpy(), synth.EUROC_CAMERA)
             nf, wall = ref.run(args.cpu_seconds)
@@ -822,7 +876,8 @@ def main():
     e2e_value = shard.throughput(total_frames, e2e_wall_ms)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC + (" [classic mode: NOT reference parity]" if classic else ""), "value": round(value, 1),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": (f"configs[4]: {frames_all} synthetic {W}x{H} stereo frames in total, frame-sharded over "
