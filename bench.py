@@ -722,7 +722,8 @@ def main():
         o.matches, o.points_cam, o.points_valid = ob.m[i].ctypes.data, ob.pts[i].ctypes.data, ob.valid[i].ctypes.data
     # per frame: 32 B header + min(capacity, n_features) rows of every result array (2-D copies: the tail rows of the
     # [frames][capacity] arrays never cross PCIe)
-    d2h_bytes = n * (32 + min(sp.capacity, NFEAT) * (28 * 2 + 32 * 2 + 16 + 24 + 1))
+    d2h_rows = min(sp.capacity, NFEAT + (24 if args.mode == "classic" else 0))  # classic: + 3 nodes per level (quadtree overshoot)
+    d2h_bytes = n * (32 + d2h_rows * (28 * 2 + 32 * 2 + 16 + 24 + 1))
 
     def step_e2e():
         sp.process_batch_raw(n, lp, rp, W, ob)

@@ -43,71 +43,113 @@ struct ClassicP {
   CLevel lv[VSLAM_MAX_LEVELS];
 };
 
-// ---- S - 1 of every pixel (0 unless S > min_th): thread per aligned 4-pixel word of rows [19, h - 19).
-__global__ void __launch_bounds__(256) k_cfast_score(const __grid_constant__ PyrP P, int l, int min_th,
+// ---- S - 1 of every pixel (0 unless S > min_th).  Block = 256 threads = a tile of 64 aligned 4-pixel words x 16 rows of
+//      rows [19, h - 19): the tile and its 3-row / 1-word apron are staged in shared memory with coalesced loads, every
+//      thread then scores 4 words (rows ty, ty + 4, ty + 8, ty + 12 of column tx).  A word whose four pixels all fail the
+//      byte-SIMD necessary test of k_fast's phase A (one of every antipodal pair {k, k + 8}, k = 0, 2, 4, 6, must differ
+//      from the centre by more than the threshold) skips the exact DPX scoring: its scores are 0 either way.
+constexpr int kCfTW = 64, kCfTH = 16;
+__global__ void __launch_bounds__(256) k_cfast_score(const __grid_constant__ PyrP P, int l, int min_th, int tiles_x,
                                                      const uint8_t* __restrict__ in_l, const uint8_t* __restrict__ in_r,
                                                      const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score) {
+  __shared__ unsigned s_t[kCfTH + 6][kCfTW + 2];
   const LevelP& L = P.lv[l];
   const int img = blockIdx.y;
   const int x_lo = kCEdge & ~3, nwx = ((L.w - kCEdge + 3) >> 2) - (x_lo >> 2);  // words covering [19, w - 19)
   const int rows = L.h - 2 * kCEdge;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (nwx <= 0 || rows <= 0 || idx >= nwx * rows) return;
-  const int ry = idx / nwx, wx = idx - ry * nwx;
-  const int y = kCEdge + ry, x = x_lo + 4 * wx;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int wx0 = tile_x * kCfTW, ry0 = tile_y * kCfTH;
   int pitch;
   const uint8_t* base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
-  unsigned w[7][3];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (size_t)(y - 3 + j) * pitch + x);
-    w[j][0] = q[-1];
-    w[j][1] = q[0];
-    w[j][2] = q[1];
+  const int pw = pitch >> 2;  // words per row (pitch is a multiple of 16)
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(base);
+  for (int i = threadIdx.x; i < (kCfTH + 6) * (kCfTW + 2); i += 256) {
+    const int r = i / (kCfTW + 2), c = i - r * (kCfTW + 2);
+    const int gy = min(kCEdge + ry0 + r - 3, L.h - 1);                     // rows past the level only feed unused words
+    const int gx = min((x_lo >> 2) + wx0 + c - 1, pw - 1);
+    s_t[r][c] = gw[(size_t)gy * pw + gx];
   }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int wx = wx0 + tx;
+  if (wx >= nwx) return;
+  const unsigned t = (unsigned)min_th, t2 = t * 0x00010001u, tadd = (127u - t) * 0x01010101u;
+  for (int k = 0; k < 4; ++k) {
+    const int rr = ty + 4 * k, ry = ry0 + rr;
+    if (ry >= rows) break;
+    unsigned w[7][3];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      w[j][0] = s_t[rr + j][tx];
+      w[j][1] = s_t[rr + j][tx + 1];
+      w[j][2] = s_t[rr + j][tx + 2];
+    }
 #define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
-  unsigned sv[16];
-  sv[0] = shifted4<0>(VS_ROW(3));
-  sv[1] = shifted4<1>(VS_ROW(3));
-  sv[2] = shifted4<2>(VS_ROW(2));
-  sv[3] = shifted4<3>(VS_ROW(1));
-  sv[4] = shifted4<3>(VS_ROW(0));
-  sv[5] = shifted4<3>(VS_ROW(-1));
-  sv[6] = shifted4<2>(VS_ROW(-2));
-  sv[7] = shifted4<1>(VS_ROW(-3));
-  sv[8] = shifted4<0>(VS_ROW(-3));
-  sv[9] = shifted4<-1>(VS_ROW(-3));
-  sv[10] = shifted4<-2>(VS_ROW(-2));
-  sv[11] = shifted4<-3>(VS_ROW(-1));
-  sv[12] = shifted4<-3>(VS_ROW(0));
-  sv[13] = shifted4<-3>(VS_ROW(1));
-  sv[14] = shifted4<-2>(VS_ROW(2));
-  sv[15] = shifted4<-1>(VS_ROW(3));
+    const unsigned cw = w[3][1];
+    unsigned out = 0;
+    {
+      const unsigned a0 = __vabsdiffu4(w[6][1], cw), a8 = __vabsdiffu4(w[0][1], cw);
+      const unsigned a4 = __vabsdiffu4(shifted4<3>(VS_ROW(0)), cw), a12 = __vabsdiffu4(shifted4<-3>(VS_ROW(0)), cw);
+      const unsigned a2 = __vabsdiffu4(shifted4<2>(VS_ROW(2)), cw), a14 = __vabsdiffu4(shifted4<-2>(VS_ROW(2)), cw);
+      const unsigned a6 = __vabsdiffu4(shifted4<2>(VS_ROW(-2)), cw), a10 = __vabsdiffu4(shifted4<-2>(VS_ROW(-2)), cw);
+      // per byte "v > t" as bit 7 of (v + 127 - t) | v (a carry can only add false positives of this necessary test)
+      const unsigned pass = ((a0 + tadd) | a0 | (a8 + tadd) | a8) & ((a4 + tadd) | a4 | (a12 + tadd) | a12) &
+                            ((a2 + tadd) | a2 | (a10 + tadd) | a10) & ((a6 + tadd) | a6 | (a14 + tadd) | a14) & 0x80808080u;
+      if (pass) {
+        unsigned sv[16];
+        sv[0] = shifted4<0>(VS_ROW(3));
+        sv[1] = shifted4<1>(VS_ROW(3));
+        sv[2] = shifted4<2>(VS_ROW(2));
+        sv[3] = shifted4<3>(VS_ROW(1));
+        sv[4] = shifted4<3>(VS_ROW(0));
+        sv[5] = shifted4<3>(VS_ROW(-1));
+        sv[6] = shifted4<2>(VS_ROW(-2));
+        sv[7] = shifted4<1>(VS_ROW(-3));
+        sv[8] = shifted4<0>(VS_ROW(-3));
+        sv[9] = shifted4<-1>(VS_ROW(-3));
+        sv[10] = shifted4<-2>(VS_ROW(-2));
+        sv[11] = shifted4<-3>(VS_ROW(-1));
+        sv[12] = shifted4<-3>(VS_ROW(0));
+        sv[13] = shifted4<-3>(VS_ROW(1));
+        sv[14] = shifted4<-2>(VS_ROW(2));
+        sv[15] = shifted4<-1>(VS_ROW(3));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (!(pass & (half ? 0x80800000u : 0x00008080u))) continue;
+          const unsigned sel = half ? 0x4342u : 0x4140u;
+          unsigned p[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) p[q] = __byte_perm(sv[q], 0u, sel);
+          const unsigned xs = fast_score2(p, __byte_perm(cw, 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
+          const unsigned lo = xs & 0xffffu, hi = xs >> 16;                    // S - 1 = (S - t) + t - 1 where S > t
+          const unsigned b0 = lo ? lo + t - 1u : 0u, b1 = hi ? hi + t - 1u : 0u;
+          out |= (b0 | (b1 << 8)) << (16 * half);
+        }
+      }
+    }
 #undef VS_ROW
-  const unsigned t2 = (unsigned)min_th * 0x00010001u;
-  unsigned out = 0;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const unsigned sel = half ? 0x4342u : 0x4140u;
-    unsigned p[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
-    const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
-    // S - 1 = (S - t) + t - 1 where S > t
-    const unsigned lo = xs & 0xffffu, hi = xs >> 16;
-    const unsigned b0 = lo ? lo + (unsigned)min_th - 1u : 0u, b1 = hi ? hi + (unsigned)min_th - 1u : 0u;
-    out |= (b0 | (b1 << 8)) << (16 * half);
+    // pixels left of 19 / right of w - 19 inside the first / last word are never read by k_cell_select
+    *reinterpret_cast<uint32_t*>(score + (long long)img * P.blur_img_stride + L.blur_off + (size_t)(kCEdge + ry) * L.pitch +
+                                 x_lo + 4 * wx) = out;
   }
-  // pixels left of 19 / right of w - 19 inside the first / last word are never read by k_cell_select
-  *reinterpret_cast<uint32_t*>(score + (long long)img * P.blur_img_stride + L.blur_off + (size_t)y * L.pitch + x) = out;
 }
 
 // ---- per-cell selection: one warp per cell.  Candidates of a cell in raster order into its slot.
+//      The cell's scores are first copied into a zero-padded shared-memory tile with independent word loads (all in
+//      flight at once) — exactly the score buffer cv::FAST would hold for the cell image: everything outside the cell's
+//      interior reads as 0, so the NMS needs no border tests.  A pass then scans the tile's words, queues the pixels that
+//      pass the threshold in raster order (4 ballots per 128 pixels) and runs the 8-neighbour test on full warps, one
+//      queued pixel per lane.
+constexpr int kCellTW = 13;    // tile words per row: <= 41 interior pixels + alignment slack + zero ring
+constexpr int kCellTH = 46;    // tile rows: <= 41 interior rows + zero ring
+constexpr int kCellQ = 448;    // queue entries per warp: the NMS worst case of a 41 x 41 cell is 441
 __global__ void __launch_bounds__(128) k_cell_select(const __grid_constant__ PyrP P, const __grid_constant__ ClassicP CP,
                                                      const CCell* __restrict__ cells, const uint8_t* __restrict__ score,
                                                      int* __restrict__ cell_cnt, uint32_t* __restrict__ cell_rec) {
-  const int img = blockIdx.y, lane = threadIdx.x & 31;
-  const int ci = blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ uint32_t s_tile[4][kCellTH * kCellTW];
+  __shared__ uint32_t s_q[4][kCellQ];
+  const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 4 + warp;
   if (ci >= CP.total_cells) return;
   int l = 0;
   for (int k = 1; k < P.nlevels; ++k)
@@ -117,34 +159,124 @@ __global__ void __launch_bounds__(128) k_cell_select(const __grid_constant__ Pyr
   const uint8_t* sm = score + (long long)img * P.blur_img_stride + L.blur_off;
   const int pitch = L.pitch;
   uint32_t* out = cell_rec + (long long)img * CP.rec_img_stride + CP.lv[l].rec_off + c.rec_off;
+  uint32_t* q = s_q[warp];
+  uint32_t* tile = s_tile[warp];
   const unsigned lt = (1u << lane) - 1u;
+  // tile geometry: tile word (tr, tw) holds pixels x = xa + 4 (tw - 1) .. + 3 of row y = c.y0 + tr - 1; column 0 / the
+  // last column and row 0 / the last row are the zero ring
+  const int xa = c.x0 & ~3, nw = ((c.x1 - 1) >> 2) - (xa >> 2) + 1, nr = c.y1 - c.y0;  // interior words per row, rows
+  const bool fits = nw + 2 <= kCellTW && nr + 2 <= kCellTH;
   int n = 0;
-  for (int pass = 0; pass < 2 && n == 0; ++pass) {
-    const int th = pass == 0 ? CP.ini_th : CP.min_th;
-    for (int y = c.y0; y < c.y1; ++y) {
-      for (int xb = c.x0; xb < c.x1; xb += 32) {
-        const int x = xb + lane;
-        bool keep = false;
-        int s = 0;
-        if (x < c.x1) {
-          const uint8_t* p = sm + (size_t)y * pitch + x;
-          s = p[0];
-          if (s + 1 > th) {
-            // neighbours outside the cell interior read as 0 (cv::FAST sees only the cell image)
-            const bool xl = x > c.x0, xr = x + 1 < c.x1, yu = y > c.y0, yd = y + 1 < c.y1;
-            const int a = xl ? p[-1] : 0, b = xr ? p[1] : 0;
-            const int ul = (yu && xl) ? p[-pitch - 1] : 0, uc = yu ? p[-pitch] : 0, ur = (yu && xr) ? p[-pitch + 1] : 0;
-            const int dl = (yd && xl) ? p[pitch - 1] : 0, dc = yd ? p[pitch] : 0, dr = (yd && xr) ? p[pitch + 1] : 0;
-            keep = s > a && s > b && s > ul && s > uc && s > ur && s > dl && s > dc && s > dr;
+  if (fits) {
+    for (int i = lane; i < (nr + 2) * kCellTW; i += 32) tile[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < nr * nw; i += 32) {
+      const int r = i / nw, w = i - r * nw;
+      const int x = xa + 4 * w;
+      unsigned v = *reinterpret_cast<const uint32_t*>(sm + (size_t)(c.y0 + r) * pitch + x);
+      unsigned keepm = 0;  // bytes inside [c.x0, c.x1)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (x + b >= c.x0 && x + b < c.x1) keepm |= 0xffu << (8 * b);
+      tile[(r + 1) * kCellTW + w + 1] = v & keepm;
+    }
+    __syncwarp();
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tile);
+    for (int pass = 0; pass < 2 && n == 0; ++pass) {
+      const unsigned th = (unsigned)(pass == 0 ? CP.ini_th : CP.min_th);
+      int qn = 0;
+      for (int i0 = 0; i0 < nr * nw; i0 += 32) {  // scan: words in raster order, lane = word
+        const int i = i0 + lane;
+        unsigned v = 0;
+        int r = 0, w = 0;
+        if (i < nr * nw) {
+          r = i / nw;
+          w = i - r * nw;
+          v = tile[(r + 1) * kCellTW + w + 1];
+        }
+        unsigned cnt_before = 0, mine = 0;
+        unsigned mb[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const unsigned sc = (v >> (8 * b)) & 0xffu;
+          const bool cand = sc != 0u && sc + 1u > th;
+          mb[b] = __ballot_sync(VSLAM_FULL, cand);
+          cnt_before += __popc(mb[b] & lt);
+          mine |= cand ? (1u << b) : 0u;
+        }
+        // raster order inside the warp's 128 pixels: lane-major, then byte
+        int pos = qn + (int)cnt_before;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (mine & (1u << b)) {
+            if (pos < kCellQ) q[pos] = (((v >> (8 * b)) & 0xffu) << 24) | ((unsigned)(c.y0 + r) << 12) | (unsigned)(xa + 4 * w + b);
+            ++pos;
           }
+        qn += __popc(mb[0]) + __popc(mb[1]) + __popc(mb[2]) + __popc(mb[3]);
+      }
+      __syncwarp();
+      qn = min(qn, kCellQ);  // (cannot exceed the NMS worst case... of corners, but pre-NMS pixels can: see the fallback)
+      for (int b0 = 0; b0 < qn; b0 += 32) {  // NMS, one queued pixel per lane
+        bool keep = false;
+        uint32_t e = 0;
+        if (b0 + lane < qn) {
+          e = q[b0 + lane];
+          const int x = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xfffu), sc = (int)(e >> 24);
+          const unsigned char* p = tb + ((y - c.y0 + 1) * kCellTW + 1) * 4 + (x - xa);
+          constexpr int RS = kCellTW * 4;
+          keep = sc > p[-1] && sc > p[1] && sc > p[-RS - 1] && sc > p[-RS] && sc > p[-RS + 1] && sc > p[RS - 1] && sc > p[RS] &&
+                 sc > p[RS + 1];
         }
         const unsigned m = __ballot_sync(VSLAM_FULL, keep);
         if (keep) {
           const int pos = n + __popc(m & lt);
-          if (pos < c.cap) out[pos] = ((unsigned)s << 24) | ((unsigned)y << 12) | (unsigned)x;
+          if (pos < c.cap) out[pos] = e;
         }
         n += __popc(m);
       }
+    }
+  }
+  // Pre-NMS pixels can outnumber the queue only on pathological inputs (> 448 pixels above the threshold in one cell);
+  // such a cell — and any cell larger than the tile — takes the direct path: every pixel tested in place.
+  bool direct = !fits;
+  if (fits) {
+    int above = 0;  // pixels above min_th (the larger set) in the tile
+    for (int i = lane; i < nr * nw; i += 32) {
+      const unsigned v = tile[(i / nw + 1) * kCellTW + (i % nw) + 1];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) above += ((v >> (8 * b)) & 0xffu) != 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(VSLAM_FULL, above, o);
+    direct = above > kCellQ;
+  }
+  if (direct) {
+    n = 0;
+    for (int pass = 0; pass < 2 && n == 0; ++pass) {
+      const int th = pass == 0 ? CP.ini_th : CP.min_th;
+      for (int y = c.y0; y < c.y1; ++y)
+        for (int xb = c.x0; xb < c.x1; xb += 32) {
+          const int x = xb + lane;
+          bool keep = false;
+          int sc = 0;
+          if (x < c.x1) {
+            const uint8_t* p = sm + (size_t)y * pitch + x;
+            sc = p[0];
+            if (sc + 1 > th && sc > 0) {
+              const bool xl = x > c.x0, xr = x + 1 < c.x1, yu = y > c.y0, yd = y + 1 < c.y1;
+              const int a = xl ? p[-1] : 0, r = xr ? p[1] : 0;
+              const int ul = (yu && xl) ? p[-pitch - 1] : 0, uc = yu ? p[-pitch] : 0, ur = (yu && xr) ? p[-pitch + 1] : 0;
+              const int dl = (yd && xl) ? p[pitch - 1] : 0, dc = yd ? p[pitch] : 0, dr = (yd && xr) ? p[pitch + 1] : 0;
+              keep = sc > a && sc > r && sc > ul && sc > uc && sc > ur && sc > dl && sc > dc && sc > dr;
+            }
+          }
+          const unsigned m = __ballot_sync(VSLAM_FULL, keep);
+          if (keep) {
+            const int pos = n + __popc(m & lt);
+            if (pos < c.cap) out[pos] = ((unsigned)sc << 24) | ((unsigned)y << 12) | (unsigned)x;
+          }
+          n += __popc(m);
+        }
     }
   }
   if (lane == 0) cell_cnt[(long long)img * CP.total_cells + ci] = min(n, c.cap);

@@ -735,7 +735,8 @@ int enqueue_chunk(vslam_handle h, Slot& s, int frames, int eyes, const uint8_t* 
     for (int l = 0; l < P.nlevels; ++l) {
       const int nwx = ((P.lv[l].w - vk::kCEdge + 3) >> 2) - ((vk::kCEdge & ~3) >> 2), rows = P.lv[l].h - 2 * vk::kCEdge;
       if (nwx <= 0 || rows <= 0) continue;
-      vk::k_cfast_score<<<dim3((nwx * rows + 255) / 256, nimg), 256, 0, st>>>(P, l, h->CP.min_th, in_l, in_r, s.d_pyr, s.d_blur);
+      const int tiles_x = (nwx + vk::kCfTW - 1) / vk::kCfTW, tiles_y = (rows + vk::kCfTH - 1) / vk::kCfTH;
+      vk::k_cfast_score<<<dim3(tiles_x * tiles_y, nimg), 256, 0, st>>>(P, l, h->CP.min_th, tiles_x, in_l, in_r, s.d_pyr, s.d_blur);
       h->launches++;
     }
     vk::k_cell_select<<<dim3((h->CP.total_cells + 3) / 4, nimg), 128, 0, st>>>(P, h->CP, h->d_ccells, s.d_blur, s.d_ccell_cnt,
@@ -997,7 +998,8 @@ int enqueue_result_copies(vslam_handle h, Slot& s, int frames, int eyes, void* c
   // rows = n_features: cv::ORB returns exactly that many keypoints unless responses tie at the cut (retire_slot
   // fetches the extra rows of such a frame), and matches / points never outnumber the left keypoints — the
   // capacity - n_features tail rows (11 % of every array at the default capacity) never cross PCIe.
-  const int rows = std::min(h->kp_cap, h->cfg.n_features);
+  // (classic mode: the quadtree may overshoot a level's quota by up to 3 nodes)
+  const int rows = std::min(h->kp_cap, h->cfg.n_features + (h->classic ? 3 * h->P.nlevels : 0));
   s.rows_copied = rows;
   for (int a = 0; a < 7; ++a) {
     if (eyes == 1 && (a == 1 || a == 3 || a >= 4)) continue;
