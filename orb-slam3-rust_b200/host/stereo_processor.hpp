@@ -18,6 +18,7 @@
 // the value or (status, message) from vslam_last_error().  Nothing here computes on the CPU: without the CUDA
 // library / a B200 every call fails.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -324,6 +325,82 @@ inline Result<std::vector<int32_t>> search_by_projection(StereoProcessor& p, con
   idx.resize(uv.size());
   return idx;
 }
+
+// A tracking Frame whose left features + FeatureGrid stay in HBM (vslam_frame_retain): the searches of
+// track_local_map / track_with_motion_model (tracker.rs:863-923, 1093-1158) and the reference-keyframe BFMatcher
+// (tracker.rs:1001-1010) then move only (u, v) + map-point descriptors up and indices down.  RAII: released on destruction.
+class ResidentFrame {
+ public:
+  // Right after p.process(...): keeps frame `index` of that call (EuRoC grid extent by default, tracking_frame.rs:194-197).
+  static Result<ResidentFrame> retain(StereoProcessor& p, int index = 0, double img_w = 752.0, double img_h = 480.0) {
+    int id = -1;
+    int rc = vslam_frame_retain(p.raw(), index, img_w, img_h, &id);
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+    return ResidentFrame(&p, id, img_w, img_h);
+  }
+  static Result<ResidentFrame> upload(StereoProcessor& p, const FeatureSet& f, double img_w = 752.0, double img_h = 480.0) {
+    int id = -1;
+    int rc = vslam_frame_upload(p.raw(), f.keypoints.data(), reinterpret_cast<const uint8_t*>(f.descriptors.data()),
+                                (int)f.keypoints.size(), img_w, img_h, &id);
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p.raw())};
+    return ResidentFrame(&p, id, img_w, img_h);
+  }
+  ResidentFrame(ResidentFrame&& o) noexcept : p_(o.p_), id_(o.id_), w_(o.w_), h_(o.h_) { o.id_ = -1; }
+  ResidentFrame& operator=(ResidentFrame&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_; id_ = o.id_; w_ = o.w_; h_ = o.h_;
+      o.id_ = -1;
+    }
+    return *this;
+  }
+  ResidentFrame(const ResidentFrame&) = delete;
+  ResidentFrame& operator=(const ResidentFrame&) = delete;
+  ~ResidentFrame() { release(); }
+  int id() const { return id_; }
+  int num_features() const { return vslam_frame_num_features(p_->raw(), id_); }
+
+  Result<std::vector<int32_t>> search_by_projection(const std::vector<std::pair<double, double>>& uv,
+                                                    const std::vector<Descriptor>& mp_desc, SearchMode mode,
+                                                    double radius = 15.0) const {
+    if (uv.size() != mp_desc.size()) return Error{VSLAM_ERR_INVALID_ARGUMENT, "uv / descriptor count mismatch"};
+    vslam_search_params sp;
+    sp.mode = (int)mode;
+    sp.radius = radius;
+    sp.th_high = TH_HIGH;
+    sp.nn_ratio = NN_RATIO;
+    sp.img_w = w_;
+    sp.img_h = h_;
+    sp.bound_w = 2.0 * p_->camera().cx;
+    sp.bound_h = 2.0 * p_->camera().cy;
+    std::vector<int32_t> idx(uv.size() + 1), dist(uv.size() + 1);
+    int rc = vslam_frame_search_by_projection(p_->raw(), id_, reinterpret_cast<const double*>(uv.data()),
+                                              reinterpret_cast<const uint8_t*>(mp_desc.data()), (int)uv.size(), &sp, idx.data(),
+                                              dist.data());
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p_->raw())};
+    idx.resize(uv.size());
+    return idx;
+  }
+  // BFMatcher(NORM_HAMMING, true).train_match(query = this keyframe, train = frame)
+  Result<std::vector<DMatch>> bf_match_crosscheck(const ResidentFrame& train) const {
+    std::vector<DMatch> m((size_t)std::max(num_features(), 1));
+    int n = 0;
+    int rc = vslam_frame_bf_match_crosscheck(p_->raw(), id_, train.id_, m.data(), &n);
+    if (rc != VSLAM_OK) return Error{rc, vslam_last_error(p_->raw())};
+    m.resize((size_t)n);
+    return m;
+  }
+
+ private:
+  ResidentFrame(StereoProcessor* p, int id, double w, double h) : p_(p), id_(id), w_(w), h_(h) {}
+  void release() {
+    if (id_ >= 0 && p_) vslam_frame_release(p_->raw(), id_);
+    id_ = -1;
+  }
+  StereoProcessor* p_ = nullptr;
+  int id_ = -1;
+  double w_ = 752.0, h_ = 480.0;
+};
 
 // OrbVocabulary (src/vocabulary/mod.rs:79-96): the tree as the reference's loader builds it (node 0 = root).  upload()
 // flattens it once for vslam_vocab_upload; transform() mirrors OrbVocabulary::transform (mod.rs:290-331): the descent of

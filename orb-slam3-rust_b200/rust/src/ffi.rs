@@ -41,6 +41,17 @@ pub struct vslam_search_params {
     pub img_w: f64, pub img_h: f64, pub bound_w: f64, pub bound_h: f64,
 }
 
+/// local_mapping/triangulation.rs: F (row-major, built exactly as check_epipolar_constraint :668-680) and the epipole
+/// (:421-428) are computed by the caller with nalgebra; see include/vslam_b200.h.
+#[repr(C)]
+pub struct vslam_tri_params {
+    pub f: [f64; 9], pub epipole: [f64; 2], pub max_dist: u32, pub radius: f32, pub image_width: u32, pub image_height: u32,
+}
+
+pub const VSLAM_MODE_REFERENCE: i32 = 0;
+/// upstream-ORB-SLAM3 style per-cell FAST / quadtree / SAD + parabola: NOT reference parity (include/vslam_b200.h)
+pub const VSLAM_MODE_CLASSIC: i32 = 1;
+
 #[repr(C)]
 pub struct vslam_handle_s { _private: [u8; 0] }
 pub type vslam_handle = *mut vslam_handle_s;
@@ -66,6 +77,29 @@ extern "C" {
                              mp_desc: *const u8, m: c_int, desc_threshold: u32, out_idx: *mut i32, out_dist: *mut i32) -> c_int;
     pub fn vslam_distinctive_descriptors(h: vslam_handle, desc: *const u8, offsets: *const i32, m: c_int,
                                          out_idx: *mut i32) -> c_int;
+    // frames resident in HBM: Frame::from_stereo (tracking_frame.rs:194-215) without re-uploading the features
+    pub fn vslam_frame_retain(h: vslam_handle, index: c_int, img_w: f64, img_h: f64, frame_id: *mut c_int) -> c_int;
+    pub fn vslam_frame_upload(h: vslam_handle, kps: *const vslam_keypoint, desc: *const u8, n: c_int, img_w: f64, img_h: f64,
+                              frame_id: *mut c_int) -> c_int;
+    pub fn vslam_frame_release(h: vslam_handle, frame_id: c_int) -> c_int;
+    pub fn vslam_frame_num_features(h: vslam_handle, frame_id: c_int) -> c_int;
+    pub fn vslam_frame_search_by_projection(h: vslam_handle, frame_id: c_int, uv: *const f64, mp_desc: *const u8, m: c_int,
+                                            params: *const vslam_search_params, out_idx: *mut i32, out_dist: *mut i32) -> c_int;
+    pub fn vslam_frame_grid_query(h: vslam_handle, frame_id: c_int, xyr: *const f64, nq: c_int, out_start: *mut i32,
+                                  out_items: *mut i32, out_capacity: c_int) -> c_int;
+    pub fn vslam_frame_bf_match_crosscheck(h: vslam_handle, query_frame_id: c_int, train_frame_id: c_int,
+                                           matches: *mut vslam_dmatch, n_matches: *mut c_int) -> c_int;
+    // search_for_triangulation / _bow (src/local_mapping/triangulation.rs:401-530, 541-658)
+    pub fn vslam_search_for_triangulation(h: vslam_handle, kp1: *const vslam_keypoint, desc1: *const u8, flags1: *const u8,
+                                          n1: c_int, kp2: *const vslam_keypoint, desc2: *const u8, flags2: *const u8, n2: c_int,
+                                          params: *const vslam_tri_params, out_pairs: *mut i32, n_pairs: *mut c_int) -> c_int;
+    pub fn vslam_search_for_triangulation_bow(h: vslam_handle, kp1: *const vslam_keypoint, desc1: *const u8, flags1: *const u8,
+                                              n1: c_int, kp2: *const vslam_keypoint, desc2: *const u8, flags2: *const u8,
+                                              n2: c_int, params: *const vslam_tri_params, n_groups: c_int, g1_start: *const i32,
+                                              g1_items: *const i32, g2_start: *const i32, g2_items: *const i32,
+                                              out_pairs: *mut i32, n_pairs: *mut c_int) -> c_int;
+    // classic mode only (NOT reference parity): refined right coordinate / depth per left keypoint
+    pub fn vslam_classic_stereo_extra(h: vslam_handle, index: c_int, u_right: *mut f32, depth: *mut f32, capacity: c_int) -> c_int;
     // OrbVocabulary (src/vocabulary/mod.rs): tree flattened once after load_from_text, quantisation per keyframe
     pub fn vslam_vocab_upload(h: vslam_handle, n_nodes: c_int, node_desc: *const u8, child_begin: *const i32,
                               child_ids: *const i32, parent: *const u32, word_id: *const i32) -> c_int;
