@@ -260,17 +260,30 @@ __global__ void __launch_bounds__(1024) k_match_rows(const FrameLayout F, const 
   // ---- match: 8 lanes per left keypoint
   const unsigned* descL = reinterpret_cast<const unsigned*>(F.desc[0] + (long long)frame * F.desc_stride);
   const int sub = tid & 7;
+  // the left keypoint / descriptor of the NEXT round are loaded while the current round is matched (the 10 rounds of a
+  // 1200-keypoint frame would otherwise each expose one global-memory round trip: single-pair latency)
+  float n_ul = 0.f, n_vl = 0.f;
+  uint4 n_a0 = make_uint4(0, 0, 0, 0), n_a1 = make_uint4(0, 0, 0, 0);
+  auto fetch_left = [&](int li) {
+    if (li < nL) {
+      const float* kl = kp_ptr(F, frame, 0, li);
+      n_ul = kl[0];
+      n_vl = kl[1];
+      n_a0 = *reinterpret_cast<const uint4*>(descL + (size_t)li * 8);
+      n_a1 = *reinterpret_cast<const uint4*>(descL + (size_t)li * 8 + 4);
+    }
+  };
+  fetch_left(tid >> 3);
   for (int l0 = 0; l0 < nL; l0 += 128) {
     const int li = l0 + (tid >> 3);
     const bool valid = li < nL;
     unsigned key = (TH << 16) | 0xffffu, second = TH;
+    const float ul = n_ul, vl = n_vl;
+    const uint4 a0 = n_a0, a1 = n_a1;
+    fetch_left(li + 128);
     if (valid) {
-      const float* kl = kp_ptr(F, frame, 0, li);
-      const float ul = kl[0], vl = kl[1];
       const float min_u = fmaxf(__fsub_rn(ul, S.max_disparity), 0.0f);
       const float max_u = fminf(__fsub_rn(ul, S.min_disparity), __fdiv_rn(__fmul_rn((float)nR, ul), (float)nL));
-      const uint4 a0 = *reinterpret_cast<const uint4*>(descL + (size_t)li * 8);
-      const uint4 a1 = *reinterpret_cast<const uint4*>(descL + (size_t)li * 8 + 4);
       const int b0 = min(max((int)floorf(vl - 2.5f), 0), nb - 1);
       const int b1 = min(max((int)floorf(vl + 2.5f), 0), nb - 1);
       const int p1 = s_start[b1 + 1];
