@@ -100,6 +100,15 @@ def _cpu_init(path):
     import numpy as np
 
     cv2.setNumThreads(1)
+    try:  # one worker per core, pinned
+        import multiprocessing as mp
+
+        cores = sorted(os.sched_getaffinity(0))
+        ident = mp.current_process()._identity
+        if ident and cores:
+            os.sched_setaffinity(0, {cores[(ident[0] - 1) % len(cores)]})
+    except Exception:
+        pass
     _FRAMES = np.load(path, mmap_mode="r")  # [2, n, H, W] shared through the page cache
 
 

@@ -69,3 +69,10 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "orb_oracle" not in txt and "liborb_oracle" not in txt and "cv2" not in txt.replace("cv2.abi3", ""), \
                     f"{f} references the oracle / cv2"
+                # the classic mode cites its CPU model (oracle/classic_model.cpp) in comments as its SPECIFICATION; no line
+                # of product code may include, import, link or load anything from oracle/
+                for line in txt.splitlines():
+                    code = line.split("//")[0].split("#")[0] if not line.lstrip().startswith(("#include", "import", "from")) else line
+                    if "oracle" in code:
+                        assert not any(k in code for k in ("#include", "import ", "CDLL", "dlopen", "-l", "from ")), \
+                            f"{f}: product code depends on oracle/: {line.strip()}"

@@ -4,6 +4,9 @@ set -e
 python bench.py > gpurun_out/r02a_bench_n1.json 2> gpurun_out/r02a_err.txt
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02a_bench_reference.json 2>> gpurun_out/r02a_err.txt
 python bench.py --workload 720p --frames 800 --no-cpu-baseline --parity-frames 64 > gpurun_out/r02a_bench_720p.json 2>> gpurun_out/r02a_err.txt
+for b in 16 32; do python bench.py --workload 720p --frames 800 --batch $b --no-cpu-baseline --parity-frames 0 > gpurun_out/r02a_bench_720p_b$b.json 2>> gpurun_out/r02a_err.txt; done
+python bench.py --mode classic --no-cpu-baseline > gpurun_out/r02a_bench_classic.json 2>> gpurun_out/r02a_err.txt
+python bench.py --total-frames 20000 --no-cpu-baseline --parity-frames 64 > gpurun_out/r02a_strong_n1.json 2>> gpurun_out/r02a_err.txt
 python bench.py --workload tracking --steps 3 --warmup 1 > gpurun_out/r02a_bench_tracking.json 2>> gpurun_out/r02a_err.txt
 python bench.py --workload tracking --impl reference --steps 1 --warmup 1 > gpurun_out/r02a_bench_tracking_reference.json 2>> gpurun_out/r02a_err.txt
 python bench.py --frames 256 --steps 1 --warmup 1 --no-cpu-baseline --parity-frames 0 > /dev/null 2>> gpurun_out/r02a_err.txt
