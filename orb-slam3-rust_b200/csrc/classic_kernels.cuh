@@ -626,8 +626,7 @@ __global__ void __launch_bounds__(1024) k_cstereo(const __grid_constant__ PyrP P
         }
       }
     }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) key = min(key, __shfl_xor_sync(VSLAM_FULL, key, o));
+    key = __reduce_min_sync(0xffu << (lane & 24), key);  // the 8 lanes that share this left keypoint
     if (valid && sub == 0) {
       const unsigned best = key >> 16;
       s_match[li] = best < TH_ORB ? (int)(key & 0xffffu) : -1;

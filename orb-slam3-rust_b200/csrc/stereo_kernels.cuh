@@ -306,12 +306,9 @@ __global__ void __launch_bounds__(1024) k_match_rows(const FrameLayout F, const 
       }
     }
     // reduce over the 8 lanes of the group: winner = min key; runner-up = min over everything but the winner
-    unsigned kmin = key;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) kmin = min(kmin, __shfl_xor_sync(VSLAM_FULL, kmin, o));
-    unsigned other = (key == kmin && (key >> 16) < TH) ? second : (key >> 16);
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) other = min(other, __shfl_xor_sync(VSLAM_FULL, other, o));
+    const unsigned gmask = 0xffu << (lane & 24);  // the 8 lanes that share this left keypoint
+    const unsigned kmin = __reduce_min_sync(gmask, key);
+    const unsigned other = __reduce_min_sync(gmask, (key == kmin && (key >> 16) < TH) ? second : (key >> 16));
     if (valid && sub == 0) {
       const unsigned best = kmin >> 16;
       int idx = -1;

@@ -18,6 +18,14 @@ def weak_seeds(rank: int, frames_per_rank: int, unique: int = 0) -> list[int]:
     return [rank * frames_per_rank + (i % nuniq) for i in range(frames_per_rank)]
 
 
+def strong_seeds(rank: int, world: int, total_frames: int, unique: int = 0) -> list[int]:
+    """Strong scaling (BASELINE configs[4]): the fixed frame set 0 .. total_frames-1 split into contiguous per-rank ranges;
+    seed == global frame index (`unique` > 0 cycles that many distinct frames inside the rank's range)."""
+    mine = frame_range(rank, world, total_frames)
+    nuniq = unique or len(mine)
+    return [mine.start + (i % nuniq) for i in range(len(mine))]
+
+
 def reduce_max(x: float, dist=None, device=None) -> float:
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return float(x)

@@ -67,3 +67,8 @@ def test_frame_range_edge_cases():
     assert [len(shard.frame_range(r, 8, 3)) for r in range(8)] == [1, 1, 1, 0, 0, 0, 0, 0]
     assert sum(len(shard.frame_range(r, 4, 20000)) for r in range(4)) == 20000
     assert shard.weak_seeds(3, 4, unique=2) == [12, 13, 12, 13]
+    # strong scaling: the ranks' seeds tile 0 .. total-1 exactly once whatever the world size
+    for world in (1, 2, 3, 8):
+        seeds = [s for r in range(world) for s in shard.strong_seeds(r, world, 20000)]
+        assert seeds == list(range(20000))
+    assert shard.strong_seeds(1, 2, 10, unique=2) == [5, 6, 5, 6, 5]
