@@ -93,6 +93,60 @@ int main(int argc, char** argv) {
         hb = fnv1a(rec, sizeof(rec), hb);
       }
   }
+  // Resident frame (vslam_frame_retain right after process) + local-map search with the frame's own stereo points as the
+  // map (uv = the keypoints' positions shifted by (+3, -2) px) + search_for_triangulation between the two eyes with the
+  // fundamental matrix of a rectified pair (F and the epipole are the caller's job, as in the Rust binding)
+  uint64_t hs = 0, ht = 0;
+  size_t n_found = 0, n_tri = 0;
+  {
+    auto rf = vslam::ResidentFrame::retain(sp.value(), 0);
+    if (!rf) {
+      std::fprintf(stderr, "ResidentFrame::retain failed (%d): %s\n", rf.error().status, rf.error().message.c_str());
+      return 1;
+    }
+    std::vector<std::pair<double, double>> uv;
+    std::vector<vslam::Descriptor> md;
+    for (size_t i = 0; i < f.points_cam.size(); ++i)
+      if (f.points_cam[i].has_value()) {
+        uv.push_back({(double)f.left_features.keypoints[i].x + 3.0, (double)f.left_features.keypoints[i].y - 2.0});
+        md.push_back(f.left_features.descriptors[i]);
+      }
+    auto idx = rf.value().search_by_projection(uv, md, vslam::SearchMode::LocalMap);
+    if (!idx) {
+      std::fprintf(stderr, "search_by_projection failed (%d): %s\n", idx.error().status, idx.error().message.c_str());
+      return 1;
+    }
+    hs = fnv1a(idx.value().data(), idx.value().size() * sizeof(int32_t));
+    for (int32_t v : idx.value()) n_found += v >= 0;
+    vslam::TriangulationGeometry geo{};
+    // F = K^-T [t]x K^-1 with t = (baseline, 0, 0):  only F[1][2] = -b / fy and F[2][1] = b / fy ... written out
+    const double b = cam.baseline;
+    const double Kinv[3][3] = {{1.0 / cam.fx, 0.0, -cam.cx / cam.fx}, {0.0, 1.0 / cam.fy, -cam.cy / cam.fy}, {0.0, 0.0, 1.0}};
+    const double tx[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, -b}, {0.0, b, 0.0}};
+    double tmp[3][3] = {}, F[3][3] = {};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) tmp[i][j] += tx[i][k] * Kinv[k][j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) F[i][j] += Kinv[k][i] * tmp[k][j];
+    for (int i = 0; i < 9; ++i) geo.F[i] = F[i / 3][i % 3];
+    geo.epipole[0] = 1e9;
+    geo.epipole[1] = cam.cy;
+    std::vector<bool> none1(f.left_features.keypoints.size(), false), none2(f.right_features.keypoints.size(), false);
+    auto tri = vslam::search_for_triangulation(sp.value(), f.left_features, none1, none1, f.right_features, none2, geo, 50);
+    if (!tri) {
+      std::fprintf(stderr, "search_for_triangulation failed (%d): %s\n", tri.error().status, tri.error().message.c_str());
+      return 1;
+    }
+    n_tri = tri.value().size();
+    ht = 1469598103934665603ull;
+    for (const auto& pr : tri.value()) {
+      const uint32_t rec[2] = {(uint32_t)pr.first, (uint32_t)pr.second};
+      ht = fnv1a(rec, sizeof(rec), ht);
+    }
+  }
+  std::printf("found=%zu search=%016llx n_tri=%zu tri=%016llx ", n_found, (unsigned long long)hs, n_tri, (unsigned long long)ht);
   std::printf("bow_words=%zu bow_groups=%zu bow=%016llx ", n_words, n_groups, (unsigned long long)hb);
   std::printf("n_left=%zu n_right=%zu n_matches=%zu n_points=%zu kp=%016llx desc=%016llx matches=%016llx area=%zu ts=%llu\n",
               f.left_features.keypoints.size(), f.right_features.keypoints.size(), f.matches_lr.size(), valid,

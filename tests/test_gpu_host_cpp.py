@@ -57,3 +57,27 @@ def test_cpp_host_mirror_end_to_end(tmp_path, oracle, pairs, camera_dict):
             h = fnv1a(np.array([n, i], np.uint32).tobytes(), h)
     assert int(got["bow_words"]) == len(set(word.tolist())) and int(got["bow_groups"]) == len(groups)
     assert int(got["bow"], 16) == h
+    # resident-frame local-map search and search_for_triangulation through the C++ mirror
+    pts, valid = oracle.triangulate(kl, kr, m, camera_dict)
+    good = np.flatnonzero(valid)
+    uv = np.c_[kl["x"][good].astype(np.float64) + 3.0, kl["y"][good].astype(np.float64) - 2.0]
+    oi, _ = oracle.search_by_projection(kl, dl, uv, dl[good], 0)
+    assert int(got["found"]) == int((oi >= 0).sum()) and int(got["found"]) > 300
+    assert int(got["search"], 16) == fnv1a(oi.astype(np.int32).tobytes())
+    cam = camera_dict
+    Kinv = np.array([[1 / cam["fx"], 0, -cam["cx"] / cam["fx"]], [0, 1 / cam["fy"], -cam["cy"] / cam["fy"]], [0, 0, 1]])
+    tx = np.array([[0, 0, 0], [0, 0, -cam["baseline"]], [0, cam["baseline"], 0]])
+    tmp = np.zeros((3, 3))
+    F = np.zeros((3, 3))
+    for i in range(3):  # the same left-to-right accumulation as host_demo.cpp, so F is bit-identical
+        for j in range(3):
+            for k in range(3):
+                tmp[i, j] += tx[i, k] * Kinv[k, j]
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                F[i, j] += Kinv[k, i] * tmp[k, j]
+    P = oracle.tri_params(F, (1e9, cam["cy"]), 50, cam)
+    ref = oracle.search_for_triangulation(kl, dl, np.zeros(len(kl), np.uint8), kr, dr, np.zeros(len(kr), np.uint8), P)
+    assert int(got["n_tri"]) == len(ref) and len(ref) > 300
+    assert int(got["tri"], 16) == fnv1a(ref.astype(np.uint32).tobytes())

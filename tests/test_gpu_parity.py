@@ -780,3 +780,31 @@ def test_brief_tma_variant_is_bit_identical(oracle, pairs, camera_dict, monkeypa
         with StereoProcessor(CameraModel(**camera_dict), 1200, w, h, max_batch=2) as sp:
             fr = sp.process(l, r)
         check_frame(fr, oracle.detect_and_compute(l, 1200), oracle.detect_and_compute(r, 1200), oracle, camera_dict)
+
+
+def test_feature_grid_hard_coded_extent_on_720p_keypoints(sp720, oracle, pairs):
+    """SURVEY 8.C trap 7: Frame::from_stereo hard-codes a 752 x 480 grid extent (tracking_frame.rs:194-197); at 1280 x 720
+    every keypoint beyond x >= 752 or y >= 480 is clamped into the last column / row of cells.  Bug-compatible on the GPU,
+    through the host-buffer and the resident-frame entry points."""
+    left, right = pairs(3, 1280, 720)
+    fr = sp720.process(left, right)
+    kl, dl = fr.left_features.keypoints, fr.left_features.descriptors
+    assert (kl["x"] >= 752).sum() > 300 and (kl["y"] >= 480).sum() > 300
+    cs, items = sp720.grid_build(kl)            # default extent 752 x 480, as the reference
+    ocs, oit = oracle.grid_build(kl)
+    assert np.array_equal(cs, ocs) and np.array_equal(items, oit)
+    last_col = sum(int(ocs[r * 64 + 64] - ocs[r * 64 + 63]) for r in range(48))
+    assert last_col > 300                        # the clamped keypoints pile up in column 63
+    rng = np.random.default_rng(8)
+    q = np.c_[rng.uniform(-40, 1300, 80), rng.uniform(-40, 740, 80), np.full(80, 15.0)]
+    fid = sp720.frame_retain(0)
+    for a, b, (x, y, r) in zip(sp720.grid_query(kl, q), sp720.frame_grid_query(fid, q), q):
+        ref = oracle.grid_query(ocs, oit, x, y, r)
+        assert np.array_equal(a, ref) and np.array_equal(b, ref)
+    src = rng.integers(0, len(kl), 500)
+    uv = np.c_[kl["x"][src] + rng.normal(0, 4, 500), kl["y"][src] + rng.normal(0, 4, 500)].astype(np.float64)
+    for mode in (0, 1):
+        gi, gd = sp720.frame_search_by_projection(fid, uv, dl[src], mode=mode)
+        oi, od = oracle.search_by_projection(kl, dl, uv, dl[src], mode, bound_w=2 * sp720.camera.cx, bound_h=2 * sp720.camera.cy)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    sp720.frame_release(fid)
