@@ -808,3 +808,84 @@ def test_feature_grid_hard_coded_extent_on_720p_keypoints(sp720, oracle, pairs):
         oi, od = oracle.search_by_projection(kl, dl, uv, dl[src], mode, bound_w=2 * sp720.camera.cx, bound_h=2 * sp720.camera.cy)
         assert np.array_equal(gi, oi) and np.array_equal(gd, od)
     sp720.frame_release(fid)
+
+
+# ------------------------------------------------------------------ randomised geometry (both extraction modes) and concurrency
+def _random_configs(seed, n):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        levels = int(rng.integers(3, 9))
+        scale = float(np.float32(rng.choice([1.1, 1.2, 1.25, 1.33, 1.5, 1.7, 2.0])))
+        w, h = int(rng.integers(200, 1000)), int(rng.integers(160, 640))
+        if min(w, h) / scale ** (levels - 1) < 96:  # the smallest level must keep a FAST emission region
+            continue
+        out.append((w, h, int(rng.integers(100, 1600)), levels, scale, int(rng.choice([7, 12, 20, 31]))))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _random_configs(2024, 14), ids=lambda c: "%dx%d_n%d_l%d_s%.2f_t%d" % c)
+def test_random_geometry_matches_oracle(oracle, camera_dict, cfg):
+    """Image sizes, feature counts, level counts, scale factors and FAST thresholds drawn at random: the tile geometry
+    of k_resize_tile / k_fast / k_blur, the per-level quotas and the selection replay change with every one of them.
+    A batch of 3 frames goes through the pipelined entry point (chunks of 2) and the single-pair (CUDA graph) path."""
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    w, h, nfeat, levels, scale, fast_t = cfg
+    ls, rs = [], []
+    for s in (3, 4, 5):
+        l, r = synth.make_stereo_pair(s, w, h)
+        ls.append(l.numpy())
+        rs.append(r.numpy())
+    kw = dict(nlevels=levels, scale_factor=scale, fast_threshold=fast_t)
+    with StereoProcessor(CameraModel(**camera_dict), nfeat, w, h, max_batch=2, n_levels=levels, scale_factor=scale,
+                         fast_threshold=fast_t) as sp:
+        frs = sp.process_batch(np.stack(ls), np.stack(rs))
+        one = sp.process(ls[0], rs[0])
+    for i, fr in enumerate(frs + [one]):
+        l, r = (ls[i], rs[i]) if i < 3 else (ls[0], rs[0])
+        check_frame(fr, oracle.detect_and_compute(l, nfeat, **kw), oracle.detect_and_compute(r, nfeat, **kw), oracle, camera_dict)
+
+
+@pytest.mark.parametrize("cfg", [(640, 427, 700), (333, 301, 400), (905, 511, 1500)], ids=lambda c: "%dx%d_n%d" % c)
+def test_classic_random_sizes_match_model(oracle, camera_dict, cfg):
+    """classic mode (NOT reference parity) at sizes whose cell grids have ragged last rows / columns."""
+    from test_classic_mode import _check_classic
+    from vslam_b200 import CameraModel, StereoProcessor, synth
+
+    w, h, nfeat = cfg
+    l, r = synth.make_stereo_pair(21, w, h)
+    with StereoProcessor(CameraModel(**camera_dict), nfeat, w, h, mode="classic", max_batch=2) as sp:
+        _check_classic(sp, oracle, l.numpy(), r.numpy(), camera_dict, nfeat)
+
+
+def test_two_handles_two_threads(oracle, pairs, camera_dict):
+    """One handle per host thread (the header's threading contract): two handles of different geometry driven from two
+    threads at once — the device-side tables and the per-function shared-memory opt-ins are process-wide state."""
+    import threading
+
+    from vslam_b200 import CameraModel, StereoProcessor
+
+    jobs = [(752, 480, 1200, [pairs(s) for s in (30, 31, 32, 33)]), (640, 427, 600, [pairs(s, 640, 427) for s in (34, 35, 36, 37)])]
+    results, errors = {}, []
+
+    def work(k, w, h, nfeat, frames):
+        try:
+            with StereoProcessor(CameraModel(**camera_dict), nfeat, w, h, max_batch=2) as sp:
+                out = []
+                for _ in range(3):  # interleave single pairs and batches
+                    out = [sp.process(l, r) for l, r in frames[:2]]
+                    out += sp.process_batch(np.stack([f[0] for f in frames[2:]]), np.stack([f[1] for f in frames[2:]]))
+                results[k] = out
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(k, *j)) for k, j in enumerate(jobs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for k, (w, h, nfeat, frames) in enumerate(jobs):
+        for fr, (l, r) in zip(results[k], frames):
+            check_frame(fr, oracle.detect_and_compute(l, nfeat), oracle.detect_and_compute(r, nfeat), oracle, camera_dict)
