@@ -603,6 +603,9 @@ int vslam_frame_retain(vslam_handle h, int index, double img_w, double img_h, in
   vk::k_grid_build<<<1, 1024, 0, st>>>(R.kp, n, grid_params(img_w, img_h), R.cell_start, R.cell_items, R.cell_of);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
+  // The copies run on slot 0's stream.  A frame of slot 0 (every vslam_process call) is protected by stream order; the
+  // result arrays of another slot are rewritten by that slot's own stream on the next call, so wait here.
+  if (src != &h->slots[0]) CU_TRY(h, cudaStreamSynchronize(st));
   R.n = n;
   R.img_w = img_w;
   R.img_h = img_h;

@@ -1124,6 +1124,8 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
   return VSLAM_OK;
 }
 
+constexpr int kGraphUnavailable = -1000;  // internal: run_single_graph could not capture / instantiate
+
 // vslam_process, latency form: one stereo pair through a CUDA graph captured once per handle.  Everything the graph
 // touches has a fixed address (slot 0: device input, scratch and result buffers, pinned result mirror), so the per-call
 // work is: the two H2D copies, one cudaGraphLaunch (14 kernels with the forked blur + the D2H copies), one synchronize,
@@ -1169,18 +1171,17 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
       rc = enqueue_result_copies(h, s, 1, 2, dst);
     } while (false);
     cudaError_t ce = cudaStreamEndCapture(s.stream, &g);
-    if (rc != VSLAM_OK || ce != cudaSuccess || !g) {
-      if (g) cudaGraphDestroy(g);
+    if (rc == VSLAM_OK && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&h->pair_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc != VSLAM_OK || ce != cudaSuccess || !h->pair_graph) {
+      // no graph on this driver / configuration: this handle uses plain stream launches from now on (same kernels);
+      // kGraphUnavailable tells vslam_process to run this very call through that path
       cudaGetLastError();
-      h->use_graph = false;  // fall back to plain stream launches for this handle (same kernels)
-      return rc != VSLAM_OK ? rc : fail(h, VSLAM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    }
-    ce = cudaGraphInstantiate(&h->pair_graph, g, 0);
-    cudaGraphDestroy(g);
-    if (ce != cudaSuccess) {
       h->pair_graph = nullptr;
       h->use_graph = false;
-      return fail(h, VSLAM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      h->launches = l0;
+      cudaStreamSynchronize(s.stream);
+      return kGraphUnavailable;
     }
     h->pair_graph_kernels = h->launches - l0;
     h->launches = l0;
@@ -1412,7 +1413,10 @@ int vslam_process(vslam_handle h, const uint8_t* left, size_t left_stride, const
   if (!left || !right || !out) return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (left_stride < (size_t)h->cfg.width || right_stride < (size_t)h->cfg.width)
     return fail(h, VSLAM_ERR_INVALID_ARGUMENT, "row stride smaller than the image width");
-  if (h->use_graph && !h->profiling) return run_single_graph(h, left, left_stride, right, right_stride, timestamp_ns, out);
+  if (h->use_graph && !h->profiling) {
+    const int rc = run_single_graph(h, left, left_stride, right, right_stride, timestamp_ns, out);
+    if (rc != kGraphUnavailable) return rc;
+  }
   if (left_stride != right_stride) {
     // stage the right image with the left stride semantics by processing through the generic path twice is
     // wasteful; copy rows into the pinned staging instead (handled by run_batch via per-image stride)
