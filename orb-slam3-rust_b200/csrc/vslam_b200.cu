@@ -68,6 +68,11 @@ struct Slot {
   uint8_t* h_in = nullptr;         // pinned
   unsigned char* h_res = nullptr;  // pinned mirror of d_res (h_lay)
   FrameLayout h_lay;
+  // Two carvings of d_res / h_res: for max_batch frames (batch chunks) and for ONE frame (vslam_process: every array of
+  // the frame then sits in one contiguous range, so the whole result is a single D2H copy).  d_lay / h_lay are whichever
+  // the current call uses.
+  FrameLayout d_layN, h_layN, d_lay1, h_lay1;
+  size_t res1_bytes = 0;
   size_t res_bytes = 0;
   bool direct_out = false;         // D2H went straight into the caller's arrays
   // in-flight chunk bookkeeping
@@ -651,8 +656,12 @@ int alloc_slot(vslam_handle h, Slot& s) {
   CU_TRY(h, cudaMallocHost(&s.h_in, nimg * h->in_img_bytes));
   CU_TRY(h, cudaMallocHost(&s.h_res, s.res_bytes));
   CU_TRY(h, cudaMemset(s.d_res, 0, s.res_bytes));
-  carve_results(s.d_res, nfr, h->kp_cap, &s.d_lay);
-  carve_results(s.h_res, nfr, h->kp_cap, &s.h_lay);
+  carve_results(s.d_res, nfr, h->kp_cap, &s.d_layN);
+  carve_results(s.h_res, nfr, h->kp_cap, &s.h_layN);
+  s.res1_bytes = carve_results(s.d_res, 1, h->kp_cap, &s.d_lay1);
+  carve_results(s.h_res, 1, h->kp_cap, &s.h_lay1);
+  s.d_lay = s.d_layN;
+  s.h_lay = s.h_layN;
   memset(&s.maps, 0, sizeof(s.maps));
   for (int l = 0; l < P.nlevels && h->brief_tma; ++l) {
     const LevelP& L = P.lv[l];
@@ -1031,6 +1040,8 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
     for (int i = 0; i < 7; ++i) h->stage_ms[i] = 0.f;
   }
   int chunk = 0;
+  h->slots[0].d_lay = h->slots[0].d_layN;  // (vslam_process switches slot 0 to its one-frame carving)
+  h->slots[0].h_lay = h->slots[0].h_layN;
   CU_TRY(h, cudaEventRecord(h->ev_batch[0], h->slots[0].stream));
   for (int f0 = 0; f0 < n; f0 += h->max_batch, ++chunk) {
     const int frames = std::min(h->max_batch, n - f0);
@@ -1141,6 +1152,8 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
   int rc = retire_slot(h, s, nullptr, nullptr, &first_error);  // never busy here; keeps the invariant explicit
   if (rc != VSLAM_OK) return rc;
   h->call_serial++;
+  s.d_lay = s.d_lay1;  // one-frame carving: the frame's header and arrays are one contiguous range
+  s.h_lay = s.h_lay1;
   // H2D outside the graph: straight from the caller's images when they are page-locked, else through the pinned staging
   for (int e = 0; e < 2; ++e) {
     const uint8_t* src = e ? right : left;
@@ -1165,10 +1178,8 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
     do {
       rc = enqueue_chunk(h, s, 1, 2, s.d_in, s.d_in + ib, (long long)ib, P.in_pitch);
       if (rc != VSLAM_OK) break;
-      if (cudaMemcpyAsync(s.h_lay.hdr, s.d_lay.hdr, sizeof(ResHdr), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) { rc = VSLAM_ERR_CUDA; break; }
-      const FrameLayout& M = s.h_lay;
-      void* dst[7] = {M.kp[0], M.kp[1], M.desc[0], M.desc[1], M.matches, M.pts, M.valid};
-      rc = enqueue_result_copies(h, s, 1, 2, dst);
+      // header + every result array of the frame in ONE copy (eight copy nodes cost ~2 us each on the critical path)
+      if (cudaMemcpyAsync(s.h_res, s.d_res, s.res1_bytes, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) rc = VSLAM_ERR_CUDA;
     } while (false);
     cudaError_t ce = cudaStreamEndCapture(s.stream, &g);
     if (rc == VSLAM_OK && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&h->pair_graph, g, 0);
@@ -1198,6 +1209,7 @@ int run_single_graph(vslam_handle h, const uint8_t* left, size_t lstride, const 
   s.want_results = true;
   s.direct_out = false;
   s.eyes = 2;
+  s.rows_copied = h->kp_cap;  // the single copy carries every row
   h->last_slot = 0;
   h->last_frames = 1;
   h->last_in_l = s.d_in;
