@@ -744,6 +744,19 @@ def main():
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - e0)
     n_matches_total = int(sum(ob.outs[i].n_matches for i in range(n)))
+    # the same call with PAGEABLE images (what a borrowed cv::Mat is): staged through the library's pinned ring by its
+    # helper threads; reported next to the pinned-buffer number, not instead of it
+    pg_l, pg_r = left.cpu().numpy(), right.cpu().numpy()
+    plp = (C.c_void_p * n)(*[pg_l[i].ctypes.data for i in range(n)])
+    prp = (C.c_void_p * n)(*[pg_r[i].ctypes.data for i in range(n)])
+    sp.process_batch_raw(n, plp, prp, W, ob)
+    barrier()
+    g0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        sp.process_batch_raw(n, plp, prp, W, ob)
+    barrier()
+    pageable_wall_ms = 1e3 * (time.perf_counter() - g0) / max(1, min(args.steps, 3))
+    del pg_l, pg_r
 
     # ---------------- config 1 latency: one stereo pair per call through vslam_process (host buffers, default stream
     # order: H2D, 14 kernels, D2H), p50 over 30 calls
@@ -875,6 +888,7 @@ def main():
         return shard.reduce_max(x, dist if world > 1 else None, dev)
 
     dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms = rmax(dev_ms), rmax(wall_ms), rmax(e2e_dev_ms), rmax(e2e_wall_ms)
+    pageable_wall_ms = rmax(pageable_wall_ms)
     p50_frame_ms = rmax(p50_frame_ms)
     frames_all = int(shard.reduce_sum(n, dist if world > 1 else None, dev))  # == n * world (weak) or --total-frames
     total_frames = frames_all * args.steps
@@ -902,7 +916,10 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": 2 * n * img_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step_wall": round(e2e_wall_ms / args.steps, 3),
                     "ms_per_step_device": round(e2e_dev_ms / args.steps, 3), "matches_per_step": n_matches_total,
-                    "api": "vslam_process_batch (C ABI), pinned host images in, pinned host result arrays out"},
+                    "api": "vslam_process_batch (C ABI), pinned host images in, pinned host result arrays out",
+                    "pageable_inputs_value": round(frames_all / (pageable_wall_ms * 1e-3), 1),
+                    "pageable_inputs_note": "same call with pageable images (a borrowed cv::Mat): staged into the pinned ring by "
+                                            "the library's helper threads (VSLAM_STAGING_THREADS)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "parity": parity, "data_gen_s": round(t_gen, 1),
         }

@@ -10,6 +10,7 @@
 // H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c.  Every kernel takes the
 // whole chunk (grid.y = images), so launch latency is amortised over the chunk.  No CPU fallback anywhere.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -17,8 +18,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vslam_b200.h"
@@ -37,6 +41,72 @@ thread_local std::string g_create_error;
 inline int cv_roundf(float v) { return (int)nearbyintf(v); }
 inline int cv_round(double v) { return (int)nearbyint(v); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Helper threads for staging PAGEABLE caller images (the reference hands over borrowed cv::Mat data) into the pinned
+// ring: one host thread copies ~10-20 GB/s, a 2000-frame batch needs 1.44 GB per 23 ms.  parallel_for(n, f) runs f(i)
+// for i in [0, n) on the pool and the calling thread and returns when all are done.
+class StagingPool {
+ public:
+  explicit StagingPool(int nthreads) {
+    for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~StagingPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void parallel_for(int n, const std::function<void(int)>& f) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &f;
+      next_ = 0;
+      total_ = n;
+      pending_ = n;
+    }
+    cv_.notify_all();
+    run_some();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run_some() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!fn_ || next_ >= total_) return;
+        i = next_++;
+        f = fn_;
+      }
+      (*f)(i);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < total_); });
+        if (stop_) return;
+      }
+      run_some();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, pending_ = 0;
+  bool stop_ = false;
+};
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -159,6 +229,8 @@ struct vslam_handle_s {
     double img_w = 0, img_h = 0;
   };
   std::vector<Retained> retained;
+  StagingPool* pool = nullptr;  // created on the first pageable batch chunk (VSLAM_STAGING_THREADS, default min(8, cores/2))
+  int staging_threads = -1;
   uint64_t call_serial = 0;   // incremented by every process* call; slots remember the call that filled them
   // single-pair latency path (vslam_process): H2D, the 14-launch chain with its forked blur stream and the D2H copies of
   // one stereo pair captured once into a CUDA graph over slot 0's fixed staging buffers (VSLAM_GRAPH=0 disables)
@@ -1080,10 +1152,27 @@ int run_batch_impl(vslam_handle h, int n, int eyes, const uint8_t* const* left, 
                                           s.stream));
           }
         } else {
-          for (int f = 0; f < frames; ++f) {
-            if (stride == (size_t)P.in_pitch) memcpy(hst + (size_t)f * ib, src[f], ib);
+          // pageable images (borrowed cv::Mat data): staged through the slot's pinned buffer, several host threads at once
+          const int in_pitch = P.in_pitch;
+          auto stage_one = [&, hst, src, ib, in_pitch](int f) {
+            if (stride == (size_t)in_pitch) memcpy(hst + (size_t)f * ib, src[f], ib);
             else
-              for (int y = 0; y < H; ++y) memcpy(hst + (size_t)f * ib + (size_t)y * P.in_pitch, src[f] + (size_t)y * stride, W);
+              for (int y = 0; y < H; ++y) memcpy(hst + (size_t)f * ib + (size_t)y * in_pitch, src[f] + (size_t)y * stride, W);
+          };
+          if (frames >= 8 && h->staging_threads != 0) {
+            if (!h->pool) {
+              int nt = h->staging_threads;
+              if (nt < 0) {  // default: 8 threads, at most half of the CPUs this process may run on
+                cpu_set_t cs;
+                CPU_ZERO(&cs);
+                const int ncpu = sched_getaffinity(0, sizeof(cs), &cs) == 0 ? CPU_COUNT(&cs) : 2;
+                nt = std::min(8, std::max(1, ncpu / 2));
+              }
+              h->pool = new StagingPool(std::max(nt - 1, 0));  // the calling thread works too
+            }
+            h->pool->parallel_for(frames, stage_one);
+          } else {
+            for (int f = 0; f < frames; ++f) stage_one(f);
           }
           CU_TRY(h, cudaMemcpyAsync(dst, hst, (size_t)frames * ib, cudaMemcpyHostToDevice, s.stream));
         }
@@ -1309,6 +1398,7 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
   if (h->kp_cap > 65535) h->kp_cap = 65535;
   if (const char* ev = getenv("VSLAM_DEBUG_SKIP")) h->debug_skip = atoi(ev);
   if (const char* ev = getenv("VSLAM_GRAPH")) h->use_graph = atoi(ev) != 0;
+  if (const char* ev = getenv("VSLAM_STAGING_THREADS")) h->staging_threads = std::max(atoi(ev), 0);
   if (const char* ev = getenv("VSLAM_SELECT_FUSED")) h->select_fused = atoi(ev) != 0;
   if (const char* ev = getenv("VSLAM_BRIEF_TMA")) h->brief_tma = atoi(ev) != 0;
   if (!tensor_map_encoder()) h->brief_tma = false;  // driver without cuTensorMapEncodeTiled: the cp.async kernel
@@ -1404,6 +1494,7 @@ void vslam_destroy(vslam_handle h) {
   if (!h) return;
   DeviceGuard guard(h->cfg.device);
   for (int k = 0; k < MAX_SLOTS; ++k) free_slot(h->slots[k]);
+  delete h->pool;
   if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
   cudaFree(h->d_ccells);
   cudaFree(h->d_coef);
