@@ -206,11 +206,46 @@ __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_
 // (corner iff S > t, response = S-1).  min/max over the 16 circular 9-windows are computed with 3-input DPX
 // min/max on u16x2 lanes: two pixels per instruction, no branches, no divergence.
 // ----------------------------------------------------------------------------------------------------------
+#ifndef VSLAM_FAST_TREE36
+#define VSLAM_FAST_TREE36 1   // score tree over shared 8-windows (72 + 5 DPX per pixel pair instead of 80 + 5)
+#endif
+#ifndef VSLAM_FAST_GATHER8
+#define VSLAM_FAST_GATHER8 1  // phase B gathers the circle with 8/16-bit shared loads + IMAD instead of word loads + SHF + PRMT
+#endif
+#ifndef VSLAM_FAST_WAIT1
+#define VSLAM_FAST_WAIT1 1    // warp 0 owns the staging mbarrier (no block barrier before the copies are issued)
+#endif
+#ifndef VSLAM_FAST_TAIL2
+#define VSLAM_FAST_TAIL2 1    // NMS over one flat corner list with unconditional neighbour loads; emission rows interleaved
+#endif
 __device__ __forceinline__ unsigned max3u(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned min3u(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 
 // p: 16 circle samples (u16x2 = two adjacent pixels); c2: the two centres.  Returns max(S - t, 0) per lane.
 __device__ __forceinline__ unsigned fast_score2(const unsigned (&p)[16], unsigned c2, unsigned t2) {
+#if VSLAM_FAST_TREE36
+  // The 9-windows starting at k and k+1 share the 8-window {k+1..k+8}: max(min9_k, min9_{k+1}) =
+  // min(min8, max(p_k, p_{k+9})).  8-windows from pair minima at the odd positions: 36 instead of 40 DPX per polarity.
+  unsigned a2[8], b2[8], a4[8], b4[8], r[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // i <-> odd position j = 2i+1: {j, j+1}
+    a2[i] = __vminu2(p[2 * i + 1], p[(2 * i + 2) & 15]);
+    b2[i] = __vmaxu2(p[2 * i + 1], p[(2 * i + 2) & 15]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // {j .. j+3}
+    a4[i] = __vminu2(a2[i], a2[(i + 1) & 7]);
+    b4[i] = __vmaxu2(b2[i], b2[(i + 1) & 7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // even k = 2i: 8-window = a4 at positions k+1 (index i) and k+5 (index i+2)
+    const unsigned mx = __vmaxu2(p[2 * i], p[(2 * i + 9) & 15]), mn = __vminu2(p[2 * i], p[(2 * i + 9) & 15]);
+    r[i] = min3u(a4[i], a4[(i + 2) & 7], mx);
+    q[i] = max3u(b4[i], b4[(i + 2) & 7], mn);
+  }
+  const unsigned M9 = max3u(max3u(r[0], r[1], r[2]), max3u(r[3], r[4], r[5]), __vmaxu2(r[6], r[7]));
+  const unsigned m9 = min3u(min3u(q[0], q[1], q[2]), min3u(q[3], q[4], q[5]), __vminu2(q[6], q[7]));
+#else
   unsigned a3[16], b3[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -227,6 +262,7 @@ __device__ __forceinline__ unsigned fast_score2(const unsigned (&p)[16], unsigne
                       max3u(max3u(a9[9], a9[10], a9[11]), max3u(a9[12], a9[13], a9[14]), a9[15]), 0u);
   unsigned m9 = min3u(min3u(min3u(b9[0], b9[1], b9[2]), min3u(b9[3], b9[4], b9[5]), min3u(b9[6], b9[7], b9[8])),
                       min3u(min3u(b9[9], b9[10], b9[11]), min3u(b9[12], b9[13], b9[14]), b9[15]), 0xffffffffu);
+#endif
   unsigned bright = __vmaxu2(M9, c2) - c2;  // lane-wise non-negative: no borrow between lanes
   unsigned dark = c2 - __vminu2(m9, c2);
   unsigned S = __vmaxu2(bright, dark);
@@ -259,6 +295,18 @@ __device__ __forceinline__ unsigned lds16(unsigned a) {
 __device__ __forceinline__ unsigned lds8(unsigned a) {
   unsigned v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned lds16o(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned lds8o(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
   return v;
 }
 __device__ __forceinline__ void sts16(unsigned a, unsigned v) {
@@ -469,6 +517,19 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const unsigned mbar = sbase + (unsigned)o_misc;
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
+#if VSLAM_FAST_WAIT1
+  // warp 0 owns the mbarrier: it initialises it, issues the copies at once and is the only poller; the block barrier
+  // behind the poll publishes the tile (and the cleared score tile) to the other warps
+  if (warp == 0) {
+    if (lane == 0) {
+      *s_next = 0;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)((rows + 8) * pitch))
+                   : "memory");
+    }
+    __syncwarp();
+#else
   if (tid == 0) {
     *s_next = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
@@ -480,6 +541,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)((rows + 8) * pitch))
                    : "memory");
     __syncwarp();
+#endif
     for (int r = lane; r < rows + 8; r += 32) {
       const uint8_t* g = img_base + (size_t)(ys - 4 + r) * pitch;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -493,6 +555,9 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
     reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
   if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
+#if VSLAM_FAST_WAIT1
+  if (warp == 0)
+#endif
   {
     unsigned done = 0;
     while (!done)
@@ -531,6 +596,28 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
       const unsigned code = lds16(qb + 2u * (unsigned)((qhead + lane) & (kFastQ - 1)));
       const unsigned half = code & 1u, g4 = (code << 1) & 0xffcu, ry = code >> 11;  // g4 = 4 * group
       const unsigned rowo = ry * (unsigned)SP + g4;
+#if VSLAM_FAST_GATHER8
+      // byte address of the pair's first pixel; row bases y-3 .. y+3.  Even dx: one aligned 16-bit load + PRMT; odd dx:
+      // two byte loads combined by an IMAD (FMA pipe) - the ALU pipe, which bounds this kernel, only sees 7 PRMT.
+      const unsigned A = pix0 + rowo + 2u * half;
+      unsigned rb[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) rb[j] = A + (unsigned)(j - 3) * (unsigned)SP;
+      unsigned p[16];
+#define VS_G(k, dx, dy)                                                                  \
+  if constexpr ((dx) & 1) {                                                              \
+    const unsigned lo = lds8o<(dx)>(rb[(dy) + 3]), hi = lds8o<(dx) + 1>(rb[(dy) + 3]);   \
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(p[k]) : "r"(hi), "r"(lo));                \
+  } else {                                                                               \
+    p[k] = pair_lo(lds16o<(dx)>(rb[(dy) + 3]));                                          \
+  }
+      VS_G(0, 0, 3) VS_G(1, 1, 3) VS_G(2, 2, 2) VS_G(3, 3, 1) VS_G(4, 3, 0) VS_G(5, 3, -1) VS_G(6, 2, -2) VS_G(7, 1, -3)
+      VS_G(8, 0, -3) VS_G(9, -1, -3) VS_G(10, -2, -2) VS_G(11, -3, -1) VS_G(12, -3, 0) VS_G(13, -3, 1) VS_G(14, -2, 2)
+      VS_G(15, -1, 3)
+#undef VS_G
+      const unsigned c2 = pair_lo(lds16(A));
+      const unsigned xs = fast_score2(p, c2, t2);
+#else
       const unsigned a0 = pix0 + rowo - 3u * (unsigned)SP;
       unsigned w[7][3];
 #pragma unroll
@@ -564,6 +651,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
 #pragma unroll
       for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
       const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
+#endif
       const unsigned out16 = __byte_perm(xs, 0u, 0x4420);                     // (lane0, lane1) low bytes -> one u16
       const unsigned xo = g4 + 2u * half;
       sts16(sc0 + ry * (unsigned)SP + xo, out16);
@@ -656,6 +744,39 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int w = 0; w < kFastWarps; ++w) sparse = sparse && s_ccnt[w] <= kFastCL;
   if (sparse) {
     const int ry_lo = ys - sy_lo, ry_hi = ye - sy_lo;  // score rows that are emission rows: [ry_lo, ry_hi)
+#if VSLAM_FAST_TAIL2
+    // one flat index space over the warps' lists; the eight neighbours are loaded unconditionally (one shared-memory
+    // latency instead of a short-circuit chain of up to eight)
+    int cnt[kFastWarps], total = 0;
+#pragma unroll
+    for (int w = 0; w < kFastWarps; ++w) {
+      cnt[w] = s_ccnt[w];
+      total += cnt[w];
+    }
+    for (int i = tid; i < total; i += kFastThreads) {
+      int off = i, w = 0;
+#pragma unroll
+      for (int k = 0; k < kFastWarps - 1; ++k)
+        if (w == k && off >= cnt[k]) {
+          off -= cnt[k];
+          w = k + 1;
+        }
+      const unsigned code = lds16(sbase + (unsigned)(o_cl + (w * kFastCL + off) * 2));
+      const int ry = (int)(code >> 11), x = (int)(code & 0x7ffu);
+      if (ry < ry_lo || ry >= ry_hi || x < L.ex0 || x >= L.ex1) continue;
+      const int er = ry - ry_lo;  // emission row
+      const unsigned ca = sbase + (unsigned)(o_sc + (er + 1) * SP + 16 + x);
+      const unsigned up = ca - (unsigned)SP, dn = ca + (unsigned)SP;
+      const unsigned v = lds8o<0>(ca);
+      const unsigned n0 = lds8o<-1>(ca), n1 = lds8o<1>(ca), n2 = lds8o<-1>(up), n3 = lds8o<0>(up), n4 = lds8o<1>(up),
+                     n5 = lds8o<-1>(dn), n6 = lds8o<0>(dn), n7 = lds8o<1>(dn);
+      const unsigned m = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+      if (v > m) {
+        atomicOr(&bits[er * BW + (x >> 5)], 1u << (x & 31));
+        atomicAdd(&s_rowcnt[er], 1);
+      }
+    }
+#else
     for (int w = 0; w < kFastWarps; ++w) {
       const int n = s_ccnt[w];
       for (int i = tid; i < n; i += kFastThreads) {
@@ -673,6 +794,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
         }
       }
     }
+#endif
   } else {
     const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
     const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
@@ -714,6 +836,57 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
     }
     const int excl = incl - rc;  // lane r: records of the rows above row r
     uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
+#if VSLAM_FAST_TAIL2
+    if (BW <= 32) {
+      // the warp's rows (er = warp + k * kFastWarps) side by side: their prefix scans and their record loops interleave,
+      // so the shuffle and shared-load latencies of one row hide behind the other rows
+      constexpr int RPW = (VSLAM_FAST_ROWS + kFastWarps - 1) / kFastWarps;
+      unsigned bwv[RPW];
+      int pin[RPW], off[RPW];
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {
+        const int er = warp + k * kFastWarps;
+        bwv[k] = (er < rows && lane < BW) ? bits[er * BW + lane] : 0u;
+        pin[k] = __popc(bwv[k]);
+        off[k] = -pin[k];
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+          const int o = __shfl_up_sync(VSLAM_FULL, pin[k], d);
+          if (lane >= d) pin[k] += o;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) off[k] += pin[k] + __shfl_sync(VSLAM_FULL, excl, min(warp + k * kFastWarps, 31));
+      const unsigned srow0 = sbase + (unsigned)(o_sc + (warp + 1) * SP + 16 + (lane << 5));
+      const unsigned tm1 = (unsigned)P.fast_threshold - 1u;
+      unsigned any = 1u;
+      while (any) {
+        // branch-free body: the RPW score loads are issued back to back (an exhausted row reads the pad byte in front
+        // of its word), only the stores are predicated
+        unsigned scv[RPW];
+        int bp[RPW];
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+          bp[k] = __ffs(bwv[k]) - 1;
+          scv[k] = lds8(srow0 + (unsigned)(k * kFastWarps * SP + bp[k]));
+        }
+        any = 0u;
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+          const bool act = bwv[k] != 0u;
+          const unsigned rec = ((scv[k] + tm1) << 24) | ((unsigned)(ys + warp + k * kFastWarps) << 12) |
+                               (unsigned)((lane << 5) + bp[k]);  // score S - 1 <= 254
+          if (act) out[off[k]] = rec;
+          off[k] += act ? 1 : 0;
+          bwv[k] &= bwv[k] - 1u;
+          any |= bwv[k];
+        }
+      }
+    } else
+#endif
     for (int er = warp; er < rows; er += kFastWarps) {
       int run = __shfl_sync(VSLAM_FULL, excl, er);
       for (int j0 = 0; j0 < BW; j0 += 32) {
