@@ -206,24 +206,11 @@ __global__ void __launch_bounds__(128, VSLAM_RESIZE_MINB) k_resize(const __grid_
 // (corner iff S > t, response = S-1).  min/max over the 16 circular 9-windows are computed with 3-input DPX
 // min/max on u16x2 lanes: two pixels per instruction, no branches, no divergence.
 // ----------------------------------------------------------------------------------------------------------
-#ifndef VSLAM_FAST_TREE36
-#define VSLAM_FAST_TREE36 1   // score tree over shared 8-windows (72 + 5 DPX per pixel pair instead of 80 + 5)
-#endif
-#ifndef VSLAM_FAST_GATHER8
-#define VSLAM_FAST_GATHER8 1  // phase B gathers the circle with 8/16-bit shared loads + IMAD instead of word loads + SHF + PRMT
-#endif
-#ifndef VSLAM_FAST_WAIT1
-#define VSLAM_FAST_WAIT1 1    // warp 0 owns the staging mbarrier (no block barrier before the copies are issued)
-#endif
-#ifndef VSLAM_FAST_TAIL2
-#define VSLAM_FAST_TAIL2 1    // NMS over one flat corner list with unconditional neighbour loads; emission rows interleaved
-#endif
 __device__ __forceinline__ unsigned max3u(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned min3u(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 
 // p: 16 circle samples (u16x2 = two adjacent pixels); c2: the two centres.  Returns max(S - t, 0) per lane.
 __device__ __forceinline__ unsigned fast_score2(const unsigned (&p)[16], unsigned c2, unsigned t2) {
-#if VSLAM_FAST_TREE36
   // The 9-windows starting at k and k+1 share the 8-window {k+1..k+8}: max(min9_k, min9_{k+1}) =
   // min(min8, max(p_k, p_{k+9})).  8-windows from pair minima at the odd positions: 36 instead of 40 DPX per polarity.
   unsigned a2[8], b2[8], a4[8], b4[8], r[8], q[8];
@@ -245,24 +232,6 @@ __device__ __forceinline__ unsigned fast_score2(const unsigned (&p)[16], unsigne
   }
   const unsigned M9 = max3u(max3u(r[0], r[1], r[2]), max3u(r[3], r[4], r[5]), __vmaxu2(r[6], r[7]));
   const unsigned m9 = min3u(min3u(q[0], q[1], q[2]), min3u(q[3], q[4], q[5]), __vminu2(q[6], q[7]));
-#else
-  unsigned a3[16], b3[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    a3[k] = min3u(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-    b3[k] = max3u(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-  }
-  unsigned a9[16], b9[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    a9[k] = min3u(a3[k], a3[(k + 3) & 15], a3[(k + 6) & 15]);
-    b9[k] = max3u(b3[k], b3[(k + 3) & 15], b3[(k + 6) & 15]);
-  }
-  unsigned M9 = max3u(max3u(max3u(a9[0], a9[1], a9[2]), max3u(a9[3], a9[4], a9[5]), max3u(a9[6], a9[7], a9[8])),
-                      max3u(max3u(a9[9], a9[10], a9[11]), max3u(a9[12], a9[13], a9[14]), a9[15]), 0u);
-  unsigned m9 = min3u(min3u(min3u(b9[0], b9[1], b9[2]), min3u(b9[3], b9[4], b9[5]), min3u(b9[6], b9[7], b9[8])),
-                      min3u(min3u(b9[9], b9[10], b9[11]), min3u(b9[12], b9[13], b9[14]), b9[15]), 0xffffffffu);
-#endif
   unsigned bright = __vmaxu2(M9, c2) - c2;  // lane-wise non-negative: no borrow between lanes
   unsigned dark = c2 - __vminu2(m9, c2);
   unsigned S = __vmaxu2(bright, dark);
@@ -517,7 +486,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const unsigned mbar = sbase + (unsigned)o_misc;
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
-#if VSLAM_FAST_WAIT1
   // warp 0 owns the mbarrier: it initialises it, issues the copies at once and is the only poller; the block barrier
   // behind the poll publishes the tile (and the cleared score tile) to the other warps
   if (warp == 0) {
@@ -529,19 +497,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
                    : "memory");
     }
     __syncwarp();
-#else
-  if (tid == 0) {
-    *s_next = 0;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 0) {
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)((rows + 8) * pitch))
-                   : "memory");
-    __syncwarp();
-#endif
     for (int r = lane; r < rows + 8; r += 32) {
       const uint8_t* g = img_base + (size_t)(ys - 4 + r) * pitch;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -555,9 +510,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
     reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
   if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
-#if VSLAM_FAST_WAIT1
   if (warp == 0)
-#endif
   {
     unsigned done = 0;
     while (!done)
@@ -596,7 +549,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
       const unsigned code = lds16(qb + 2u * (unsigned)((qhead + lane) & (kFastQ - 1)));
       const unsigned half = code & 1u, g4 = (code << 1) & 0xffcu, ry = code >> 11;  // g4 = 4 * group
       const unsigned rowo = ry * (unsigned)SP + g4;
-#if VSLAM_FAST_GATHER8
       // byte address of the pair's first pixel; row bases y-3 .. y+3.  Even dx: one aligned 16-bit load + PRMT; odd dx:
       // two byte loads combined by an IMAD (FMA pipe) - the ALU pipe, which bounds this kernel, only sees 7 PRMT.
       const unsigned A = pix0 + rowo + 2u * half;
@@ -617,41 +569,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
 #undef VS_G
       const unsigned c2 = pair_lo(lds16(A));
       const unsigned xs = fast_score2(p, c2, t2);
-#else
-      const unsigned a0 = pix0 + rowo - 3u * (unsigned)SP;
-      unsigned w[7][3];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const unsigned a = a0 + (unsigned)j * (unsigned)SP;
-        w[j][0] = lds32<-4>(a);
-        w[j][1] = lds32<0>(a);
-        w[j][2] = lds32<4>(a);
-      }
-#define VS_ROW(dy) w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2]
-      unsigned sv[16];
-      sv[0] = shifted4<0>(VS_ROW(3));
-      sv[1] = shifted4<1>(VS_ROW(3));
-      sv[2] = shifted4<2>(VS_ROW(2));
-      sv[3] = shifted4<3>(VS_ROW(1));
-      sv[4] = shifted4<3>(VS_ROW(0));
-      sv[5] = shifted4<3>(VS_ROW(-1));
-      sv[6] = shifted4<2>(VS_ROW(-2));
-      sv[7] = shifted4<1>(VS_ROW(-3));
-      sv[8] = shifted4<0>(VS_ROW(-3));
-      sv[9] = shifted4<-1>(VS_ROW(-3));
-      sv[10] = shifted4<-2>(VS_ROW(-2));
-      sv[11] = shifted4<-3>(VS_ROW(-1));
-      sv[12] = shifted4<-3>(VS_ROW(0));
-      sv[13] = shifted4<-3>(VS_ROW(1));
-      sv[14] = shifted4<-2>(VS_ROW(2));
-      sv[15] = shifted4<-1>(VS_ROW(3));
-#undef VS_ROW
-      const unsigned sel = half ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> u16x2
-      unsigned p[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) p[k] = __byte_perm(sv[k], 0u, sel);
-      const unsigned xs = fast_score2(p, __byte_perm(w[3][1], 0u, sel), t2);  // max(S - t, 0) per 16-bit lane
-#endif
       const unsigned out16 = __byte_perm(xs, 0u, 0x4420);                     // (lane0, lane1) low bytes -> one u16
       const unsigned xo = g4 + 2u * half;
       sts16(sc0 + ry * (unsigned)SP + xo, out16);
@@ -744,7 +661,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int w = 0; w < kFastWarps; ++w) sparse = sparse && s_ccnt[w] <= kFastCL;
   if (sparse) {
     const int ry_lo = ys - sy_lo, ry_hi = ye - sy_lo;  // score rows that are emission rows: [ry_lo, ry_hi)
-#if VSLAM_FAST_TAIL2
     // one flat index space over the warps' lists; the eight neighbours are loaded unconditionally (one shared-memory
     // latency instead of a short-circuit chain of up to eight)
     int cnt[kFastWarps], total = 0;
@@ -776,25 +692,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
         atomicAdd(&s_rowcnt[er], 1);
       }
     }
-#else
-    for (int w = 0; w < kFastWarps; ++w) {
-      const int n = s_ccnt[w];
-      for (int i = tid; i < n; i += kFastThreads) {
-        const unsigned code = lds16(sbase + (unsigned)(o_cl + (w * kFastCL + i) * 2));
-        const int ry = (int)(code >> 11), x = (int)(code & 0x7ffu);
-        if (ry < ry_lo || ry >= ry_hi || x < L.ex0 || x >= L.ex1) continue;
-        const int er = ry - ry_lo;  // emission row
-        const uint8_t* c = sc + (er + 1) * SP + 16 + x;
-        const int v = c[0];
-        const bool keep = v > c[-1] && v > c[1] && v > c[-SP - 1] && v > c[-SP] && v > c[-SP + 1] && v > c[SP - 1] &&
-                          v > c[SP] && v > c[SP + 1];
-        if (keep) {
-          atomicOr(&bits[er * BW + (x >> 5)], 1u << (x & 31));
-          atomicAdd(&s_rowcnt[er], 1);
-        }
-      }
-    }
-#endif
   } else {
     const int egx0 = L.ex0 >> 2, negx = ((L.ex1 - 1) >> 2) - egx0 + 1;
     const unsigned inv_negx = (unsigned)((0x100000000ull + (unsigned)negx - 1u) / (unsigned)negx);
@@ -836,7 +733,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
     }
     const int excl = incl - rc;  // lane r: records of the rows above row r
     uint32_t* out = strip_rec + (long long)img * P.rec_img_stride + L.rec_off + (long long)s_local * L.strip_cap;
-#if VSLAM_FAST_TAIL2
     if (BW <= 32) {
       // the warp's rows (er = warp + k * kFastWarps) side by side: their prefix scans and their record loops interleave,
       // so the shuffle and shared-load latencies of one row hide behind the other rows
@@ -886,7 +782,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
         }
       }
     } else
-#endif
     for (int er = warp; er < rows; er += kFastWarps) {
       int run = __shfl_sync(VSLAM_FULL, excl, er);
       for (int j0 = 0; j0 < BW; j0 += 32) {
