@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(288) k_resize_tile(const __grid_constant__ Pyr
   }
 }
 
+#ifndef VSLAM_FAST_BULK
+#define VSLAM_FAST_BULK 1  // stage the pixel tile with two large bulk copies (rows packed at the global pitch) on two mbarriers
+#endif
+#ifndef VSLAM_FAST_LIN
+#define VSLAM_FAST_LIN 1   // phase-A work items over the linearised (segment, group) list
+#endif
 #ifndef VSLAM_FAST_THREADS
 #define VSLAM_FAST_THREADS 192  // 6 warps: one per 128-pixel column group of a 752-wide level
 #endif
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const int strip = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   int l = 0;
-  for (int k = 1; k < P.nlevels; ++k)
-    if (strip >= P.lv[k].fast_strip0 && P.lv[k].fast_nstrips > 0) l = k;
+  for (int k = 1; k < P.nlevels && strip >= P.lv[k].fast_strip0; ++k)  // fast_strip0 is non-decreasing
+    if (P.lv[k].fast_nstrips > 0) l = k;
   const LevelP& L = P.lv[l];
   const int s_local = strip - L.fast_strip0;
   const int ys = L.ey0 + s_local * VSLAM_FAST_ROWS;
@@ -471,8 +477,13 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   int pitch;
   const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
   const int SP = fast_sp(pitch), BW = fast_bw(pitch);
+#if VSLAM_FAST_BULK
+  const int PP = pitch;  // pixel-tile row stride == global row stride: the tile is ONE contiguous range of global memory
+#else
+  const int PP = SP;
+#endif
   // layout (byte offsets into the dynamic shared memory)
-  const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*SP + 16
+  const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*PP + 16
   const int o_bits = o_sc + (VSLAM_FAST_ROWS + 2) * SP;      // score tile: image row ys-1+r at o_sc + r*SP + 16
   const int o_q = o_bits + ((VSLAM_FAST_ROWS * BW * 4 + 15) & ~15);  // corner bitmask; then the per-warp candidate rings
   const int o_cl = o_q + kFastWarps * kFastQ * 2;            // per-warp corner lists
@@ -480,14 +491,37 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   uint8_t* sc = smem + o_sc;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + o_bits);
-  int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 8);   // [kFastWarps] corner-list lengths
+  int* s_ccnt = reinterpret_cast<int*>(smem + o_misc + 16);  // [kFastWarps] corner-list lengths
   int* s_next = s_ccnt + kFastWarps;
   int* s_rowcnt = s_next + 1;                                // [VSLAM_FAST_ROWS] NMS survivors per emission row                               // dynamic work-item counter of phase A
-  const unsigned mbar = sbase + (unsigned)o_misc;
+  const unsigned mbar = sbase + (unsigned)o_misc;  // two mbarriers: tile rows [0, n0) and [n0, rows + 8)
 
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
   // warp 0 owns the mbarrier: it initialises it, issues the copies at once and is the only poller; the block barrier
   // behind the poll publishes the tile (and the cleared score tile) to the other warps
+#if VSLAM_FAST_BULK
+  // two copies: the first 14 rows (all that segment 0 of phase A reads) complete on mbarrier 0, the rest on mbarrier 1
+  const int n0 = min(2 * kFastSeg, rows + 8), n1 = rows + 8 - n0;
+  if (tid == 0) {
+    *s_next = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 8u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint8_t* g = img_base + (size_t)(ys - 4) * pitch;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)(n0 * pitch)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + 16u),
+                 "l"(g), "r"((unsigned)(n0 * pitch)), "r"(mbar)
+                 : "memory");
+    if (n1 > 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar + 8u), "r"((unsigned)(n1 * pitch))
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       sbase + 16u + (unsigned)(n0 * pitch)),
+                   "l"(g + (size_t)n0 * pitch), "r"((unsigned)(n1 * pitch)), "r"(mbar + 8u)
+                   : "memory");
+    }
+  }
+#else
   if (warp == 0) {
     if (lane == 0) {
       *s_next = 0;
@@ -505,6 +539,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
                    : "memory");
     }
   }
+#endif
   for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
@@ -535,7 +570,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const unsigned t2 = t * 0x00010001u;
   const unsigned tadd = (127u - t) * 0x01010101u;  // fast_threshold <= 127 (checked by vslam_create)
   const unsigned lt = (1u << lane) - 1u;
-  const unsigned pix0 = sbase + (unsigned)((sy_lo - (ys - 4)) * SP + 16);  // centre pixel of score row 0, x = 0
+  const unsigned pix0 = sbase + (unsigned)((sy_lo - (ys - 4)) * PP + 16);  // centre pixel of score row 0, x = 0
   const unsigned sc0 = sbase + (unsigned)(o_sc + (sy_lo - (ys - 1)) * SP + 16);
   const unsigned qb = sbase + (unsigned)(o_q + warp * kFastQ * 2);
   const unsigned clb = sbase + (unsigned)(o_cl + warp * kFastCL * 2);
@@ -548,13 +583,13 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
     if (lane < qn) {
       const unsigned code = lds16(qb + 2u * (unsigned)((qhead + lane) & (kFastQ - 1)));
       const unsigned half = code & 1u, g4 = (code << 1) & 0xffcu, ry = code >> 11;  // g4 = 4 * group
-      const unsigned rowo = ry * (unsigned)SP + g4;
+      const unsigned rowo = ry * (unsigned)PP + g4;
       // byte address of the pair's first pixel; row bases y-3 .. y+3.  Even dx: one aligned 16-bit load + PRMT; odd dx:
       // two byte loads combined by an IMAD (FMA pipe) - the ALU pipe, which bounds this kernel, only sees 7 PRMT.
       const unsigned A = pix0 + rowo + 2u * half;
       unsigned rb[7];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) rb[j] = A + (unsigned)(j - 3) * (unsigned)SP;
+      for (int j = 0; j < 7; ++j) rb[j] = A + (unsigned)(j - 3) * (unsigned)PP;
       unsigned p[16];
 #define VS_G(k, dx, dy)                                                                  \
   if constexpr ((dx) & 1) {                                                              \
@@ -589,30 +624,61 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
 
   // Work items = (32-group column block, 7-row segment), handed out dynamically (one shared atomic per item) so that
   // the warps of a block finish together whatever the level width; every item refills its register window (6 rows).
+#if VSLAM_FAST_LIN
+  // items = 32 consecutive (segment, group) columns of the segment-major list: no idle lanes in the last column block
+  // of a level whose width is not a multiple of 128 pixels (10 % of the lane slots on the 8-level 752-wide pyramid)
+  const int nseg = (nsr + kFastSeg - 1) / kFastSeg, nlin = nseg * ngx, nitems = (nlin + 31) >> 5;
+  const unsigned inv_ngx = 0xffffffffu / (unsigned)ngx + 1u;  // ceil(2^32 / ngx): exact quotients for li < 2^16
+#else
   const int nseg = (nsr + kFastSeg - 1) / kFastSeg, nitems = ncg * nseg;
+#endif
+#if VSLAM_FAST_BULK
+  bool got1 = n1 == 0;  // warp-uniform: this warp has seen the second staging barrier complete
+#endif
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(s_next, 1);
     item = __shfl_sync(VSLAM_FULL, item, 0);
     if (item >= nitems) break;
+#if VSLAM_FAST_LIN
+    const int li = min(item * 32 + lane, nlin - 1);
+    const bool has = item * 32 + lane < nlin;
+    const int seg = (int)__umulhi((unsigned)li, inv_ngx), gi = li - seg * ngx, r0 = seg * kFastSeg;
+    const int g = gx0 + gi;
+    const int seg_hi = (int)__umulhi((unsigned)min(item * 32 + 31, nlin - 1), inv_ngx);
+#else
     const int seg = item / ncg, cgi = item - seg * ncg, r0 = seg * kFastSeg;
     const int gi = cgi * 32 + lane;
     const bool has = gi < ngx;
     const int g = gx0 + min(gi, ngx - 1);
+    const int seg_hi = seg;
+#endif
+#if VSLAM_FAST_BULK
+    if (!got1 && seg_hi > 0) {  // segments >= 1 read tile rows >= 14
+      unsigned done = 0;
+      while (!done)
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(mbar + 8u)
+            : "memory");
+      got1 = true;
+    }
+#endif
     // per-byte mask of the scored columns [sx0, sx1) of this group (only the first / last group is partial)
     unsigned colmask = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b)
       if (has && 4 * g + b >= sx0 && 4 * g + b < sx1) colmask |= 0x80u << (8 * b);
     const unsigned codeg = (unsigned)g << 1;
-    unsigned arow = pix0 + 4u * (unsigned)g + (unsigned)((r0 - 3) * SP);  // word b of pixel row (sy_lo + r0 - 3)
+    unsigned arow = pix0 + 4u * (unsigned)g + (unsigned)((r0 - 3) * PP);  // word b of pixel row (sy_lo + r0 - 3)
     unsigned W[7][3];  // raw words (x-4, x, x+4) of the pixel rows y-3 .. y+3; every index is a compile-time constant
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       W[j][0] = lds32<-4>(arow);
       W[j][1] = lds32<0>(arow);
       W[j][2] = lds32<4>(arow);
-      arow += (unsigned)SP;
+      arow += (unsigned)PP;
     }
 #pragma unroll
     for (int ph = 0; ph < kFastSeg; ++ph) {
@@ -621,7 +687,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
       WR(6, 0) = lds32<-4>(arow);
       WR(6, 1) = lds32<0>(arow);
       WR(6, 2) = lds32<4>(arow);
-      arow += (unsigned)SP;
+      arow += (unsigned)PP;
       const unsigned cw = WR(3, 1);
       const unsigned a0 = __vabsdiffu4(WR(6, 1), cw), a8 = __vabsdiffu4(WR(0, 1), cw);
       const unsigned a4 = __vabsdiffu4(shifted4<3>(WR(3, 0), WR(3, 1), WR(3, 2)), cw);
