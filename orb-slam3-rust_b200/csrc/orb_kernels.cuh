@@ -415,12 +415,6 @@ __global__ void __launch_bounds__(288) k_resize_tile(const __grid_constant__ Pyr
   }
 }
 
-#ifndef VSLAM_FAST_BULK
-#define VSLAM_FAST_BULK 1  // stage the pixel tile with two large bulk copies (rows packed at the global pitch) on two mbarriers
-#endif
-#ifndef VSLAM_FAST_LIN
-#define VSLAM_FAST_LIN 1   // phase-A work items over the linearised (segment, group) list
-#endif
 #ifndef VSLAM_FAST_THREADS
 #define VSLAM_FAST_THREADS 192  // 6 warps: one per 128-pixel column group of a 752-wide level
 #endif
@@ -477,11 +471,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   int pitch;
   const uint8_t* img_base = level_ptr(P, l, img, in_l, in_r, pyr, pitch);
   const int SP = fast_sp(pitch), BW = fast_bw(pitch);
-#if VSLAM_FAST_BULK
   const int PP = pitch;  // pixel-tile row stride == global row stride: the tile is ONE contiguous range of global memory
-#else
-  const int PP = SP;
-#endif
   // layout (byte offsets into the dynamic shared memory)
   const int o_sc = (VSLAM_FAST_ROWS + 8) * SP;               // pixel tile: image row ys-4+r at r*PP + 16
   const int o_bits = o_sc + (VSLAM_FAST_ROWS + 2) * SP;      // score tile: image row ys-1+r at o_sc + r*SP + 16
@@ -499,7 +489,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
   // warp 0 owns the mbarrier: it initialises it, issues the copies at once and is the only poller; the block barrier
   // behind the poll publishes the tile (and the cleared score tile) to the other warps
-#if VSLAM_FAST_BULK
   // two copies: the first 14 rows (all that segment 0 of phase A reads) complete on mbarrier 0, the rest on mbarrier 1
   const int n0 = min(2 * kFastSeg, rows + 8), n1 = rows + 8 - n0;
   if (tid == 0) {
@@ -521,25 +510,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
                    : "memory");
     }
   }
-#else
-  if (warp == 0) {
-    if (lane == 0) {
-      *s_next = 0;
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)((rows + 8) * pitch))
-                   : "memory");
-    }
-    __syncwarp();
-    for (int r = lane; r < rows + 8; r += 32) {
-      const uint8_t* g = img_base + (size_t)(ys - 4 + r) * pitch;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       sbase + (unsigned)(r * SP + 16)),
-                   "l"(g), "r"((unsigned)pitch), "r"(mbar)
-                   : "memory");
-    }
-  }
-#endif
   for (int i = tid; i < ((VSLAM_FAST_ROWS + 2) * SP) >> 4; i += kFastThreads)
     reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
@@ -575,7 +545,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   const unsigned qb = sbase + (unsigned)(o_q + warp * kFastQ * 2);
   const unsigned clb = sbase + (unsigned)(o_cl + warp * kFastCL * 2);
   int qn = 0, qhead = 0, cn = 0;  // warp-uniform: ring fill / head, corner-list length
-  const int ncg = (ngx + 31) >> 5;
 
   // exact scores of up to 32 queued pairs, one pair per lane
   auto phase_b = [&]() {
@@ -624,36 +593,21 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
 
   // Work items = (32-group column block, 7-row segment), handed out dynamically (one shared atomic per item) so that
   // the warps of a block finish together whatever the level width; every item refills its register window (6 rows).
-#if VSLAM_FAST_LIN
   // items = 32 consecutive (segment, group) columns of the segment-major list: no idle lanes in the last column block
   // of a level whose width is not a multiple of 128 pixels (10 % of the lane slots on the 8-level 752-wide pyramid)
   const int nseg = (nsr + kFastSeg - 1) / kFastSeg, nlin = nseg * ngx, nitems = (nlin + 31) >> 5;
   const unsigned inv_ngx = 0xffffffffu / (unsigned)ngx + 1u;  // ceil(2^32 / ngx): exact quotients for li < 2^16
-#else
-  const int nseg = (nsr + kFastSeg - 1) / kFastSeg, nitems = ncg * nseg;
-#endif
-#if VSLAM_FAST_BULK
   bool got1 = n1 == 0;  // warp-uniform: this warp has seen the second staging barrier complete
-#endif
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(s_next, 1);
     item = __shfl_sync(VSLAM_FULL, item, 0);
     if (item >= nitems) break;
-#if VSLAM_FAST_LIN
     const int li = min(item * 32 + lane, nlin - 1);
     const bool has = item * 32 + lane < nlin;
     const int seg = (int)__umulhi((unsigned)li, inv_ngx), gi = li - seg * ngx, r0 = seg * kFastSeg;
     const int g = gx0 + gi;
     const int seg_hi = (int)__umulhi((unsigned)min(item * 32 + 31, nlin - 1), inv_ngx);
-#else
-    const int seg = item / ncg, cgi = item - seg * ncg, r0 = seg * kFastSeg;
-    const int gi = cgi * 32 + lane;
-    const bool has = gi < ngx;
-    const int g = gx0 + min(gi, ngx - 1);
-    const int seg_hi = seg;
-#endif
-#if VSLAM_FAST_BULK
     if (!got1 && seg_hi > 0) {  // segments >= 1 read tile rows >= 14
       unsigned done = 0;
       while (!done)
@@ -664,7 +618,6 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
             : "memory");
       got1 = true;
     }
-#endif
     // per-byte mask of the scored columns [sx0, sx1) of this group (only the first / last group is partial)
     unsigned colmask = 0;
 #pragma unroll
@@ -729,20 +682,9 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
     const int ry_lo = ys - sy_lo, ry_hi = ye - sy_lo;  // score rows that are emission rows: [ry_lo, ry_hi)
     // one flat index space over the warps' lists; the eight neighbours are loaded unconditionally (one shared-memory
     // latency instead of a short-circuit chain of up to eight)
-    int cnt[kFastWarps], total = 0;
-#pragma unroll
-    for (int w = 0; w < kFastWarps; ++w) {
-      cnt[w] = s_ccnt[w];
-      total += cnt[w];
-    }
-    for (int i = tid; i < total; i += kFastThreads) {
-      int off = i, w = 0;
-#pragma unroll
-      for (int k = 0; k < kFastWarps - 1; ++k)
-        if (w == k && off >= cnt[k]) {
-          off -= cnt[k];
-          w = k + 1;
-        }
+    // every warp walks its OWN corner list (cn is still in a register): no list selection, no count exchange
+    for (int off = lane; off < cn; off += 32) {
+      const int w = warp;
       const unsigned code = lds16(sbase + (unsigned)(o_cl + (w * kFastCL + off) * 2));
       const int ry = (int)(code >> 11), x = (int)(code & 0x7ffu);
       if (ry < ry_lo || ry >= ry_hi || x < L.ex0 || x >= L.ex1) continue;
