@@ -34,11 +34,10 @@ namespace vk {
 #define VSLAM_FULL 0xffffffffu
 
 // rBRIEF pattern in global (not __constant__) memory: every lane reads a different test, which the constant cache would
-// serialise.  Stored as float (|coordinate| <= 13 is exact) and TRANSPOSED for coalescing: lane b evaluates tests
-// 8b .. 8b+7, so g_brief_pattern_t[q][b] = test 8b + q = (x0, y0, x1, y1); one LDG.128 per q then touches 4 cache lines
-// instead of 32.  Filled by the host at handle creation (upload_tables in vslam_b200.cu) from brief_pattern.inc.
-__device__ float4 g_brief_pattern_t[8][32];
-// the same table as four int8 per test (|coordinate| <= 13): one 4-byte load per test instead of 16 (VSLAM_BRIEF_I8)
+// serialise.  TRANSPOSED for coalescing - lane b evaluates tests 8b .. 8b+7, so g_brief_pattern_i8[q][b] = test 8b + q -
+// and packed as four bytes (x0, y0, x1, y1) per test (|coordinate| <= 13): one 4-byte load per test, one cache line per
+// warp.  With VSLAM_BRIEF_PACKED the bytes are biased by 128 (steered_brief_byte), else two's complement.  Filled by the
+// host at handle creation (upload_tables in vslam_b200.cu) from brief_pattern.inc.
 __device__ unsigned g_brief_pattern_i8[8][32];
 
 // Orientation tables (filled by the host at handle creation, see upload_tables in vslam_b200.cu):
@@ -1453,6 +1452,9 @@ __device__ __forceinline__ f32x2_t pk2u(unsigned lo, unsigned hi) {
 __device__ __forceinline__ void upk2u(f32x2_t v, unsigned& lo, unsigned& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
 }
+__device__ __forceinline__ void upk2f(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 __device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
   f32x2_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -1701,13 +1703,64 @@ constexpr int kAngleRows = 2 * kAngleR + 1;     // 31
 constexpr int kAngleRowWords = 9;               // 31 px + up to 3 alignment bytes = 9 words
 constexpr int kPatchWords = kBriefRows * kBriefRowWords + kAngleRows * kAngleRowWords;
 
-#ifndef VSLAM_BRIEF_I8
-#define VSLAM_BRIEF_I8 1
+#ifndef VSLAM_BRIEF_PACKED
+#define VSLAM_BRIEF_PACKED 1  // steering arithmetic on packed f32x2 (both points of a test per instruction)
 #endif
 #ifndef VSLAM_BRIEF_WARPS
 #define VSLAM_BRIEF_WARPS 4
 #endif
 constexpr int kBriefWarps = VSLAM_BRIEF_WARPS;  // keypoints (warps) per block
+// Descriptor byte `lane` of a keypoint: tests 8*lane .. 8*lane+7 of the rotated pattern.  `center` is the shared-window
+// address of the patch centre with the cvRound bias folded in (see k_brief), ROWB the patch row stride in bytes.
+// a = (float)cos, b = (float)sin.  ix = cvRound(x*a - y*b), iy = cvRound(x*b + y*a), every product and sum rounded to f32.
+template <unsigned ROWB>
+__device__ __forceinline__ unsigned steered_brief_byte(const unsigned center, const float a, const float b, const int lane) {
+  unsigned byte = 0;
+#if VSLAM_BRIEF_PACKED
+  // Packed f32x2 where it is exact: the pattern bytes (biased by 128) are dropped into the mantissa of 2^23 by PRMT and
+  // un-biased by one packed add per two coordinates; the four products of a test's two points take four FMUL2
+  // (x*a - y*b == x*a + y*(-b)); the cvRound bias of two coordinates is one FADD2.  The sums of two products stay
+  // SCALAR: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 - a single rounding, not what the
+  // reference computes - and honours .rn only on the scalar forms.
+  const f32x2_t AA = pk2(a, a), BB = pk2(b, b), NB = pk2(-b, -b), MAGIC = pk2(12582912.0f, 12582912.0f),
+                 UNBIAS = pk2(-8388736.0f, -8388736.0f);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const unsigned pw = g_brief_pattern_i8[q][lane];  // test 8*lane + q: (x0, y0, x1, y1), bytes biased by 128
+    const f32x2_t X = add2(pk2u(__byte_perm(pw, 0x4B000000u, 0x7440), __byte_perm(pw, 0x4B000000u, 0x7442)), UNBIAS);
+    const f32x2_t Y = add2(pk2u(__byte_perm(pw, 0x4B000000u, 0x7441), __byte_perm(pw, 0x4B000000u, 0x7443)), UNBIAS);
+    unsigned ix0, ix1, iy0, iy1;
+    float xa0, xa1, ynb0, ynb1, xb0, xb1, ya0, ya1;
+    upk2f(mul2(X, AA), xa0, xa1);
+    upk2f(mul2(Y, NB), ynb0, ynb1);
+    upk2f(mul2(X, BB), xb0, xb1);
+    upk2f(mul2(Y, AA), ya0, ya1);
+    upk2u(add2(pk2(__fadd_rn(xa0, ynb0), __fadd_rn(xa1, ynb1)), MAGIC), ix0, ix1);
+    upk2u(add2(pk2(__fadd_rn(xb0, ya0), __fadd_rn(xb1, ya1)), MAGIC), iy0, iy1);
+    const unsigned t0 = lds8(center + iy0 * ROWB + ix0), t1 = lds8(center + iy1 * ROWB + ix1);
+    byte |= (unsigned)(t0 < t1) << q;
+  }
+#else
+  auto raw = [](float v) -> unsigned { return __float_as_uint(__fadd_rn(v, 12582912.0f)); };
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const unsigned pw = g_brief_pattern_i8[q][lane];  // test 8*lane + q: (x0, y0, x1, y1) as int8, exact in f32
+    float4 t;
+    t.x = (float)(int)(signed char)(pw & 0xffu);
+    t.y = (float)(int)(signed char)((pw >> 8) & 0xffu);
+    t.z = (float)(int)(signed char)((pw >> 16) & 0xffu);
+    t.w = (float)(int)(signed char)(pw >> 24);
+    const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
+    const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
+    const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
+    const unsigned iy1 = raw(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
+    const unsigned t0 = lds8(center + iy0 * ROWB + ix0), t1 = lds8(center + iy1 * ROWB + ix1);
+    byte |= (unsigned)(t0 < t1) << q;
+  }
+#endif
+  return byte;
+}
+
 __global__ void __launch_bounds__(32 * kBriefWarps) k_brief(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                const uint8_t* __restrict__ in_r, const uint8_t* __restrict__ pyr,
                                                const uint8_t* __restrict__ blur, const LvlKp* __restrict__ lvl_kp,
@@ -1831,27 +1884,7 @@ __global__ void __launch_bounds__(32 * kBriefWarps) k_brief(const __grid_constan
   constexpr unsigned kRowB = kBriefRowWords * 4;
   const unsigned center = (unsigned)__cvta_generic_to_shared(sb) + kBriefR * kRowB + (unsigned)(cx - xb0) -
                           (kRowB + 1u) * 0x4B400000u;
-  auto raw = [](float v) -> unsigned { return __float_as_uint(__fadd_rn(v, 12582912.0f)); };
-  unsigned byte = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-#if VSLAM_BRIEF_I8
-    const unsigned pw = g_brief_pattern_i8[q][lane];  // test 8*lane + q: (x0,y0,x1,y1) as int8, exact in f32
-    float4 t;
-    t.x = (float)(int)(signed char)(pw & 0xffu);
-    t.y = (float)(int)(signed char)((pw >> 8) & 0xffu);
-    t.z = (float)(int)(signed char)((pw >> 16) & 0xffu);
-    t.w = (float)(int)(signed char)(pw >> 24);
-#else
-    const float4 t = g_brief_pattern_t[q][lane];  // test 8*lane + q: (x0,y0,x1,y1)
-#endif
-    const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
-    const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
-    const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
-    const unsigned iy1 = raw(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
-    const unsigned t0 = lds8(center + iy0 * kRowB + ix0), t1 = lds8(center + iy1 * kRowB + ix1);
-    byte |= (unsigned)(t0 < t1) << q;
-  }
+  const unsigned byte = steered_brief_byte<kRowB>(center, a, b, lane);
   unsigned char* descbase = eye ? F.desc[1] : F.desc[0];
   (descbase + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
 }
@@ -1996,23 +2029,7 @@ __global__ void __launch_bounds__(32 * kBriefWarps) k_brief_tma(const __grid_con
   // sample address = patch centre + 48 * iy + ix with the cvRound bias folded in (see k_brief)
   constexpr unsigned kRowB = kTmaBriefW;
   const unsigned center = sb + kBriefR * kRowB + (unsigned)kBriefR + ((unsigned)(cx - kBriefR) & 15u) - (kRowB + 1u) * 0x4B400000u;
-  auto raw = [](float v) -> unsigned { return __float_as_uint(__fadd_rn(v, 12582912.0f)); };
-  unsigned byte = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const unsigned pw = g_brief_pattern_i8[q][lane];
-    float4 t;
-    t.x = (float)(int)(signed char)(pw & 0xffu);
-    t.y = (float)(int)(signed char)((pw >> 8) & 0xffu);
-    t.z = (float)(int)(signed char)((pw >> 16) & 0xffu);
-    t.w = (float)(int)(signed char)(pw >> 24);
-    const unsigned ix0 = raw(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
-    const unsigned iy0 = raw(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
-    const unsigned ix1 = raw(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
-    const unsigned iy1 = raw(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
-    const unsigned t0 = lds8(center + iy0 * kRowB + ix0), t1 = lds8(center + iy1 * kRowB + ix1);
-    byte |= (unsigned)(t0 < t1) << q;
-  }
+  const unsigned byte = steered_brief_byte<kRowB>(center, a, b, lane);
   unsigned char* descbase = eye ? F.desc[1] : F.desc[0];
   (descbase + (long long)frame * F.desc_stride)[(size_t)j * VSLAM_DESC_BYTES + lane] = (unsigned char)byte;
 }

@@ -356,18 +356,14 @@ bool encode_u8_map(CUtensorMap* m, const void* base, size_t pitch, size_t rows, 
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Tables of k_brief (see orb_kernels.cuh): transposed float rBRIEF pattern, disc masks and packed int8 column offsets.
+// Tables of k_brief (see orb_kernels.cuh): transposed byte-packed rBRIEF pattern, disc masks and packed int8 column offsets.
 int upload_tables(vslam_handle h) {
   static const int pattern[1024] = {
 #include "brief_pattern.inc"
   };
   static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
   // scratch is per call (vslam_create may run concurrently on several host threads)
-  float pat_t[8][32][4];
   unsigned mask[4][9][32], uu[4][9];
-  for (int b = 0; b < 32; ++b)
-    for (int q = 0; q < 8; ++q)
-      for (int c = 0; c < 4; ++c) pat_t[q][b][c] = (float)pattern[4 * (8 * b + q) + c];
   for (int o = 0; o < 4; ++o) {
     for (int j = 0; j < 9; ++j) {
       unsigned w = 0;
@@ -386,13 +382,15 @@ int upload_tables(vslam_handle h) {
       }
     }
   }
-  CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_t, pat_t, sizeof(pat_t)));
   {
     unsigned pat_i8[8][32];
     for (int b = 0; b < 32; ++b)
       for (int q = 0; q < 8; ++q) {
         unsigned w = 0;
         for (int c = 0; c < 4; ++c) w |= (unsigned)(uint8_t)(int8_t)pattern[4 * (8 * b + q) + c] << (8 * c);
+#if VSLAM_BRIEF_PACKED
+        w ^= 0x80808080u;  // bytes biased by 128 (steered_brief_byte)
+#endif
         pat_i8[q][b] = w;
       }
     CU_TRY(h, cudaMemcpyToSymbol(vk::g_brief_pattern_i8, pat_i8, sizeof(pat_i8)));
@@ -1481,7 +1479,11 @@ int vslam_create(const vslam_config* cfg, vslam_handle* out) {
     rc = alloc_slot(h, h->slots[k]);
     if (rc != VSLAM_OK) return bail(rc == VSLAM_ERR_CUDA ? VSLAM_ERR_OUT_OF_MEMORY : rc);
   }
-  e = cudaDeviceSynchronize();
+  // The set-up work above (memsets, table and coefficient uploads) went to the legacy default stream; the handle's own
+  // streams are non-blocking and do not order after it.  Not cudaDeviceSynchronize(): that call fails with
+  // cudaErrorStreamCaptureUnsupported while ANOTHER host thread captures its handle's single-pair graph (measured:
+  // tools/stress_two_handles.py, 5 of 60 concurrent creations), although that capture is thread-local.
+  e = cudaStreamSynchronize(cudaStreamLegacy);
   if (e != cudaSuccess) {
     fail(h, VSLAM_ERR_CUDA, "device error after setup: %s", cudaGetErrorString(e));
     return bail(VSLAM_ERR_CUDA);

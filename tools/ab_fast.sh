@@ -1,9 +1,11 @@
 #!/bin/bash
-# A/B of k_fast build variants on one box: tools/ab_fast.sh (libs in build/ab/lib_<name>.so)
+# A/B of libvslam_b200.so build variants on one box.  AB_LIST="name[@ENV=VAL[,ENV=VAL]] ..." ; libs in build/ab/lib_<name>.so
 mkdir -p gpurun_out
-for n in ${AB_LIST:-base T G W TG TGW base TGW}; do
-  VSLAM_B200_LIB=$PWD/build/ab/lib_$n.so timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --parity-frames 64 > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err
-  python - "$n" <<'PY'
+for item in ${AB_LIST}; do
+  n=${item%%@*}; e=""; [ "$item" != "$n" ] && e=$(echo "${item#*@}" | tr ',' ' ')
+  tag=$(echo "$item" | tr '@=,' '___')
+  env $e VSLAM_B200_LIB=$PWD/build/ab/lib_$n.so timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --parity-frames 64 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  python - "$tag" <<'PY'
 import json,sys
 n=sys.argv[1]
 try:
