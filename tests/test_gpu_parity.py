@@ -880,12 +880,18 @@ def test_two_handles_two_threads(oracle, pairs, camera_dict):
         except Exception as e:  # noqa: BLE001
             errors.append(e)
 
-    th = [threading.Thread(target=work, args=(k, *j)) for k, j in enumerate(jobs)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
-    assert not errors, errors
-    for k, (w, h, nfeat, frames) in enumerate(jobs):
-        for fr, (l, r) in zip(results[k], frames):
-            check_frame(fr, oracle.detect_and_compute(l, nfeat), oracle.detect_and_compute(r, nfeat), oracle, camera_dict)
+    refs = [[(oracle.detect_and_compute(l, nfeat), oracle.detect_and_compute(r, nfeat)) for l, r in frames]
+            for _, _, nfeat, frames in jobs]
+    # several rounds: handle creation in one thread overlaps the other thread's first vslam_process (which captures the
+    # handle's CUDA graph) only now and then - a device-wide synchronisation in vslam_create used to fail 1 time in 12
+    for _ in range(10):
+        results.clear()
+        th = [threading.Thread(target=work, args=(k, *j)) for k, j in enumerate(jobs)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors
+        for k in range(len(jobs)):
+            for fr, (ref_l, ref_r) in zip(results[k], refs[k]):
+                check_frame(fr, ref_l, ref_r, oracle, camera_dict)
