@@ -838,7 +838,7 @@ def main():
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "note": ("k_fast is bound by the integer ALU pipe and instruction issue (ncu, profiles/r02_summary.md: ALU pipe "
-                 "63 %, issue 59 %, DRAM 5 %), not by HBM; the HBM fraction is reported because SURVEY.md 8(d) defines "
+                 "66 %, issue 68 %, DRAM 6 %), not by HBM; the HBM fraction is reported because SURVEY.md 8(d) defines "
                  "the roofline in algorithmic bytes"),
         "algorithmic_bytes_per_launch": alg[dom] * images_per_launch, "launch_ms": round(per_launch_ms, 4),
         "stage_ms_per_step": {names[i]: round(float(stage[i]), 3) for i in range(6)}, "stage_share": shares,
