@@ -290,6 +290,34 @@ class CpuReference:
             pass
 
 
+def euroc_config(args, world):
+    """The `config` of the headline workload: a pure function of the command line, so the reference arm (same flags, CPU
+    implementation) prints the very dict this arm prints."""
+    strong = args.total_frames > 0
+    n = -(-args.total_frames // world) if strong else args.frames
+    frames_all = args.total_frames if strong else n * world
+    img_bytes = W * H
+    return {"workload": (f"configs[4]: {frames_all} synthetic {W}x{H} stereo frames in total, frame-sharded over "
+                         f"{world} GPU(s), {NFEAT} features, 8 levels, scale 1.2: ORB extract x2 + stereo match + "
+                         "triangulate" if strong else
+                         f"{CONFIG_NAME}: batch of {n} synthetic {W}x{H} stereo frames per GPU, {NFEAT} features, "
+                         "8 levels, scale 1.2: ORB extract x2 + stereo match + triangulate"),
+            "frames_per_gpu_per_step": n, "frames_all_gpus_per_step": frames_all, "distinct_frames": args.unique or n,
+            "chunk": args.batch,
+            "cache": f"inputs larger than L2 ({2 * n * img_bytes / 1e9:.2f} GB per step vs 126 MB L2); no flush needed",
+            "sharding": "independent frames per rank, no collective"}
+
+
+def tracking_config(args, world):
+    T = args.seq_frames
+    return {"workload": f"configs[3]: synthetic {W}x{H} sequence of {T} stereo frames per replica (camera "
+                        f"translated {TRACK_STEP_PX} px/frame), {NFEAT} features; per frame: ORB x2 + stereo match "
+                        f"+ triangulate + FeatureGrid + local-map search (map points = the triangulated points of frame 0) + "
+                        f"motion-model search + ref-KF BFMatcher every {TRACK_BF_EVERY}th frame",
+            "sharding": "replicas only (tracking is sequential across frames)",
+            "cache": "a step walks 2 x 86 MB of distinct images; every frame is new to L2"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -317,7 +345,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{CONFIG_NAME}: batch of synthetic {W}x{H} stereo frames, {NFEAT} features, 8 levels, scale 1.2"},
+        "config": euroc_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
                          "cpu_model": cpu_model_string(), "single_process": single},
         "e2e": {"value": round(value, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -419,7 +447,7 @@ def run_tracking(args, rank, local_rank, world):
         emit({"impl": "reference", "metric": TRACK_METRIC, "value": round(v, 2), "unit": "frames/s", "n_gpus": args.gpus,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / max(args.steps, 1), 3),
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-              "config": {"workload": f"configs[3]: synthetic {W}x{H} sequence, {NFEAT} features, tracking front end"},
+              "config": tracking_config(args, max(args.gpus, 1)),
               "cpu_baseline": {"value": round(v, 2), "unit": "frames/s", "cores": 1, "kind": "port",
                                "sample": f"{frames} sequence frames, single process, cv2 cv::ORB + restated Rust loops",
                                "cpu_model": cpu_model_string()},
@@ -551,12 +579,7 @@ def run_tracking(args, rank, local_rank, world):
         emit({"metric": TRACK_METRIC, "value": round(frames_all / dev_wall, 1), "unit": "frames/s", "n_gpus": world,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dev_wall / args.steps, 3),
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-              "config": {"workload": f"configs[3]: synthetic {W}x{H} sequence of {T} stereo frames per replica (camera "
-                                     f"translated {TRACK_STEP_PX} px/frame), {NFEAT} features; per frame: ORB x2 + stereo match "
-                                     f"+ triangulate + FeatureGrid + local-map search (M={M}) + motion-model search + ref-KF "
-                                     f"BFMatcher every {TRACK_BF_EVERY}th frame",
-                         "sharding": "replicas only (tracking is sequential across frames)", "map_points": int(M),
-                         "cache": "a step walks 2 x 86 MB of distinct images; every frame is new to L2"},
+              "config": tracking_config(args, world), "map_points": int(M),
               "timing": "host wall clock around the sequence loop (every frame ends in a synchronising search), max over ranks",
               "p50_ms_per_frame": round(1e3 * dev_wall / args.steps / (T - 1), 4),
               "e2e": {"value": round(frames_all / e2e_wall, 1), "unit": "frames/s", "h2d_bytes_per_step": (T - 1) * (2 * img_bytes + M * 48 * 2),
@@ -900,15 +923,7 @@ def main():
             "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": (f"configs[4]: {frames_all} synthetic {W}x{H} stereo frames in total, frame-sharded over "
-                                    f"{world} GPU(s), {NFEAT} features, 8 levels, scale 1.2: ORB extract x2 + stereo match + "
-                                    "triangulate" if strong else
-                                    f"{CONFIG_NAME}: batch of {n} synthetic {W}x{H} stereo frames per GPU, {NFEAT} features, "
-                                    "8 levels, scale 1.2: ORB extract x2 + stereo match + triangulate"),
-                       "frames_per_gpu_per_step": n, "frames_all_gpus_per_step": frames_all, "distinct_frames": nuniq,
-                       "chunk": args.batch,
-                       "cache": f"inputs larger than L2 ({2 * n * img_bytes / 1e9:.2f} GB per step vs 126 MB L2); no flush needed",
-                       "sharding": "independent frames per rank, no collective"},
+            "config": euroc_config(args, world),
             "ms_per_step_wall": round(wall_ms / args.steps, 3), "mean_ms_per_frame": round(dev_ms / args.steps / n, 5),
             "p50_ms_per_frame": round(p50_frame_ms, 5),
             "p50_ms_single_pair_latency": round(p50_single, 3),
