@@ -443,14 +443,17 @@ __host__ inline size_t fast_smem_bytes(int pitch) {
 
 // grid = (total_fast_strips, n_img), block = kFastThreads.  One block = one strip of VSLAM_FAST_ROWS emission rows of
 // one level of one image.
-//   staging   the strip's pixel rows (+-4) are copied global -> shared by the bulk-copy engine (cp.async.bulk, one
-//             instruction per row, completion on an mbarrier) while the threads clear the score tile
-//   phase A   every lane owns one group of 4 pixels and walks DOWN the strip with a 7-row window of raw words in
+//   staging   the strip's pixel rows (+-4) are one contiguous range of global memory and keep the global pitch in shared
+//             memory: two cp.async.bulk copies (rows 0-13, the rest) on two mbarriers, issued before anything else; the
+//             threads clear the score tile meanwhile, warp 0 polls the first barrier, one block barrier publishes it
+//   phase A   every lane owns one group of 4 pixels and walks DOWN a 7-row segment with a 7-row window of raw words in
 //             registers (3 LDS per step): byte-SIMD necessary condition on 4 antipodal pairs of the circle; the pixel
-//             pairs that pass are appended to the warp's candidate ring (ballot compaction)
+//             pairs that pass are appended to the warp's candidate ring (ballot compaction).  Work items = 32
+//             consecutive columns of the segment-major (segment, group) list, handed out dynamically; a warp polls the
+//             second staging barrier before its first item that reaches into a later segment
 //   phase B   whenever the ring holds >= 32 pairs (and once at the end) 32 lanes score 32 pairs exactly (DPX);
 //             non-zero scores go to the score tile and to the warp's pre-NMS corner list
-//   NMS       sparse, over the corner lists (full scan if a list overflowed), into a bitmask
+//   NMS       sparse, every warp over its own corner list (full scan if a list overflowed), into a bitmask
 //   emission  popcount scan of the bitmask -> raster-ordered records (== cv::FAST's output order), no atomics, no sort
 __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __grid_constant__ PyrP P, const uint8_t* __restrict__ in_l,
                                                        const uint8_t* __restrict__ in_r,
@@ -485,10 +488,10 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   int* s_rowcnt = s_next + 1;                                // [VSLAM_FAST_ROWS] NMS survivors per emission row                               // dynamic work-item counter of phase A
   const unsigned mbar = sbase + (unsigned)o_misc;  // two mbarriers: tile rows [0, n0) and [n0, rows + 8)
 
-  // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4)
-  // warp 0 owns the mbarrier: it initialises it, issues the copies at once and is the only poller; the block barrier
-  // behind the poll publishes the tile (and the cleared score tile) to the other warps
-  // two copies: the first 14 rows (all that segment 0 of phase A reads) complete on mbarrier 0, the rest on mbarrier 1
+  // ---- staging: bulk copies of the rows ys-4 .. ye+3 (always inside the image: ey0 >= 4, ey1 <= h - 4).  Two copies:
+  // the first 14 rows (all that segment 0 of phase A reads) complete on mbarrier 0, the rest on mbarrier 1.  Thread 0
+  // initialises both barriers and issues both copies at once; warp 0 is the only poller of barrier 0, the block barrier
+  // behind its poll publishes the rows (and the cleared score tile, and the barriers' initialisation) to the other warps.
   const int n0 = min(2 * kFastSeg, rows + 8), n1 = rows + 8 - n0;
   if (tid == 0) {
     *s_next = 0;
@@ -514,8 +517,8 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
     reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
   if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
-  if (warp == 0)
-  {
+  if (warp == 0) {
+    __syncwarp();  // lanes 1..31 must not look at the barrier before lane 0 has initialised it
     unsigned done = 0;
     while (!done)
       asm volatile(
