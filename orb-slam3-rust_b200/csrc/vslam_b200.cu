@@ -176,11 +176,13 @@ struct vslam_handle_s {
   // 16 BRIEF, 32 match.  The drop in step time is that stage's marginal cost inside the 4-slot pipeline.
   int debug_skip = 0;
   uint64_t chunks_run = 0;
-  // VSLAM_BRIEF_TMA=1: BRIEF / orientation patches through TMA tensor-tile loads (k_brief_tma) instead of per-lane
-  // cp.async (k_brief).  Measured on B200 (profiles/r02_summary.md): the TMA kernel is 14 % faster alone (4.12 vs 4.79 ms
-  // per 2000 frames) but 1 % slower inside the 4-slot pipeline (87.1k vs 88.0k frames/s: larger shared-memory footprint,
-  // and it shares the bulk-copy engine with k_fast's row staging), so the cp.async kernel stays the default.
-  bool brief_tma = false;
+  // BRIEF / orientation patches through TMA tensor-tile loads (k_brief_tma); VSLAM_BRIEF_TMA=0 selects the per-lane
+  // cp.async kernel (k_brief), which is also the fallback when the driver has no cuTensorMapEncodeTiled.  Measured on
+  // B200 (profiles/r02_summary.md): mid-round the TMA kernel was 14 % faster alone (4.12 vs 4.79 ms per 2000 frames) but
+  // 1 % slower inside the 4-slot pipeline (its 16 KB of shared memory per block against 11 KB cost it two of sixteen
+  // blocks per SM); since the packed-steering build both kernels hold 12 blocks per SM by registers and the TMA kernel
+  // wins in the pipeline too (95.8k vs 95.3k frames/s, two A/B pairs on one box).
+  bool brief_tma = true;
   bool select_fused = true;  // VSLAM_SELECT_FUSED=0: the three-kernel selection chain (k_select1, k_harris, k_select2)
   bool resize_tile = true;   // VSLAM_RESIZE_TILE=0 selects the per-lane cp.async ring kernel (k_resize)
   int rtile_rows = 16;       // VSLAM_RTILE_ROWS

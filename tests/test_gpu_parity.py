@@ -769,12 +769,14 @@ def test_natural_images(name, oracle, cv2mod, camera_dict):
         assert np.array_equal(fr.points_cam, ref["points"]) and np.array_equal(fr.points_valid, ref["points_valid"])
 
 
-def test_brief_tma_variant_is_bit_identical(oracle, pairs, camera_dict, monkeypatch):
-    """k_brief_tma (patches staged by cp.async.bulk.tensor tile loads) is kept as a measured alternative to k_brief
-    (VSLAM_BRIEF_TMA=1): same bits, including keypoints whose 16-byte aligned boxes hang over the right image edge."""
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_brief_kernel_variants_are_bit_identical(oracle, pairs, camera_dict, monkeypatch, tma):
+    """k_brief_tma (patches staged by cp.async.bulk.tensor tile loads, the default) and k_brief (per-lane cp.async,
+    VSLAM_BRIEF_TMA=0, also the fallback without a tensor-map encoder): same bits, including keypoints whose 16-byte
+    aligned boxes hang over the right image edge."""
     from vslam_b200 import CameraModel, StereoProcessor
 
-    monkeypatch.setenv("VSLAM_BRIEF_TMA", "1")
+    monkeypatch.setenv("VSLAM_BRIEF_TMA", tma)
     for (w, h, seed) in ((752, 480, 4), (640, 427, 9)):
         l, r = pairs(seed, w, h)
         with StereoProcessor(CameraModel(**camera_dict), 1200, w, h, max_batch=2) as sp:
