@@ -517,17 +517,23 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
   for (int i = tid; i < (VSLAM_FAST_ROWS * BW + 3) >> 2; i += kFastThreads)  // 128-bit stores; the region is padded
     reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
   if (tid < VSLAM_FAST_ROWS) s_rowcnt[tid] = 0;
-  if (warp == 0) {
-    __syncwarp();  // lanes 1..31 must not look at the barrier before lane 0 has initialised it
+  auto wait_rows = [&](unsigned bar) {  // acquire the rows whose copy completes on this mbarrier
     unsigned done = 0;
     while (!done)
       asm volatile(
           "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
           : "=r"(done)
-          : "r"(mbar)
+          : "r"(bar)
           : "memory");
+  };
+  if (warp == 0) {
+    __syncwarp();  // lanes 1..31 must not look at the barrier before lane 0 has initialised it
+    wait_rows(mbar);
   }
   __syncthreads();
+  // the other warps observe the (by now completed) phase themselves: one try_wait that succeeds at once, so that every
+  // thread that reads the bulk-copied rows has acquired them through the mbarrier, not only through the block barrier
+  if (warp != 0) wait_rows(mbar);
 
   // ---- scores on the emission region dilated by one pixel (always inside FAST's own 3-px border because ex0 >= 4).
   // Phase A: a 9-arc of the 16-circle contains at least one point of every antipodal pair {k, k+8}, so
@@ -611,13 +617,7 @@ __global__ void __launch_bounds__(kFastThreads, VSLAM_FAST_MINB) k_fast(const __
     const int g = gx0 + gi;
     const int seg_hi = (int)__umulhi((unsigned)min(item * 32 + 31, nlin - 1), inv_ngx);
     if (!got1 && seg_hi > 0) {  // segments >= 1 read tile rows >= 14
-      unsigned done = 0;
-      while (!done)
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(mbar + 8u)
-            : "memory");
+      wait_rows(mbar + 8u);
       got1 = true;
     }
     // per-byte mask of the scored columns [sx0, sx1) of this group (only the first / last group is partial)
